@@ -1,0 +1,173 @@
+/*
+ * fq.h -- C ABI of the B200-native fake-quantization hot path (libfq_b200.so).
+ *
+ * Drop-in boundary for hey-yahei/Quantization.MXNet.  The reference has no FFI
+ * of its own for this path: every entry point below replaces a run of MXNet
+ * NDArray ops (or NumPy code) issued from the reference's Python, cited as
+ * <file>:<lines> relative to the reference root.  The only C-ABI convention the
+ * reference uses is libmxnet's (quantize/freeze/freeze.py:32,67-76):
+ * int return code (0 = ok), message from a *GetLastError() call, out-params by
+ * pointer.  This header follows the same convention.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from fq_last_error() (thread local);
+ *   - tensors are borrowed `const DLTensor*` (DLPack), device kDLCUDA,
+ *     compact row-major, lanes == 1; NULL is allowed only where stated;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     nothing here allocates, synchronises the host or changes the device;
+ *   - `ws` is a caller-owned device workspace of fq_workspace_bytes() bytes that
+ *     was zero-filled once with fq_workspace_init(); kernels leave it zeroed.
+ *     One workspace serves one stream at a time;
+ *   - `promotion` selects how the reference's HOST scalar math is replayed:
+ *     FQ_PROMOTION_LEGACY  numpy.float32 (op) python-number -> float64 (NumPy 1.x,
+ *                          what an MXNet 1.x install computes),
+ *     FQ_PROMOTION_NEP50   stays float32 (NumPy >= 2).
+ */
+#ifndef FQ_B200_FQ_H_
+#define FQ_B200_FQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- minimal DLPack (ABI-compatible with dlpack/dlpack.h v0.8 / v1.x) ---- */
+#ifndef DLPACK_DLPACK_H_
+typedef enum { kDLCPU = 1, kDLCUDA = 2, kDLCUDAHost = 3, kDLCUDAManaged = 13 } DLDeviceType;
+typedef struct { int32_t device_type; int32_t device_id; } DLDevice;
+typedef enum { kDLInt = 0, kDLUInt = 1, kDLFloat = 2 } DLDataTypeCode;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } DLDataType;
+typedef struct {
+  void* data;
+  DLDevice device;
+  int32_t ndim;
+  DLDataType dtype;
+  int64_t* shape;
+  int64_t* strides;     /* NULL = compact row-major */
+  uint64_t byte_offset;
+} DLTensor;
+#endif
+
+#if defined(__GNUC__)
+#define FQ_API __attribute__((visibility("default")))
+#else
+#define FQ_API
+#endif
+
+#define FQ_PROMOTION_LEGACY 0
+#define FQ_PROMOTION_NEP50 1
+
+#define FQ_STE_IDENTITY 0   /* ste_func.py:43-44: dx = dy (the reference)          */
+#define FQ_STE_CLIP_MASK 1  /* extension: dx = dy * 1[lo <= x <= hi]               */
+
+#define FQ_LO_ZERO 0        /* unsigned inputs, and ALL Dense inputs (convert_dense.py:49) */
+#define FQ_LO_NEG_MAX 1     /* signed Conv2D inputs (convert_conv2d.py:60)          */
+
+#define FQ_QP_D 0           /* qparams[4] = {divisor d, multiplier s, clip lo, clip hi} */
+#define FQ_QP_S 1
+#define FQ_QP_LO 2
+#define FQ_QP_HI 3
+
+#define FQ_MAX_ROWS 65536   /* rows (samples / channels / groups) a fused kernel accepts */
+
+/* ---- library ---- */
+FQ_API int fq_version(void);
+FQ_API const char* fq_last_error(void);                 /* cf. MXGetLastError, freeze.py:32 */
+FQ_API size_t fq_workspace_bytes(void);
+FQ_API int fq_workspace_init(void* ws, size_t bytes, void* stream);
+FQ_API int fq_sm_count(int* out);
+
+/* ---- K1 range reductions ------------------------------------------------ */
+/* out[r] = max |x[r, :]| for x viewed as [rows, numel/rows].
+ * convert_conv2d.py:56 (rows=N), :75 (Cout), :86 (G), :92 (1); convert_dense.py:41,54,60;
+ * nn/quantized_conv.py:65. */
+FQ_API int fq_absmax_rows(const DLTensor* x, int64_t rows, const DLTensor* out, void* ws, void* stream);
+/* out2 = {min x, max x}.  nn/quantized_conv.py:68-69; distribution_calibrate.py:34-35. */
+FQ_API int fq_minmax(const DLTensor* x, const DLTensor* out2, void* ws, void* stream);
+/* out[0] = MXNet CPU mean: sequential Kahan fp32 sum / fp32(n).  convert_conv2d.py:56 `.mean()`. */
+FQ_API int fq_mean_kahan(const DLTensor* v, const DLTensor* out, void* stream);
+/* cur_max[0] = mean_n max_chw |x| in ONE launch; per_sample (NULL or [n_samples]) receives the maxima.
+ * convert_conv2d.py:56; convert_dense.py:41. */
+FQ_API int fq_input_range(const DLTensor* x, int64_t n_samples, const DLTensor* per_sample,
+                   const DLTensor* cur_max, void* ws, void* stream);
+/* qparams[4] from a device-resident max_: the host scalar math of
+ * convert_conv2d.py:57-64 / convert_dense.py:42-47 + ste_func.py:41 without the .asscalar() sync. */
+FQ_API int fq_scale_from_max(const DLTensor* max_, int bits, int is_signed, int lo_mode, int promotion,
+                      const DLTensor* qparams, void* stream);
+
+/* ---- K2 fake-quant forward ---------------------------------------------- */
+/* y = roundf(clip(x, lo, hi) / d) * s, qparams on the device.  ste_func.py:41.
+ * codes: NULL, or int8/uint8/int16/uint16/int32/float32 tensor receiving the rounded quotient. */
+FQ_API int fq_forward_scalar(const DLTensor* x, const DLTensor* qparams, const DLTensor* y,
+                      const DLTensor* codes, void* stream);
+/* Same with host scalars (LinearQuantizeSTE called with Python floats). use_clip=0 -> ste_func.py:39. */
+FQ_API int fq_forward_scalar_host(const DLTensor* x, float d, float s, float lo, float hi, int use_clip,
+                           const DLTensor* y, const DLTensor* codes, void* stream);
+/* y[r,:] = roundf(x[r,:] / (scale[r] + 1e-10f)) * scale[r].  ste_func.py:39 with an NDArray scale
+ * (convert_conv2d.py:77-79, 88-90, 93-95; convert_dense.py:56-58, 61-63). */
+FQ_API int fq_forward_rows(const DLTensor* x, int64_t rows, const DLTensor* scale, const DLTensor* y,
+                    const DLTensor* codes, void* stream);
+/* Online input path in ONE cooperative launch: per-sample absmax -> Kahan mean -> scale -> quantise,
+ * the second pass walking each block's slice backwards so it re-reads from L2.
+ * convert_conv2d.py:56-66 / convert_dense.py:41-49.  cur_max[0] and qparams[4] are written.
+ * input_max != NULL selects the offline range (`input_max.asscalar()`, :58) while cur_max is still tracked;
+ * y == NULL tracks the range only (quantize_input disabled, :55-57). */
+FQ_API int fq_forward_online(const DLTensor* x, int64_t n_samples, int bits, int is_signed, int lo_mode,
+                      int promotion, const DLTensor* input_max, const DLTensor* y, const DLTensor* codes,
+                      const DLTensor* cur_max, const DLTensor* qparams, const DLTensor* per_sample,
+                      void* ws, void* stream);
+/* Weight path in ONE cooperative launch: optional BN fold -> per-row absmax -> scale -> quantise.
+ * rows in {1 (layer), G (group), Cout (channel)}; bits <= 0 folds only (merge_bn.py:65-74).
+ * gamma/beta/mean/var all NULL = no fold; bias may be NULL (treated as zeros, initialize.py:65-70).
+ * convert_conv2d.py:47-51, 70-95; convert_dense.py:52-63. */
+FQ_API int fq_quant_weight(const DLTensor* w, int64_t rows, int bits, const DLTensor* gamma, const DLTensor* beta,
+                    const DLTensor* mean, const DLTensor* var, const DLTensor* bias, const DLTensor* w_out,
+                    const DLTensor* bias_out, const DLTensor* scale_out, const DLTensor* codes,
+                    void* ws, void* stream);
+
+/* ---- K3 straight-through estimator backward ----------------------------- */
+FQ_API int fq_ste_backward(const DLTensor* dy, const DLTensor* x, const DLTensor* qparams, const DLTensor* dx,
+                    int mode, void* stream);
+
+/* ---- K4 EMA   convert.py:66-78 ------------------------------------------ */
+/* scalar_cur != 0: `cur` plays the host numpy.float32 of convert.py:70 (promotion applies);
+ * scalar_cur == 0: `cur` is an NDArray (running_mean / running_var, convert.py:75-78). */
+FQ_API int fq_ema_update(const DLTensor* state, const DLTensor* cur, double momentum, int scalar_cur,
+                  int promotion, void* stream);
+
+/* ---- K5 KL calibration   quantize/distribution_calibrate.py ------------- */
+/* counts[bin] += 1 for every clipped non-zero element; counts is uint64/int64 [bins+1].  :39-45 */
+FQ_API int fq_hist_nonzero(const DLTensor* x, const DLTensor* max_, int bins, int promotion,
+                    const DLTensor* counts, void* stream);
+/* hist = (first ? 0 : hist) + float32(counts); counts <- 0; seen_last[0] |= counts[bins] != 0.  :47,103-104 */
+FQ_API int fq_hist_accumulate_f32(const DLTensor* counts, const DLTensor* hist, int first,
+                           const DLTensor* seen_last, void* stream);
+/* best[l] = first strict arg-min of the KL divergence over i in [min_bins, bins).  :117-171
+ * hist: float32 [n_data] or [layers, n_data] with n_data in {bins, bins+1}; best: int32 [layers];
+ * divergence: caller-provided float64 [layers, bins] scratch that receives D_i (entries below
+ * min_bins are left untouched). */
+FQ_API int fq_kl_search(const DLTensor* hist, int levels, int min_bins, int bins, int promotion,
+                 const DLTensor* best, const DLTensor* divergence, void* stream);
+/* input_max[0] = (best + 0.5) * (fm_max / bins).  examples/simulate_quantization.py:310,314 */
+FQ_API int fq_kl_threshold(const DLTensor* best, const DLTensor* fm_max, int bins, const DLTensor* input_max,
+                    void* stream);
+
+/* ---- K6 integer export -------------------------------------------------- */
+/* MXNet contrib.quantize(out_type="int8"), zero centred.  freeze.py:100-103.
+ * range2 = {min_range, max_range} on the device; out_range2 receives {-real, +real}. */
+FQ_API int fq_quantize_int8_export(const DLTensor* w, const DLTensor* range2, const DLTensor* out_i8,
+                            const DLTensor* out_range2, void* stream);
+/* nn/quantized_conv.py:54-61: int32 codes + scale_out[0]; range2 = {min, max} on the device. */
+FQ_API int fq_qconv_quantize(const DLTensor* x, const DLTensor* range2, const DLTensor* codes_i32,
+                      const DLTensor* scale_out, void* stream);
+/* nn/quantized_conv.py:74-76: y = float(acc) * (s_in * s_w). */
+FQ_API int fq_qconv_dequantize(const DLTensor* acc_i32, const DLTensor* s_in, const DLTensor* s_w,
+                        const DLTensor* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FQ_B200_FQ_H_ */

@@ -1,0 +1,320 @@
+// K4/K5: on-device EMA, shared-memory-privatised |x| histograms, block-per-candidate KL search.
+//   reference: quantize/convert/convert.py:66-78; quantize/distribution_calibrate.py:31-47,117-171;
+//              examples/simulate_quantization.py:310
+#include "fq_fused.cuh"
+
+namespace fq {
+
+// ---------------------------------------------------------------------------------------------
+// EMA
+// ---------------------------------------------------------------------------------------------
+__global__ void ema_kernel(float* __restrict__ state, const float* __restrict__ cur, int64_t n, double one_minus_m,
+                           float m32, int scalar_cur, int promotion) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float t;
+    if (scalar_cur && promotion == FQ_PROMOTION_LEGACY)
+      t = (float)(one_minus_m * (double)cur[i]);            // python float * numpy.float32 -> float64
+    else
+      t = __fmul_rn((float)one_minus_m, cur[i]);            // NEP 50 scalar, or _mul_scalar on an NDArray
+    state[i] = __fadd_rn(__fmul_rn(m32, state[i]), t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// histogram of the clipped non-zero values
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) hist_kernel(const float* __restrict__ x, int64_t n, int64_t per_block,
+                                                        const float* __restrict__ max_dev, int bins, int promotion,
+                                                        unsigned long long* __restrict__ counts, int vectorised) {
+  extern __shared__ unsigned int sh[];     // bins + 1 private counters
+  for (int b = threadIdx.x; b <= bins; b += blockDim.x) sh[b] = 0u;
+  const float max_ = __ldg(max_dev);
+  // scales = bins / (max_ + 1e-5)      distribution_calibrate.py:41
+  const float sc = (promotion == FQ_PROMOTION_LEGACY) ? (float)((double)bins / ((double)max_ + 1e-5))
+                                                      : __fdiv_rn((float)bins, __fadd_rn(max_, 1e-5f));
+  __syncthreads();
+  auto one = [&](float v) {
+    v = fminf(fmaxf(v, 0.f), max_);                         // ndarray.clip(0, max_)
+    if (v != 0.f) {                                          // zeros are ignored (:40)
+      const int b = (int)__fmul_rn(v, sc);                   // astype(int32): truncation
+      if (b >= 0 && b <= bins) atomicAdd(&sh[b], 1u);
+    }
+  };
+  if (vectorised) {
+    const int64_t begin = (int64_t)blockIdx.x * per_block;
+    const int64_t end = min(n, begin + per_block);
+    for_range<false, false>(
+        x, begin, end,
+        [&](int64_t, float4 v) {
+          one(v.x);
+          one(v.y);
+          one(v.z);
+          one(v.w);
+        },
+        [&](int64_t, float v) { one(v); });
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) one(x[i]);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b <= bins; b += blockDim.x) {
+    const unsigned int c = sh[b];
+    if (c) atomicAdd(&counts[b], (unsigned long long)c);
+  }
+}
+
+__global__ void hist_accumulate_kernel(unsigned long long* __restrict__ counts, float* __restrict__ hist, int nb,
+                                       int first, int* __restrict__ seen_last) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const unsigned long long c = counts[b];
+  counts[b] = 0ull;
+  const float f = __ull2float_rn(c);                         // hist.astype("float32")  (:47)
+  hist[b] = first ? f : __fadd_rn(hist[b], f);               // last_hist + hist        (:103-104)
+  if (b == nb - 1 && seen_last != nullptr && c != 0ull) seen_last[0] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// KL threshold search: one block per candidate bin count i
+// ---------------------------------------------------------------------------------------------
+template <bool LEGACY>
+__global__ void __launch_bounds__(kThreads) kl_candidate_kernel(const float* __restrict__ hist_all, int n_data,
+                                                                int levels, int min_bins, int bins,
+                                                                double* __restrict__ div_all) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int i = min_bins + blockIdx.x;
+  const float* hist = hist_all + (int64_t)blockIdx.y * n_data;
+  double* div = div_all + (int64_t)blockIdx.y * bins;
+  double* cand = reinterpret_cast<double*>(smem_raw);                 // [levels]
+  double* Q = cand + levels;                                          // [bins]
+  float* H = reinterpret_cast<float*>(Q + bins);                      // [n_data]
+  float* ref = H + ((n_data + 3) & ~3);                               // [bins]
+  __shared__ float s_last, s_total;
+  __shared__ double s_qsum;
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  for (int j = tid; j < n_data; j += nt) H[j] = hist[j];
+  __syncthreads();
+
+  // P: tail mass folded into bin i-1, then normalised.  Python's builtin sum is strictly left to
+  // right; its accumulator is float32 under NEP 50 and float64 under legacy promotion (:143-145).
+  if (tid == 0) {
+    if (LEGACY) {
+      double tail = 0.0;
+      for (int j = i; j < n_data; ++j) tail = __dadd_rn(tail, (double)H[j]);
+      const float last = (float)__dadd_rn((double)H[i - 1], tail);
+      double tot = 0.0;
+      for (int j = 0; j < i - 1; ++j) tot = __dadd_rn(tot, (double)H[j]);
+      tot = __dadd_rn(tot, (double)last);
+      s_last = last;
+      s_total = (float)tot;                  // float32 array /= float64 scalar: the scalar is cast first
+    } else {
+      float tail = 0.f;
+      for (int j = i; j < n_data; ++j) tail = __fadd_rn(tail, H[j]);
+      const float last = __fadd_rn(H[i - 1], tail);
+      float tot = 0.f;
+      for (int j = 0; j < i - 1; ++j) tot = __fadd_rn(tot, H[j]);
+      tot = __fadd_rn(tot, last);
+      s_last = last;
+      s_total = tot;
+    }
+  }
+  // Q buckets: cand[k] = sum of hist[j] with floor(j*levels/i) == k, float64, ascending j (:149-152)
+  for (int k = tid; k < levels; k += nt) {
+    const int j0 = (int)(((long long)k * i + levels - 1) / levels);
+    const int j1 = (int)(((long long)(k + 1) * i + levels - 1) / levels);
+    double c = 0.0;
+    for (int j = j0; j < j1 && j < i; ++j) c = __dadd_rn(c, (double)H[j]);
+    cand[k] = c;
+  }
+  __syncthreads();
+  const float total = s_total, last = s_last;
+  for (int j = tid; j < i; j += nt) {
+    const float p = __fdiv_rn(j == i - 1 ? last : H[j], total);
+    ref[j] = p;
+    // linear interpolation between the neighbouring buckets (:154-158), no FMA contraction
+    const double t = __ddiv_rn((double)((long long)j * levels), (double)i);
+    const int fl = (int)t;
+    int ce = (int)ceil(t);
+    ce = ce > levels - 1 ? levels - 1 : ce;
+    double q = __dadd_rn(__dmul_rn(__dsub_rn(cand[ce], cand[fl]), __dsub_rn(t, (double)fl)), cand[fl]);
+    q = __dmul_rn(q, (p != 0.f) ? 1.0 : 0.0);              // Q *= (P != 0)   (:159)
+    Q[j] = q;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double qs = 0.0;
+    for (int j = 0; j < i; ++j) qs = __dadd_rn(qs, Q[j]);
+    s_qsum = qs;
+  }
+  __syncthreads();
+  const double qsum = s_qsum;
+  for (int j = tid; j < i; j += nt) {
+    const double qn = __ddiv_rn(Q[j], qsum);
+    double term = 0.0;                                       // entries with Q == 0 are dropped (:164-165)
+    if (qn != 0.0) {
+      const double p = (double)ref[j];
+      term = __dmul_rn(p, log(__ddiv_rn(p, qn)));
+    }
+    Q[j] = term;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double d = 0.0;
+    for (int j = 0; j < i; ++j) d = __dadd_rn(d, Q[j]);
+    div[i] = d;
+  }
+}
+
+// first strict minimum, NaN never wins (:167-169)
+__global__ void kl_argmin_kernel(const double* __restrict__ div_all, int min_bins, int bins, int* __restrict__ best) {
+  __shared__ double sv[kThreads];
+  __shared__ int si[kThreads];
+  const double* div = div_all + (int64_t)blockIdx.x * bins;
+  double bv = INFINITY;
+  int bi = min_bins;
+  for (int i = min_bins + threadIdx.x; i < bins; i += blockDim.x) {
+    const double d = div[i];
+    if (d < bv) {
+      bv = d;
+      bi = i;
+    }
+  }
+  sv[threadIdx.x] = bv;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const double ov = sv[threadIdx.x + o];
+      const int oi = si[threadIdx.x + o];
+      if (ov < sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) {
+        sv[threadIdx.x] = ov;
+        si[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) best[blockIdx.x] = (sv[0] < INFINITY) ? si[0] : min_bins;
+}
+
+__global__ void kl_threshold_kernel(const int* __restrict__ best, const float* __restrict__ fm_max, int bins,
+                                    float* __restrict__ input_max, int n) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < n) input_max[l] = (float)(((double)best[l] + 0.5) * ((double)fm_max[l] / (double)bins));
+}
+
+}  // namespace fq
+
+using namespace fq;
+
+extern "C" {
+
+int fq_ema_update(const DLTensor* state_, const DLTensor* cur_, double momentum, int scalar_cur, int promotion,
+                  void* stream) {
+  View state, cur;
+  FQ_TRY(view_of(state_, "fq_ema_update: state", false, &state));
+  FQ_TRY(view_of(cur_, "fq_ema_update: cur", false, &cur));
+  FQ_REQUIRE(state.is_f32() && cur.is_f32() && state.numel == cur.numel, "fq_ema_update: float32 tensors of equal size");
+  FQ_REQUIRE(promotion == FQ_PROMOTION_LEGACY || promotion == FQ_PROMOTION_NEP50, "fq_ema_update: bad promotion");
+  if (state.numel == 0) return 0;
+  const int grid = (int)((state.numel + 255) / 256 > 1184 ? 1184 : (state.numel + 255) / 256);
+  ema_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(state.as<float>(), cur.as<const float>(), state.numel,
+                                                     1 - momentum, (float)momentum, scalar_cur, promotion);
+  FQ_LAUNCH_CHECK("ema_kernel");
+  return 0;
+}
+
+int fq_hist_nonzero(const DLTensor* x_, const DLTensor* max__, int bins, int promotion, const DLTensor* counts_,
+                    void* stream) {
+  View x, mx, counts;
+  FQ_TRY(view_of(x_, "fq_hist_nonzero: x", false, &x));
+  FQ_TRY(view_of(max__, "fq_hist_nonzero: max_", false, &mx));
+  FQ_TRY(view_of(counts_, "fq_hist_nonzero: counts", false, &counts));
+  FQ_REQUIRE(x.is_f32() && mx.is_f32() && mx.numel >= 1, "fq_hist_nonzero: x and max_ must be float32");
+  FQ_REQUIRE(bins >= 1 && bins <= 8192, "fq_hist_nonzero: bins=%d outside [1, 8192]", bins);
+  FQ_REQUIRE((counts.code == kDLInt || counts.code == kDLUInt) && counts.bits == 64 && counts.numel == bins + 1,
+             "fq_hist_nonzero: counts must be (u)int64 [bins+1]");
+  FQ_REQUIRE(promotion == FQ_PROMOTION_LEGACY || promotion == FQ_PROMOTION_NEP50, "fq_hist_nonzero: bad promotion");
+  if (x.numel == 0) return 0;
+  const int vec = aligned16(x.data);
+  int64_t per_block = 0;
+  int grid;
+  if (vec) {
+    grid = slice_grid(x.numel, sm_count() * 8, &per_block);
+  } else {
+    const int64_t b = (x.numel + kThreads - 1) / kThreads;
+    grid = (int)(b > sm_count() * 8 ? sm_count() * 8 : b);
+  }
+  hist_kernel<<<grid, kThreads, sizeof(unsigned int) * (bins + 1), (cudaStream_t)stream>>>(
+      x.as<const float>(), x.numel, per_block, mx.as<const float>(), bins, promotion,
+      counts.as<unsigned long long>(), vec);
+  FQ_LAUNCH_CHECK("hist_kernel");
+  return 0;
+}
+
+int fq_hist_accumulate_f32(const DLTensor* counts_, const DLTensor* hist_, int first, const DLTensor* seen_last_,
+                           void* stream) {
+  View counts, hist, seen;
+  FQ_TRY(view_of(counts_, "fq_hist_accumulate_f32: counts", false, &counts));
+  FQ_TRY(view_of(hist_, "fq_hist_accumulate_f32: hist", false, &hist));
+  FQ_TRY(view_of(seen_last_, "fq_hist_accumulate_f32: seen_last", true, &seen));
+  FQ_REQUIRE((counts.code == kDLInt || counts.code == kDLUInt) && counts.bits == 64, "fq_hist_accumulate_f32: counts must be (u)int64");
+  FQ_REQUIRE(hist.is_f32() && hist.numel == counts.numel && hist.numel > 0, "fq_hist_accumulate_f32: hist must be float32 like counts");
+  FQ_REQUIRE(seen.null || (seen.code == kDLInt && seen.bits == 32 && seen.numel >= 1), "fq_hist_accumulate_f32: seen_last must be int32");
+  const int nb = (int)counts.numel;
+  hist_accumulate_kernel<<<(nb + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      counts.as<unsigned long long>(), hist.as<float>(), nb, first, seen.null ? nullptr : seen.as<int>());
+  FQ_LAUNCH_CHECK("hist_accumulate_kernel");
+  return 0;
+}
+
+int fq_kl_search(const DLTensor* hist_, int levels, int min_bins, int bins, int promotion, const DLTensor* best_,
+                 const DLTensor* divergence_, void* stream) {
+  const char* who = "fq_kl_search";
+  View hist, best, dv;
+  FQ_TRY(view_of(hist_, "fq_kl_search: hist", false, &hist));
+  FQ_TRY(view_of(best_, "fq_kl_search: best", false, &best));
+  FQ_TRY(view_of(divergence_, "fq_kl_search: divergence", false, &dv));
+  FQ_REQUIRE(hist.is_f32() && hist_->ndim >= 1, "%s: hist must be float32 [n_data] or [layers, n_data]", who);
+  const int n_data = (int)hist_->shape[hist_->ndim - 1];
+  const int layers = n_data > 0 ? (int)(hist.numel / n_data) : 0;
+  // the reference asserts min_bins >= levels (:133)
+  FQ_REQUIRE(levels >= 1 && min_bins >= levels, "%s: min_bins should be greater than levels (%d vs. %d)", who, min_bins, levels);
+  FQ_REQUIRE(bins <= 8192 && n_data >= bins && n_data <= bins + 1, "%s: hist length %d must be bins or bins+1 (bins=%d)", who,
+             n_data, bins);
+  FQ_REQUIRE(best.code == kDLInt && best.bits == 32 && best.numel == layers, "%s: best must be int32 [layers=%d]", who, layers);
+  FQ_REQUIRE(dv.code == kDLFloat && dv.bits == 64 && dv.numel == (int64_t)layers * bins,
+             "%s: divergence must be float64 [layers, bins] scratch", who);
+  FQ_REQUIRE(promotion == FQ_PROMOTION_LEGACY || promotion == FQ_PROMOTION_NEP50, "%s: bad promotion", who);
+  if (layers == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ncand = bins - min_bins;
+  if (ncand > 0) {
+    const size_t smem = sizeof(double) * (levels + bins) + sizeof(float) * (((n_data + 3) & ~3) + bins);
+    auto kern = (promotion == FQ_PROMOTION_LEGACY) ? kl_candidate_kernel<true> : kl_candidate_kernel<false>;
+    FQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(ncand, layers), kThreads, smem, st>>>(hist.as<const float>(), n_data, levels, min_bins, bins,
+                                                      dv.as<double>());
+    FQ_LAUNCH_CHECK("kl_candidate_kernel");
+  }
+  kl_argmin_kernel<<<layers, kThreads, 0, st>>>(dv.as<const double>(), min_bins, bins, best.as<int>());
+  FQ_LAUNCH_CHECK("kl_argmin_kernel");
+  return 0;
+}
+
+int fq_kl_threshold(const DLTensor* best_, const DLTensor* fm_max_, int bins, const DLTensor* input_max_,
+                    void* stream) {
+  View best, mx, im;
+  FQ_TRY(view_of(best_, "fq_kl_threshold: best", false, &best));
+  FQ_TRY(view_of(fm_max_, "fq_kl_threshold: fm_max", false, &mx));
+  FQ_TRY(view_of(input_max_, "fq_kl_threshold: input_max", false, &im));
+  FQ_REQUIRE(best.code == kDLInt && best.bits == 32 && mx.is_f32() && im.is_f32(), "fq_kl_threshold: best int32, fm_max/input_max float32");
+  FQ_REQUIRE(best.numel == mx.numel && best.numel == im.numel && best.numel > 0, "fq_kl_threshold: sizes differ");
+  FQ_REQUIRE(bins >= 1, "fq_kl_threshold: bins must be positive");
+  const int n = (int)best.numel;
+  kl_threshold_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(best.as<const int>(), mx.as<const float>(), bins,
+                                                                        im.as<float>(), n);
+  FQ_LAUNCH_CHECK("kl_threshold_kernel");
+  return 0;
+}
+
+}  // extern "C"

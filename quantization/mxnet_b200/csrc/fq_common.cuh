@@ -1,0 +1,204 @@
+// Shared device/host helpers for libfq_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "fq.h"
+
+namespace fq {
+
+// ---------------------------------------------------------------------------
+// host side: errors, tensor views, device properties
+// ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int sm_count();                      // SMs of the current device (148 on B200)
+
+struct View {
+  void* data = nullptr;
+  int64_t numel = 0;
+  int code = 0, bits = 0;
+  bool null = true;
+  template <class T> T* as() const { return reinterpret_cast<T*>(data); }
+  bool is_f32() const { return code == kDLFloat && bits == 32; }
+};
+// Validates a borrowed DLTensor (CUDA device, lanes 1, compact).  Returns false + sets the error.
+bool view_of(const DLTensor* t, const char* name, bool allow_null, View* out);
+
+#define FQ_TRY(expr)                 \
+  do {                               \
+    if (!(expr)) return -1;          \
+  } while (0)
+#define FQ_REQUIRE(cond, ...)        \
+  do {                               \
+    if (!(cond)) {                   \
+      ::fq::set_error(__VA_ARGS__);  \
+      return -1;                     \
+    }                                \
+  } while (0)
+#define FQ_CUDA(call)                                                            \
+  do {                                                                           \
+    cudaError_t e__ = (call);                                                    \
+    if (e__ != cudaSuccess) {                                                    \
+      ::fq::set_error("%s failed: %s", #call, cudaGetErrorString(e__));          \
+      return -1;                                                                 \
+    }                                                                            \
+  } while (0)
+#define FQ_LAUNCH_CHECK(name)                                                    \
+  do {                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                        \
+    if (e__ != cudaSuccess) {                                                    \
+      ::fq::set_error("launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+      return -1;                                                                 \
+    }                                                                            \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// workspace layout (device memory, zero-filled once; kernels restore the zeros)
+// ---------------------------------------------------------------------------
+struct Workspace {
+  unsigned int ticket;          // "last block done" counter
+  unsigned int ticket2;
+  unsigned int bar_count;       // grid barrier
+  unsigned int bar_gen;         // monotonically increasing generation (never reset)
+  unsigned int pad[28];
+  unsigned int rowmax[FQ_MAX_ROWS];   // |x| bit patterns, atomicMax target
+  float minmax_part[2 * 4096];        // per-block partials of fq_minmax
+};
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;            // independent 16 B loads in flight per thread
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+// keeps the line in L2 with normal priority (first pass of a two-pass kernel)
+__device__ __forceinline__ float4 ld_keep(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// mshadow_op::round == roundf (half away from zero); rintf + tie fix-up, branch free.
+__device__ __forceinline__ float round_half_away(float q) {
+  float r = rintf(q);                              // half to even
+  float diff = __fsub_rn(q, r);                    // exact
+  // a tie that went towards zero has diff == +-0.5 with the sign of q
+  if (fabsf(diff) == 0.5f && (diff > 0.f) == (q > 0.f)) r = __fadd_rn(r, copysignf(1.0f, q));
+  return r;
+}
+
+// mshadow_op::clip: x > hi -> hi ; x < lo -> lo ; else x  (NaN passes through)
+__device__ __forceinline__ float clipf(float x, float lo, float hi) {
+  return x > hi ? hi : (x < lo ? lo : x);
+}
+
+// clip -> IEEE divide -> roundf.  Returns the integer-valued "code".
+__device__ __forceinline__ float quant_code(float x, float d) {
+  return round_half_away(__fdiv_rn(x, d));
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// max over the block of a non-negative value; valid in thread 0.  `red` = 32 floats of smem.
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();                       // protect `red` from the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.f;
+    v = warp_max(v);
+  }
+  return v;
+}
+
+// Block-cooperative walk over x[begin, end): scalar head up to 16 B alignment, float4 body with
+// kUnroll independent loads in flight, scalar tail.  vf(elem_index, float4), sf(elem_index, float).
+// REVERSE walks the body from the top (second pass of a two-pass kernel: most recently read first).
+template <bool REVERSE, bool KEEP, class VF, class SF>
+__device__ __forceinline__ void for_range(const float* __restrict__ x, int64_t begin, int64_t end, VF vf, SF sf) {
+  const int64_t len = end - begin;
+  if (len <= 0) return;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const float* p = x + begin;
+  int64_t head = (int64_t)(((16u - (unsigned)((uintptr_t)p & 15u)) & 15u) >> 2);
+  if (head > len) head = len;
+  const int64_t nvec = (len - head) >> 2;
+  const int64_t tail0 = head + 4 * nvec;
+  if (tid < head) sf(begin + tid, p[tid]);
+  if (tid < len - tail0) sf(begin + tail0 + tid, p[tail0 + tid]);
+  const float4* p4 = reinterpret_cast<const float4*>(p + head);
+  const int64_t base = begin + head;
+  int64_t i = tid;
+  for (; i + (int64_t)(kUnroll - 1) * nt < nvec; i += (int64_t)kUnroll * nt) {
+    float4 v[kUnroll];
+    int64_t j[kUnroll];
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      j[k] = REVERSE ? (nvec - 1 - (i + (int64_t)k * nt)) : (i + (int64_t)k * nt);
+      v[k] = KEEP ? ld_keep(p4 + j[k]) : ld_stream(p4 + j[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) vf(base + 4 * j[k], v[k]);
+  }
+  for (; i < nvec; i += nt) {
+    const int64_t j = REVERSE ? (nvec - 1 - i) : i;
+    vf(base + 4 * j, KEEP ? ld_keep(p4 + j) : ld_stream(p4 + j));
+  }
+}
+
+// Grid-wide barrier for cooperative (co-resident) launches.  The last arriver runs `fn` (whole block)
+// before releasing the others.  bar_gen only ever grows, bar_count returns to 0.
+template <class FN>
+__device__ __forceinline__ void grid_barrier(Workspace* ws, FN fn) {
+  __shared__ unsigned int s_last, s_gen;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int gen = *((volatile unsigned int*)&ws->bar_gen);
+    __threadfence();
+    unsigned int t = atomicAdd(&ws->bar_count, 1u);
+    s_last = (t == gridDim.x - 1);
+    s_gen = gen;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    fn();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ws->bar_count = 0;
+      __threadfence();
+      atomicAdd(&ws->bar_gen, 1u);
+    }
+  } else if (threadIdx.x == 0) {
+    while (*((volatile unsigned int*)&ws->bar_gen) == s_gen) { __nanosleep(32); }
+    __threadfence();
+  }
+  __syncthreads();
+}
+#endif  // __CUDACC__
+
+}  // namespace fq

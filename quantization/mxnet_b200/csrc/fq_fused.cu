@@ -1,0 +1,489 @@
+// Fused single-launch paths of one converted block.
+//
+//  fq_forward_online : per-sample absmax -> Kahan mean -> scale -> clip/quantise   (inputs)
+//      reference: quantize/convert/convert_conv2d.py:56-66, convert_dense.py:41-49, ste_func.py:41
+//      (abs, max, mean, .asscalar() sync, clip, div, round, mul = 7 passes + a host round trip there;
+//       here: one cooperative launch, 12 B/element worst case, 8 B/element when the tensor fits in L2
+//       because the second pass walks each block's slice backwards.)
+//  fq_quant_weight   : optional BN fold -> per-row absmax -> scale -> quantise      (weights)
+//      reference: convert_conv2d.py:47-51, 70-95; convert_dense.py:52-63; merge_bn.py:65-74
+#include "fq_fused.cuh"
+
+namespace fq {
+
+enum InputMode { kRangeOnly = 0, kOnline = 1, kOfflineTrack = 2 };
+
+struct InputArgs {
+  const float* x;
+  float* y;
+  void* codes;
+  int code_kind;          // 0 none, 1 i8, 2 u8, 3 i16, 4 u16, 5 i32, 6 f32
+  int64_t n, rows, L, per_block;
+  Workspace* ws;
+  FinishParams fin;
+};
+
+__device__ __forceinline__ void put_code1(void* p, int kind, int64_t i, float c) {
+  switch (kind) {
+    case 1: ((signed char*)p)[i] = (signed char)(int)c; break;
+    case 2: ((unsigned char*)p)[i] = (unsigned char)(int)c; break;
+    case 3: ((short*)p)[i] = (short)(int)c; break;
+    case 4: ((unsigned short*)p)[i] = (unsigned short)(int)c; break;
+    case 5: ((int*)p)[i] = (int)c; break;
+    case 6: ((float*)p)[i] = c; break;
+    default: break;
+  }
+}
+__device__ __forceinline__ void put_code4(void* p, int kind, int64_t i, float4 c) {
+  switch (kind) {
+    case 1:
+    case 2:
+      *reinterpret_cast<uchar4*>((unsigned char*)p + i) =
+          make_uchar4((unsigned char)(int)c.x, (unsigned char)(int)c.y, (unsigned char)(int)c.z, (unsigned char)(int)c.w);
+      break;
+    case 3:
+    case 4:
+      *reinterpret_cast<ushort4*>((unsigned short*)p + i) = make_ushort4(
+          (unsigned short)(int)c.x, (unsigned short)(int)c.y, (unsigned short)(int)c.z, (unsigned short)(int)c.w);
+      break;
+    case 5: *reinterpret_cast<int4*>((int*)p + i) = make_int4((int)c.x, (int)c.y, (int)c.z, (int)c.w); break;
+    case 6: *reinterpret_cast<float4*>((float*)p + i) = c; break;
+    default: break;
+  }
+}
+
+template <bool REVERSE>
+__device__ __forceinline__ void quantise_slice(const InputArgs& a, int64_t begin, int64_t end, float d, float s,
+                                               float lo, float hi) {
+  auto one = [&](float v, float& c) {
+    c = quant_code(clipf(v, lo, hi), d);
+    return __fmul_rn(c, s);
+  };
+  for_range<REVERSE, false>(
+      a.x, begin, end,
+      [&](int64_t i, float4 v) {
+        float4 c, o;
+        o.x = one(v.x, c.x);
+        o.y = one(v.y, c.y);
+        o.z = one(v.z, c.z);
+        o.w = one(v.w, c.w);
+        st_stream(reinterpret_cast<float4*>(a.y + i), o);
+        if (a.code_kind) put_code4(a.codes, a.code_kind, i, c);
+      },
+      [&](int64_t i, float v) {
+        float c;
+        a.y[i] = one(v, c);
+        if (a.code_kind) put_code1(a.codes, a.code_kind, i, c);
+      });
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) input_path_kernel(InputArgs a) {
+  __shared__ float red[32];
+  __shared__ unsigned int s_last;
+  const int64_t begin = (int64_t)blockIdx.x * a.per_block;
+  const int64_t end = min(a.n, begin + a.per_block);
+
+  if (MODE == kOfflineTrack) {
+    // the range is tracked for the EMA but the quantiser uses input_max: a single pass, 8 B/element
+    __shared__ float qp[4];
+    if (threadIdx.x == 0)
+      compute_qparams(a.fin.input_max[0], a.fin.bits, a.fin.is_signed, a.fin.lo_mode, a.fin.promotion, qp);
+    __syncthreads();
+    const float d = qp[0], s = qp[1], lo = qp[2], hi = qp[3];
+    if (a.L < 2048) {
+      // short rows: per-warp row maxima first, then the slice is quantised out of L1/L2
+      absmax_segments<true>(a.x, begin, end, a.L, a.ws, red);
+      quantise_slice<true>(a, begin, end, d, s, lo, hi);
+    } else if (begin < end) {
+      // absmax and quantisation share the loads: walk row segments, quantise as we go
+      for (int64_t r = begin / a.L; r * a.L < end; ++r) {
+        const int64_t b0 = max(begin, r * a.L), b1 = min(end, (r + 1) * a.L);
+        float m = 0.f;
+        auto one = [&](float v, float& c) {
+          m = fmaxf(m, fabsf(v));
+          c = quant_code(clipf(v, lo, hi), d);
+          return __fmul_rn(c, s);
+        };
+        for_range<false, false>(
+            a.x, b0, b1,
+            [&](int64_t i, float4 v) {
+              float4 c, o;
+              o.x = one(v.x, c.x);
+              o.y = one(v.y, c.y);
+              o.z = one(v.z, c.z);
+              o.w = one(v.w, c.w);
+              st_stream(reinterpret_cast<float4*>(a.y + i), o);
+              if (a.code_kind) put_code4(a.codes, a.code_kind, i, c);
+            },
+            [&](int64_t i, float v) {
+              float c;
+              a.y[i] = one(v, c);
+              if (a.code_kind) put_code1(a.codes, a.code_kind, i, c);
+            });
+        m = block_max(m, red);
+        if (threadIdx.x == 0) atomicMax(&a.ws->rowmax[r], __float_as_uint(m));
+      }
+    }
+  } else {
+    absmax_segments<MODE == kOnline>(a.x, begin, end, a.L, a.ws, red);
+  }
+
+  if (MODE == kOnline) {
+    grid_barrier(a.ws, [&]() { finish_rows(a.ws, a.rows, a.fin); });
+    const float d = __ldcg(a.fin.qparams + FQ_QP_D), s = __ldcg(a.fin.qparams + FQ_QP_S);
+    const float lo = __ldcg(a.fin.qparams + FQ_QP_LO), hi = __ldcg(a.fin.qparams + FQ_QP_HI);
+    quantise_slice<true>(a, begin, end, d, s, lo, hi);
+  } else {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&a.ws->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    finish_rows(a.ws, a.rows, a.fin);
+    if (threadIdx.x == 0) a.ws->ticket = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------------------------
+struct WeightArgs {
+  const float* w;
+  float* w_out;
+  void* codes;
+  int code_kind;
+  int64_t n, cout, Lc, rows, per_block;   // Lc = elements per output channel; rows = quantisation rows
+  int bits;                               // <= 0: fold only
+  const float *gamma, *beta, *mean, *var, *bias;   // all NULL = no fold
+  float* bias_out;
+  float* scale_out;
+  Workspace* ws;
+};
+
+// per-channel fold factors: W' = (W * gamma) / sqrtf(var + 1e-10)      convert_conv2d.py:50
+__device__ __forceinline__ void fold_factors(const WeightArgs& a, int64_t c, float& g, float& sd) {
+  g = __ldg(a.gamma + c);
+  sd = __fsqrt_rn(__fadd_rn(__ldg(a.var + c), 1e-10f));
+}
+
+template <bool FOLD, class CF, class VF, class SF>
+__device__ __forceinline__ void for_channels(const WeightArgs& a, int64_t begin, int64_t end, CF cf, VF vf, SF sf,
+                                             bool reverse) {
+  // cf(c) -> per-channel context; VF(ctx, i, float4 folded) / SF(ctx, i, float folded).
+  // Channel rows shorter than 2048 elements go one per warp, longer ones to the whole block.
+  if (begin >= end) return;
+  const int64_t c0 = begin / a.Lc, c1 = (end - 1) / a.Lc;
+  if (a.Lc < 2048) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int64_t c = c0 + warp; c <= c1; c += nw) {
+      float g = 1.f, sd = 1.f;
+      if (FOLD) fold_factors(a, c, g, sd);
+      const auto ctx = cf(c);
+      const int64_t lo = max(begin, c * a.Lc), hi = min(end, (c + 1) * a.Lc);
+      for (int64_t i = lo + lane; i < hi; i += 32) {
+        float v = __ldg(a.w + i);
+        if (FOLD) v = __fdiv_rn(__fmul_rn(v, g), sd);
+        sf(ctx, i, v);
+      }
+    }
+  } else {
+    for (int64_t c = c0; c <= c1; ++c) {
+      float g = 1.f, sd = 1.f;
+      if (FOLD) fold_factors(a, c, g, sd);
+      const auto ctx = cf(c);
+      const int64_t lo = max(begin, c * a.Lc), hi = min(end, (c + 1) * a.Lc);
+      auto f1 = [&](float v) { return FOLD ? __fdiv_rn(__fmul_rn(v, g), sd) : v; };
+      auto v4 = [&](int64_t i, float4 v) { vf(ctx, i, make_float4(f1(v.x), f1(v.y), f1(v.z), f1(v.w))); };
+      auto s1 = [&](int64_t i, float v) { sf(ctx, i, f1(v)); };
+      if (reverse)
+        for_range<true, true>(a.w, lo, hi, v4, s1);
+      else
+        for_range<false, true>(a.w, lo, hi, v4, s1);
+    }
+  }
+}
+
+template <bool FOLD>
+__global__ void __launch_bounds__(kThreads) weight_path_kernel(WeightArgs a) {
+  __shared__ float red[32];
+  __shared__ unsigned int s_last;
+  const int64_t begin = (int64_t)blockIdx.x * a.per_block;
+  const int64_t end = min(a.n, begin + a.per_block);
+  const int64_t ch_per_row = a.cout / a.rows;
+
+  // folded bias: b' = ((gamma * (b - mean)) / sqrtf(var + 1e-10)) + beta      convert_conv2d.py:51
+  if (FOLD && a.bias_out != nullptr) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < a.cout; c += (int64_t)gridDim.x * blockDim.x) {
+      const float b = a.bias ? __ldg(a.bias + c) : 0.f;
+      const float sd = __fsqrt_rn(__fadd_rn(__ldg(a.var + c), 1e-10f));
+      a.bias_out[c] =
+          __fadd_rn(__fdiv_rn(__fmul_rn(__ldg(a.gamma + c), __fsub_rn(b, __ldg(a.mean + c))), sd), __ldg(a.beta + c));
+    }
+  }
+
+  if (a.bits <= 0) {   // fold only (merge_bn.py:65-66)
+    for_channels<FOLD>(
+        a, begin, end, [&](int64_t) { return 0; },
+        [&](int, int64_t i, float4 v) { st_stream(reinterpret_cast<float4*>(a.w_out + i), v); },
+        [&](int, int64_t i, float v) { a.w_out[i] = v; }, false);
+    return;
+  }
+
+  // phase 1: per-row max of |W'|
+  if (begin < end) {
+    if (a.Lc < 2048) {
+      // warp-per-channel: every lane keeps its own running max, merged per channel
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+      const int64_t c0 = begin / a.Lc, c1 = (end - 1) / a.Lc;
+      for (int64_t c = c0 + warp; c <= c1; c += nw) {
+        float g = 1.f, sd = 1.f;
+        if (FOLD) fold_factors(a, c, g, sd);
+        const int64_t lo = max(begin, c * a.Lc), hi = min(end, (c + 1) * a.Lc);
+        float m = 0.f;
+        for (int64_t i = lo + lane; i < hi; i += 32) {
+          float v = __ldg(a.w + i);
+          if (FOLD) v = __fdiv_rn(__fmul_rn(v, g), sd);
+          m = fmaxf(m, fabsf(v));
+        }
+        m = warp_max(m);
+        if (lane == 0) atomicMax(&a.ws->rowmax[c / ch_per_row], __float_as_uint(m));
+      }
+    } else {
+      const int64_t c0 = begin / a.Lc, c1 = (end - 1) / a.Lc;
+      for (int64_t c = c0; c <= c1; ++c) {
+        float g = 1.f, sd = 1.f;
+        if (FOLD) fold_factors(a, c, g, sd);
+        const int64_t lo = max(begin, c * a.Lc), hi = min(end, (c + 1) * a.Lc);
+        auto f1 = [&](float v) { return FOLD ? __fdiv_rn(__fmul_rn(v, g), sd) : v; };
+        float m = 0.f;
+        for_range<false, true>(
+            a.w, lo, hi,
+            [&](int64_t, float4 v) { m = absmax4(m, make_float4(f1(v.x), f1(v.y), f1(v.z), f1(v.w))); },
+            [&](int64_t, float v) { m = fmaxf(m, fabsf(f1(v))); });
+        m = block_max(m, red);
+        if (threadIdx.x == 0) atomicMax(&a.ws->rowmax[c / ch_per_row], __float_as_uint(m));
+      }
+    }
+  }
+
+  grid_barrier(a.ws, [&]() {
+    if (a.scale_out != nullptr) {
+      const float qmax = (float)((1 << (a.bits - 1)) - 1);
+      for (int64_t r = threadIdx.x; r < a.rows; r += blockDim.x)
+        a.scale_out[r] = __fdiv_rn(__uint_as_float(__ldcg(&a.ws->rowmax[r])), qmax);
+    }
+  });
+
+  // phase 2: quantise, newest lines first
+  const float qmax = (float)((1 << (a.bits - 1)) - 1);
+  for_channels<FOLD>(
+      a, begin, end,
+      [&](int64_t c) {   // {s_r, d_r}: convert_conv2d.py:76 / ste_func.py:39
+        const float s = __fdiv_rn(__uint_as_float(__ldcg(&a.ws->rowmax[c / ch_per_row])), qmax);
+        return make_float2(s, __fadd_rn(s, 1e-10f));
+      },
+      [&](float2 sd, int64_t i, float4 v) {
+        float4 q = make_float4(quant_code(v.x, sd.y), quant_code(v.y, sd.y), quant_code(v.z, sd.y), quant_code(v.w, sd.y));
+        st_stream(reinterpret_cast<float4*>(a.w_out + i),
+                  make_float4(__fmul_rn(q.x, sd.x), __fmul_rn(q.y, sd.x), __fmul_rn(q.z, sd.x), __fmul_rn(q.w, sd.x)));
+        if (a.code_kind) put_code4(a.codes, a.code_kind, i, q);
+      },
+      [&](float2 sd, int64_t i, float v) {
+        const float q = quant_code(v, sd.y);
+        a.w_out[i] = __fmul_rn(q, sd.x);
+        if (a.code_kind) put_code1(a.codes, a.code_kind, i, q);
+      },
+      true);
+
+  // restore the workspace invariant once every block has consumed the row maxima
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&a.ws->ticket2, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    for (int64_t r = threadIdx.x; r < a.rows; r += blockDim.x) a.ws->rowmax[r] = 0u;
+    if (threadIdx.x == 0) a.ws->ticket2 = 0;
+  }
+}
+
+static int code_kind_of(const char* who, const View& codes, int64_t n, int* kind) {
+  *kind = 0;
+  if (codes.null) return 0;
+  FQ_REQUIRE(codes.numel == n, "%s: codes has %lld elements, expected %lld", who, (long long)codes.numel, (long long)n);
+  if (codes.code == kDLInt && codes.bits == 8) *kind = 1;
+  else if (codes.code == kDLUInt && codes.bits == 8) *kind = 2;
+  else if (codes.code == kDLInt && codes.bits == 16) *kind = 3;
+  else if (codes.code == kDLUInt && codes.bits == 16) *kind = 4;
+  else if (codes.code == kDLInt && codes.bits == 32) *kind = 5;
+  else if (codes.code == kDLFloat && codes.bits == 32) *kind = 6;
+  else FQ_REQUIRE(false, "%s: codes dtype (code %d, %d bits) unsupported", who, codes.code, codes.bits);
+  return 0;
+}
+
+// co-resident grid size for a cooperative kernel
+template <class K>
+static int coop_blocks(K kernel, int* out) {
+  int per_sm = 0;
+  FQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
+  FQ_REQUIRE(per_sm >= 1, "cooperative kernel does not fit on an SM");
+  if (per_sm > 8) per_sm = 8;
+  *out = per_sm * sm_count();
+  return 0;
+}
+
+template <class K, class A>
+static int launch_coop(K kernel, int grid, A& args, cudaStream_t st, const char* name) {
+  void* params[] = {(void*)&args};
+  FQ_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(kThreads), params, 0, st));
+  FQ_LAUNCH_CHECK(name);
+  return 0;
+}
+
+}  // namespace fq
+
+using namespace fq;
+
+extern "C" {
+
+int fq_forward_online(const DLTensor* x_, int64_t n_samples, int bits, int is_signed, int lo_mode, int promotion,
+                      const DLTensor* input_max_, const DLTensor* y_, const DLTensor* codes_,
+                      const DLTensor* cur_max_, const DLTensor* qparams_, const DLTensor* per_sample_, void* ws,
+                      void* stream) {
+  const char* who = "fq_forward_online";
+  View x, imax, y, codes, cur, qp, ps;
+  FQ_TRY(view_of(x_, "fq_forward_online: x", false, &x));
+  FQ_TRY(view_of(input_max_, "fq_forward_online: input_max", true, &imax));
+  FQ_TRY(view_of(y_, "fq_forward_online: y", true, &y));
+  FQ_TRY(view_of(codes_, "fq_forward_online: codes", true, &codes));
+  FQ_TRY(view_of(cur_max_, "fq_forward_online: cur_max", false, &cur));
+  FQ_TRY(view_of(qparams_, "fq_forward_online: qparams", true, &qp));
+  FQ_TRY(view_of(per_sample_, "fq_forward_online: per_sample", true, &ps));
+  FQ_REQUIRE(ws != nullptr, "%s: NULL workspace", who);
+  FQ_REQUIRE(x.is_f32() && cur.is_f32() && cur.numel >= 1, "%s: x and cur_max must be float32", who);
+  FQ_REQUIRE(n_samples >= 1 && n_samples <= FQ_MAX_ROWS, "%s: n_samples=%lld outside [1, %d]", who,
+             (long long)n_samples, FQ_MAX_ROWS);
+  FQ_REQUIRE(x.numel > 0 && x.numel % n_samples == 0, "%s: numel %lld not a positive multiple of n_samples %lld", who,
+             (long long)x.numel, (long long)n_samples);
+  FQ_REQUIRE(ps.null || (ps.is_f32() && ps.numel == n_samples), "%s: per_sample must be float32 [n_samples]", who);
+  FQ_REQUIRE(imax.null || (imax.is_f32() && imax.numel >= 1), "%s: input_max must be float32", who);
+  FQ_TRY(check_quant_args(who, bits, lo_mode, promotion));
+  cudaStream_t st = (cudaStream_t)stream;
+
+  InputArgs a = {};
+  a.x = x.as<const float>();
+  a.n = x.numel;
+  a.rows = n_samples;
+  a.L = x.numel / n_samples;
+  a.ws = (Workspace*)ws;
+  a.fin.out_rows = ps.null ? nullptr : ps.as<float>();
+  a.fin.out_mean = cur.as<float>();
+  a.fin.input_max = imax.null ? nullptr : imax.as<const float>();
+  a.fin.bits = bits;
+  a.fin.is_signed = is_signed;
+  a.fin.lo_mode = lo_mode;
+  a.fin.promotion = promotion;
+  a.fin.qparams = qp.null ? nullptr : qp.as<float>();
+
+  if (y.null) {   // range tracking only
+    FQ_REQUIRE(codes.null, "%s: codes without y", who);
+    const int grid = slice_grid(a.n, sm_count() * 8, &a.per_block);
+    input_path_kernel<kRangeOnly><<<grid, kThreads, 0, st>>>(a);
+    FQ_LAUNCH_CHECK("input_path_kernel<range>");
+    return 0;
+  }
+  FQ_REQUIRE(y.is_f32() && y.numel == x.numel, "%s: y must be float32 like x", who);
+  FQ_REQUIRE(!qp.null && qp.is_f32() && qp.numel == 4, "%s: qparams must be 4 float32", who);
+  FQ_REQUIRE(aligned16(x.data) && aligned16(y.data) && (codes.null || aligned16(codes.data)),
+             "%s: x, y and codes must be 16-byte aligned", who);
+  a.y = y.as<float>();
+  a.codes = codes.null ? nullptr : codes.data;
+  FQ_TRY(code_kind_of(who, codes, x.numel, &a.code_kind) == 0);
+
+  if (!imax.null) {   // offline range, current range still tracked: one pass
+    const int grid = slice_grid(a.n, sm_count() * 8, &a.per_block);
+    input_path_kernel<kOfflineTrack><<<grid, kThreads, 0, st>>>(a);
+    FQ_LAUNCH_CHECK("input_path_kernel<offline>");
+    return 0;
+  }
+  int max_blocks = 0;
+  FQ_TRY(coop_blocks(input_path_kernel<kOnline>, &max_blocks) == 0);
+  const int grid = slice_grid(a.n, max_blocks, &a.per_block);
+  return launch_coop(input_path_kernel<kOnline>, grid, a, st, "input_path_kernel<online>");
+}
+
+int fq_quant_weight(const DLTensor* w_, int64_t rows, int bits, const DLTensor* gamma_, const DLTensor* beta_,
+                    const DLTensor* mean_, const DLTensor* var_, const DLTensor* bias_, const DLTensor* w_out_,
+                    const DLTensor* bias_out_, const DLTensor* scale_out_, const DLTensor* codes_, void* ws,
+                    void* stream) {
+  const char* who = "fq_quant_weight";
+  View w, gamma, beta, mean, var, bias, w_out, bias_out, scale_out, codes;
+  FQ_TRY(view_of(w_, "fq_quant_weight: w", false, &w));
+  FQ_TRY(view_of(gamma_, "fq_quant_weight: gamma", true, &gamma));
+  FQ_TRY(view_of(beta_, "fq_quant_weight: beta", true, &beta));
+  FQ_TRY(view_of(mean_, "fq_quant_weight: mean", true, &mean));
+  FQ_TRY(view_of(var_, "fq_quant_weight: var", true, &var));
+  FQ_TRY(view_of(bias_, "fq_quant_weight: bias", true, &bias));
+  FQ_TRY(view_of(w_out_, "fq_quant_weight: w_out", false, &w_out));
+  FQ_TRY(view_of(bias_out_, "fq_quant_weight: bias_out", true, &bias_out));
+  FQ_TRY(view_of(scale_out_, "fq_quant_weight: scale_out", true, &scale_out));
+  FQ_TRY(view_of(codes_, "fq_quant_weight: codes", true, &codes));
+  FQ_REQUIRE(ws != nullptr, "%s: NULL workspace", who);
+  FQ_REQUIRE(w.is_f32() && w_out.is_f32() && w.numel == w_out.numel && w.numel > 0,
+             "%s: w and w_out must be non-empty float32 of equal size", who);
+  FQ_REQUIRE(w_->ndim >= 1 && w_->shape[0] >= 1, "%s: w needs a leading output-channel axis", who);
+  const int64_t cout = w_->shape[0];
+  const bool fold = !gamma.null;
+  FQ_REQUIRE(fold == !beta.null && fold == !mean.null && fold == !var.null,
+             "%s: gamma, beta, mean and var must be given together", who);
+  if (fold) {
+    FQ_REQUIRE(gamma.is_f32() && beta.is_f32() && mean.is_f32() && var.is_f32() && gamma.numel == cout &&
+                   beta.numel == cout && mean.numel == cout && var.numel == cout,
+               "%s: BN vectors must be float32 [Cout=%lld]", who, (long long)cout);
+    FQ_REQUIRE(bias.null || (bias.is_f32() && bias.numel == cout), "%s: bias must be float32 [Cout]", who);
+    FQ_REQUIRE(bias_out.null || (bias_out.is_f32() && bias_out.numel == cout), "%s: bias_out must be float32 [Cout]", who);
+  }
+  if (bits > 0) {
+    FQ_REQUIRE(bits >= 2 && bits <= 24, "%s: bits=%d outside [2, 24]", who, bits);
+    FQ_REQUIRE(rows >= 1 && rows <= FQ_MAX_ROWS && cout % rows == 0, "%s: rows=%lld must divide Cout=%lld", who,
+               (long long)rows, (long long)cout);
+    FQ_REQUIRE(scale_out.null || (scale_out.is_f32() && scale_out.numel == rows), "%s: scale_out must be float32 [rows]", who);
+  } else {
+    rows = 1;
+    FQ_REQUIRE(fold, "%s: bits <= 0 (fold only) needs the BN vectors", who);
+  }
+  FQ_REQUIRE(aligned16(w.data) && aligned16(w_out.data) && (codes.null || aligned16(codes.data)),
+             "%s: w, w_out and codes must be 16-byte aligned", who);
+
+  WeightArgs a = {};
+  a.w = w.as<const float>();
+  a.w_out = w_out.as<float>();
+  a.codes = codes.null ? nullptr : codes.data;
+  FQ_TRY(code_kind_of(who, codes, w.numel, &a.code_kind) == 0);
+  a.n = w.numel;
+  a.cout = cout;
+  a.Lc = w.numel / cout;
+  a.rows = rows;
+  a.bits = bits;
+  a.gamma = fold ? gamma.as<const float>() : nullptr;
+  a.beta = fold ? beta.as<const float>() : nullptr;
+  a.mean = fold ? mean.as<const float>() : nullptr;
+  a.var = fold ? var.as<const float>() : nullptr;
+  a.bias = bias.null ? nullptr : bias.as<const float>();
+  a.bias_out = bias_out.null ? nullptr : bias_out.as<float>();
+  a.scale_out = scale_out.null ? nullptr : scale_out.as<float>();
+  a.ws = (Workspace*)ws;
+  cudaStream_t st = (cudaStream_t)stream;
+  int max_blocks = 0;
+  if (fold) {
+    FQ_TRY(coop_blocks(weight_path_kernel<true>, &max_blocks) == 0);
+    const int grid = slice_grid(a.n, max_blocks, &a.per_block);
+    return launch_coop(weight_path_kernel<true>, grid, a, st, "weight_path_kernel<fold>");
+  }
+  FQ_TRY(coop_blocks(weight_path_kernel<false>, &max_blocks) == 0);
+  const int grid = slice_grid(a.n, max_blocks, &a.per_block);
+  return launch_coop(weight_path_kernel<false>, grid, a, st, "weight_path_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,351 @@
+// K2/K3/K6: elementwise fake-quant forward, STE backward, integer export.
+// HBM-bound streaming kernels: 128-bit loads/stores with streaming cache hints, kUnroll independent
+// loads in flight per thread, one contiguous 16 B aligned slice per block, grid = k * SM count.
+//   reference: quantize/convert/ste_func.py:37-44; freeze.py:100-103; nn/quantized_conv.py:54-76
+#include "fq_fused.cuh"
+
+namespace fq {
+
+// ---- code (rounded quotient) sinks -----------------------------------------------------------
+struct NoCode {
+  __device__ __forceinline__ void put4(int64_t, float4) const {}
+  __device__ __forceinline__ void put1(int64_t, float) const {}
+};
+template <class T>
+struct IntCode {
+  T* p;
+  __device__ __forceinline__ void put1(int64_t i, float c) const { p[i] = (T)(int)c; }
+  __device__ __forceinline__ void put4(int64_t i, float4 c) const {
+    if constexpr (sizeof(T) == 1) {
+      uchar4 o = make_uchar4((unsigned char)(T)(int)c.x, (unsigned char)(T)(int)c.y, (unsigned char)(T)(int)c.z,
+                             (unsigned char)(T)(int)c.w);
+      *reinterpret_cast<uchar4*>(p + i) = o;
+    } else if constexpr (sizeof(T) == 2) {
+      ushort4 o = make_ushort4((unsigned short)(T)(int)c.x, (unsigned short)(T)(int)c.y, (unsigned short)(T)(int)c.z,
+                               (unsigned short)(T)(int)c.w);
+      *reinterpret_cast<ushort4*>(p + i) = o;
+    } else {
+      int4 o = make_int4((int)c.x, (int)c.y, (int)c.z, (int)c.w);
+      *reinterpret_cast<int4*>(p + i) = o;
+    }
+  }
+};
+struct FloatCode {
+  float* p;
+  __device__ __forceinline__ void put1(int64_t i, float c) const { p[i] = c; }
+  __device__ __forceinline__ void put4(int64_t i, float4 c) const { st_stream(reinterpret_cast<float4*>(p + i), c); }
+};
+
+// ---- y = roundf(clip(x) / d) * s with scalar qparams --------------------------------------------
+template <bool CLIP, class Code>
+struct ScalarQuant {
+  float d, s, lo, hi;
+  float* y;
+  Code code;
+  __device__ __forceinline__ float one(float x, float& c) const {
+    if (CLIP) x = clipf(x, lo, hi);
+    c = quant_code(x, d);
+    return __fmul_rn(c, s);
+  }
+  __device__ __forceinline__ void vec(int64_t i, float4 v) const {
+    float4 c, o;
+    o.x = one(v.x, c.x);
+    o.y = one(v.y, c.y);
+    o.z = one(v.z, c.z);
+    o.w = one(v.w, c.w);
+    st_stream(reinterpret_cast<float4*>(y + i), o);
+    code.put4(i, c);
+  }
+  __device__ __forceinline__ void sca(int64_t i, float v) const {
+    float c;
+    y[i] = one(v, c);
+    code.put1(i, c);
+  }
+};
+
+template <bool CLIP, class Code>
+__global__ void __launch_bounds__(kThreads) forward_scalar_kernel(const float* __restrict__ x, int64_t n,
+                                                                  int64_t per_block, const float* __restrict__ qp_dev,
+                                                                  ScalarQuant<CLIP, Code> op, int vectorised) {
+  if (qp_dev != nullptr) {
+    op.d = __ldg(qp_dev + FQ_QP_D);
+    op.s = __ldg(qp_dev + FQ_QP_S);
+    op.lo = __ldg(qp_dev + FQ_QP_LO);
+    op.hi = __ldg(qp_dev + FQ_QP_HI);
+  }
+  if (vectorised) {
+    const int64_t begin = (int64_t)blockIdx.x * per_block;
+    const int64_t end = min(n, begin + per_block);
+    for_range<false, false>(
+        x, begin, end, [&](int64_t i, float4 v) { op.vec(i, v); }, [&](int64_t i, float v) { op.sca(i, v); });
+  } else {   // some pointer is not 16 B aligned: plain scalar grid-stride loop
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      op.sca(i, x[i]);
+  }
+}
+
+// ---- per-row scale tensor (weights): y = roundf(x / (s_r + 1e-10)) * s_r -------------------------
+template <class Code>
+__global__ void __launch_bounds__(kThreads) forward_rows_kernel(const float* __restrict__ x, int64_t n, int64_t L,
+                                                                int64_t per_block, const float* __restrict__ scale,
+                                                                float* __restrict__ y, Code code, int vectorised) {
+  if (vectorised && L >= 1024) {
+    const int64_t begin = (int64_t)blockIdx.x * per_block;
+    const int64_t end = min(n, begin + per_block);
+    if (begin >= end) return;
+    for (int64_t r = begin / L; r * L < end; ++r) {
+      ScalarQuant<false, Code> op;
+      op.s = __ldg(scale + r);
+      op.d = __fadd_rn(op.s, 1e-10f);
+      op.lo = op.hi = 0.f;
+      op.y = y;
+      op.code = code;
+      for_range<false, false>(
+          x, max(begin, r * L), min(end, (r + 1) * L), [&](int64_t i, float4 v) { op.vec(i, v); },
+          [&](int64_t i, float v) { op.sca(i, v); });
+    }
+  } else {   // short rows (depthwise 3x3: L = 9) or misaligned pointers: one element per thread
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const float s = __ldg(scale + i / L);
+      const float c = quant_code(x[i], __fadd_rn(s, 1e-10f));
+      y[i] = __fmul_rn(c, s);
+      code.put1(i, c);
+    }
+  }
+}
+
+// ---- STE backward with the clip mask (extension; the reference's backward is the identity) ------
+__global__ void __launch_bounds__(kThreads) ste_mask_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ qp, float* __restrict__ dx,
+                                                            int64_t n, int64_t per_block, int vectorised) {
+  const float lo = __ldg(qp + FQ_QP_LO), hi = __ldg(qp + FQ_QP_HI);
+  auto m = [&](float g, float v) { return (v >= lo && v <= hi) ? g : 0.f; };
+  if (vectorised) {
+    const int64_t begin = (int64_t)blockIdx.x * per_block;
+    const int64_t end = min(n, begin + per_block);
+    for_range<false, false>(
+        dy, begin, end,
+        [&](int64_t i, float4 g) {
+          const float4 v = ld_stream(reinterpret_cast<const float4*>(x + i));
+          st_stream(reinterpret_cast<float4*>(dx + i), make_float4(m(g.x, v.x), m(g.y, v.y), m(g.z, v.z), m(g.w, v.w)));
+        },
+        [&](int64_t i, float g) { dx[i] = m(g, x[i]); });
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      dx[i] = m(dy[i], x[i]);
+  }
+}
+
+// ---- MXNet contrib.quantize(out_type=int8), zero centred ---------------------------------------
+__global__ void __launch_bounds__(kThreads) int8_export_kernel(const float* __restrict__ w, int64_t n,
+                                                               const float* __restrict__ range2,
+                                                               signed char* __restrict__ out,
+                                                               float* __restrict__ out_range2) {
+  const float real = fmaxf(fabsf(__ldg(range2)), fabsf(__ldg(range2 + 1)));
+  const float scale = __fdiv_rn(127.0f, real);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = w[i];
+    const float mag = fminf(__fadd_rn(__fmul_rn(fabsf(v), scale), 0.5f), 127.0f);
+    const float sgn = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
+    out[i] = (signed char)(int)__fmul_rn(sgn, mag);      // C cast: truncation
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && out_range2 != nullptr) {
+    out_range2[0] = -real;
+    out_range2[1] = real;
+  }
+}
+
+// ---- nn/quantized_conv.py:_quantize / dequantize ------------------------------------------------
+__global__ void __launch_bounds__(kThreads) qconv_quantize_kernel(const float* __restrict__ x, int64_t n,
+                                                                  const float* __restrict__ range2,
+                                                                  int* __restrict__ codes, float* __restrict__ scale_out) {
+  const float lo = __ldg(range2), hi = __ldg(range2 + 1);
+  const float scale = (hi == -lo) ? __fdiv_rn(hi, 127.0f) : __fdiv_rn(__fsub_rn(hi, lo), 255.0f);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    codes[i] = (int)quant_code(clipf(x[i], lo, hi), scale);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && scale_out != nullptr) scale_out[0] = scale;
+}
+
+__global__ void __launch_bounds__(kThreads) qconv_dequantize_kernel(const int* __restrict__ acc, int64_t n,
+                                                                    const float* __restrict__ s_in,
+                                                                    const float* __restrict__ s_w,
+                                                                    float* __restrict__ y) {
+  const float s = __fmul_rn(__ldg(s_in), __ldg(s_w));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = __fmul_rn((float)acc[i], s);
+}
+
+static inline int ew_grid(int64_t n) {
+  int64_t b = (n + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// dispatch on the dtype of the optional `codes` tensor
+template <class F>
+static int with_code_sink(const char* who, const View& codes, int64_t n, F f) {
+  if (codes.null) return f(NoCode());
+  if (codes.numel != n) {
+    set_error("%s: codes has %lld elements, expected %lld", who, (long long)codes.numel, (long long)n);
+    return -1;
+  }
+  if (codes.code == kDLFloat && codes.bits == 32) return f(FloatCode{codes.as<float>()});
+  if (codes.code == kDLInt && codes.bits == 8) return f(IntCode<signed char>{codes.as<signed char>()});
+  if (codes.code == kDLUInt && codes.bits == 8) return f(IntCode<unsigned char>{codes.as<unsigned char>()});
+  if (codes.code == kDLInt && codes.bits == 16) return f(IntCode<short>{codes.as<short>()});
+  if (codes.code == kDLUInt && codes.bits == 16) return f(IntCode<unsigned short>{codes.as<unsigned short>()});
+  if (codes.code == kDLInt && codes.bits == 32) return f(IntCode<int>{codes.as<int>()});
+  set_error("%s: codes dtype (code %d, %d bits) unsupported; use int8/uint8/int16/uint16/int32/float32", who,
+            codes.code, codes.bits);
+  return -1;
+}
+
+static int forward_scalar_impl(const char* who, const DLTensor* x_, const float* qp_dev, float d, float s, float lo,
+                               float hi, bool clip, const DLTensor* y_, const DLTensor* codes_, void* stream) {
+  View x, y, codes;
+  FQ_TRY(view_of(x_, who, false, &x));
+  FQ_TRY(view_of(y_, who, false, &y));
+  FQ_TRY(view_of(codes_, who, true, &codes));
+  FQ_REQUIRE(x.is_f32() && y.is_f32(), "%s: x and y must be float32", who);
+  FQ_REQUIRE(x.numel == y.numel, "%s: x has %lld elements, y %lld", who, (long long)x.numel, (long long)y.numel);
+  if (x.numel == 0) return 0;
+  const int64_t n = x.numel;
+  const int vec = aligned16(x.data) && aligned16(y.data) && (codes.null || aligned16(codes.data));
+  int64_t per_block;
+  const int grid = vec ? slice_grid(n, sm_count() * 8, &per_block) : ew_grid(n);
+  cudaStream_t st = (cudaStream_t)stream;
+  return with_code_sink(who, codes, n, [&](auto sink) -> int {
+    using Code = decltype(sink);
+    if (clip) {
+      ScalarQuant<true, Code> op{d, s, lo, hi, y.as<float>(), sink};
+      forward_scalar_kernel<true, Code><<<grid, kThreads, 0, st>>>(x.as<const float>(), n, per_block, qp_dev, op, vec);
+    } else {
+      ScalarQuant<false, Code> op{d, s, lo, hi, y.as<float>(), sink};
+      forward_scalar_kernel<false, Code><<<grid, kThreads, 0, st>>>(x.as<const float>(), n, per_block, qp_dev, op, vec);
+    }
+    FQ_LAUNCH_CHECK("forward_scalar_kernel");
+    return 0;
+  });
+}
+
+}  // namespace fq
+
+using namespace fq;
+
+extern "C" {
+
+int fq_forward_scalar(const DLTensor* x, const DLTensor* qparams_, const DLTensor* y, const DLTensor* codes,
+                      void* stream) {
+  View qp;
+  FQ_TRY(view_of(qparams_, "fq_forward_scalar: qparams", false, &qp));
+  FQ_REQUIRE(qp.is_f32() && qp.numel == 4, "fq_forward_scalar: qparams must be 4 float32 {d, s, lo, hi}");
+  return forward_scalar_impl("fq_forward_scalar", x, qp.as<const float>(), 0, 0, 0, 0, true, y, codes, stream);
+}
+
+int fq_forward_scalar_host(const DLTensor* x, float d, float s, float lo, float hi, int use_clip, const DLTensor* y,
+                           const DLTensor* codes, void* stream) {
+  return forward_scalar_impl("fq_forward_scalar_host", x, nullptr, d, s, lo, hi, use_clip != 0, y, codes, stream);
+}
+
+int fq_forward_rows(const DLTensor* x_, int64_t rows, const DLTensor* scale_, const DLTensor* y_,
+                    const DLTensor* codes_, void* stream) {
+  View x, sc, y, codes;
+  FQ_TRY(view_of(x_, "fq_forward_rows: x", false, &x));
+  FQ_TRY(view_of(scale_, "fq_forward_rows: scale", false, &sc));
+  FQ_TRY(view_of(y_, "fq_forward_rows: y", false, &y));
+  FQ_TRY(view_of(codes_, "fq_forward_rows: codes", true, &codes));
+  FQ_REQUIRE(x.is_f32() && y.is_f32() && sc.is_f32(), "fq_forward_rows: float32 only");
+  FQ_REQUIRE(rows >= 1 && sc.numel == rows, "fq_forward_rows: scale must have rows=%lld elements", (long long)rows);
+  FQ_REQUIRE(x.numel == y.numel && x.numel % rows == 0, "fq_forward_rows: numel %lld must match y and divide by rows",
+             (long long)x.numel);
+  if (x.numel == 0) return 0;
+  const int64_t n = x.numel, L = n / rows;
+  const int vec = aligned16(x.data) && aligned16(y.data) && (codes.null || aligned16(codes.data));
+  int64_t per_block = 0;
+  const int grid = (vec && L >= 1024) ? slice_grid(n, sm_count() * 8, &per_block) : ew_grid(n);
+  cudaStream_t st = (cudaStream_t)stream;
+  return with_code_sink("fq_forward_rows", codes, n, [&](auto sink) -> int {
+    forward_rows_kernel<<<grid, kThreads, 0, st>>>(x.as<const float>(), n, L, per_block, sc.as<const float>(),
+                                                   y.as<float>(), sink, vec);
+    FQ_LAUNCH_CHECK("forward_rows_kernel");
+    return 0;
+  });
+}
+
+int fq_ste_backward(const DLTensor* dy_, const DLTensor* x_, const DLTensor* qparams_, const DLTensor* dx_, int mode,
+                    void* stream) {
+  View dy, x, qp, dx;
+  FQ_TRY(view_of(dy_, "fq_ste_backward: dy", false, &dy));
+  FQ_TRY(view_of(dx_, "fq_ste_backward: dx", false, &dx));
+  FQ_REQUIRE(dy.is_f32() && dx.is_f32() && dy.numel == dx.numel, "fq_ste_backward: dy/dx must be float32 of equal size");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == FQ_STE_IDENTITY) {   // ste_func.py:43-44; callers alias instead of calling (0 bytes moved)
+    if (dx.data != dy.data && dy.numel > 0)
+      FQ_CUDA(cudaMemcpyAsync(dx.data, dy.data, sizeof(float) * dy.numel, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  FQ_REQUIRE(mode == FQ_STE_CLIP_MASK, "fq_ste_backward: bad mode %d", mode);
+  FQ_TRY(view_of(x_, "fq_ste_backward: x", false, &x));
+  FQ_TRY(view_of(qparams_, "fq_ste_backward: qparams", false, &qp));
+  FQ_REQUIRE(x.is_f32() && x.numel == dy.numel && qp.is_f32() && qp.numel == 4,
+             "fq_ste_backward: x must match dy and qparams must be 4 float32");
+  if (dy.numel == 0) return 0;
+  const int vec = aligned16(dy.data) && aligned16(x.data) && aligned16(dx.data);
+  int64_t per_block = 0;
+  const int grid = vec ? slice_grid(dy.numel, sm_count() * 8, &per_block) : ew_grid(dy.numel);
+  ste_mask_kernel<<<grid, kThreads, 0, st>>>(dy.as<const float>(), x.as<const float>(), qp.as<const float>(),
+                                             dx.as<float>(), dy.numel, per_block, vec);
+  FQ_LAUNCH_CHECK("ste_mask_kernel");
+  return 0;
+}
+
+int fq_quantize_int8_export(const DLTensor* w_, const DLTensor* range2_, const DLTensor* out_,
+                            const DLTensor* out_range2_, void* stream) {
+  View w, rg, out, org;
+  FQ_TRY(view_of(w_, "fq_quantize_int8_export: w", false, &w));
+  FQ_TRY(view_of(range2_, "fq_quantize_int8_export: range2", false, &rg));
+  FQ_TRY(view_of(out_, "fq_quantize_int8_export: out", false, &out));
+  FQ_TRY(view_of(out_range2_, "fq_quantize_int8_export: out_range2", true, &org));
+  FQ_REQUIRE(w.is_f32() && rg.is_f32() && rg.numel == 2, "fq_quantize_int8_export: w float32, range2 = 2 float32");
+  FQ_REQUIRE(out.code == kDLInt && out.bits == 8 && out.numel == w.numel, "fq_quantize_int8_export: out must be int8 like w");
+  FQ_REQUIRE(org.null || (org.is_f32() && org.numel == 2), "fq_quantize_int8_export: out_range2 = 2 float32");
+  int8_export_kernel<<<ew_grid(w.numel), kThreads, 0, (cudaStream_t)stream>>>(
+      w.as<const float>(), w.numel, rg.as<const float>(), out.as<signed char>(), org.null ? nullptr : org.as<float>());
+  FQ_LAUNCH_CHECK("int8_export_kernel");
+  return 0;
+}
+
+int fq_qconv_quantize(const DLTensor* x_, const DLTensor* range2_, const DLTensor* codes_, const DLTensor* scale_out_,
+                      void* stream) {
+  View x, rg, codes, so;
+  FQ_TRY(view_of(x_, "fq_qconv_quantize: x", false, &x));
+  FQ_TRY(view_of(range2_, "fq_qconv_quantize: range2", false, &rg));
+  FQ_TRY(view_of(codes_, "fq_qconv_quantize: codes", false, &codes));
+  FQ_TRY(view_of(scale_out_, "fq_qconv_quantize: scale_out", true, &so));
+  FQ_REQUIRE(x.is_f32() && rg.is_f32() && rg.numel == 2, "fq_qconv_quantize: x float32, range2 = 2 float32");
+  FQ_REQUIRE(codes.code == kDLInt && codes.bits == 32 && codes.numel == x.numel, "fq_qconv_quantize: codes must be int32 like x");
+  FQ_REQUIRE(so.null || (so.is_f32() && so.numel >= 1), "fq_qconv_quantize: scale_out must be float32");
+  qconv_quantize_kernel<<<ew_grid(x.numel), kThreads, 0, (cudaStream_t)stream>>>(
+      x.as<const float>(), x.numel, rg.as<const float>(), codes.as<int>(), so.null ? nullptr : so.as<float>());
+  FQ_LAUNCH_CHECK("qconv_quantize_kernel");
+  return 0;
+}
+
+int fq_qconv_dequantize(const DLTensor* acc_, const DLTensor* s_in_, const DLTensor* s_w_, const DLTensor* y_,
+                        void* stream) {
+  View acc, si, sw, y;
+  FQ_TRY(view_of(acc_, "fq_qconv_dequantize: acc", false, &acc));
+  FQ_TRY(view_of(s_in_, "fq_qconv_dequantize: s_in", false, &si));
+  FQ_TRY(view_of(s_w_, "fq_qconv_dequantize: s_w", false, &sw));
+  FQ_TRY(view_of(y_, "fq_qconv_dequantize: y", false, &y));
+  FQ_REQUIRE(acc.code == kDLInt && acc.bits == 32 && y.is_f32() && acc.numel == y.numel,
+             "fq_qconv_dequantize: acc int32 and y float32 of equal size");
+  FQ_REQUIRE(si.is_f32() && sw.is_f32() && si.numel >= 1 && sw.numel >= 1, "fq_qconv_dequantize: scales must be float32");
+  if (acc.numel == 0) return 0;
+  qconv_dequantize_kernel<<<ew_grid(acc.numel), kThreads, 0, (cudaStream_t)stream>>>(
+      acc.as<const int>(), acc.numel, si.as<const float>(), sw.as<const float>(), y.as<float>());
+  FQ_LAUNCH_CHECK("qconv_dequantize_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,254 @@
+"""Functional wrappers: torch CUDA tensors in, libfq_b200 kernels launched on torch's current stream.
+
+Each function corresponds to one C-ABI entry point of include/fq.h and cites the reference code it
+replaces.  Nothing here synchronises the host or touches the CPU.
+"""
+import torch
+
+from . import _ffi
+from ._ffi import LO_NEG_MAX, LO_ZERO, STE_CLIP_MASK, STE_IDENTITY, check_call, current_stream, dl, ptr, workspace
+
+_PROMOTIONS = {"legacy": _ffi.PROMOTION_LEGACY, "nep50": _ffi.PROMOTION_NEP50}
+_promotion = "legacy"
+
+
+def set_promotion(mode):
+    """How the reference's host scalar math is replayed: "legacy" (NumPy 1.x, what an MXNet 1.x
+    install computes; default) or "nep50" (NumPy >= 2)."""
+    global _promotion
+    if mode not in _PROMOTIONS:
+        raise ValueError("promotion must be 'legacy' or 'nep50'")
+    _promotion = mode
+
+
+def get_promotion():
+    return _promotion
+
+
+def _promo(p):
+    return _PROMOTIONS[_promotion if p is None else p]
+
+
+def _f32(x, name="x"):
+    if x.dtype != torch.float32:
+        raise _ffi.FQError("%s must be float32, got %s" % (name, x.dtype))
+    return x.contiguous()
+
+
+def _lib():
+    return _ffi.load()
+
+
+# ---- K1 ------------------------------------------------------------------------------------------
+def absmax_rows(x, rows, out=None):
+    """max |x| per row of x.view(rows, -1).  convert_conv2d.py:56,75,86,92."""
+    x = _f32(x)
+    out = torch.empty(rows, dtype=torch.float32, device=x.device) if out is None else out
+    a, o = dl(x), dl(out)
+    check_call(_lib().fq_absmax_rows(a.ptr, rows, o.ptr, workspace(x.device), current_stream()))
+    return out
+
+
+def minmax(x, out=None):
+    """{min, max} of x.  nn/quantized_conv.py:68-69; distribution_calibrate.py:34-35."""
+    x = _f32(x)
+    out = torch.empty(2, dtype=torch.float32, device=x.device) if out is None else out
+    a, o = dl(x), dl(out)
+    check_call(_lib().fq_minmax(a.ptr, o.ptr, workspace(x.device), current_stream()))
+    return out
+
+
+def mean_kahan(v, out=None):
+    """MXNet CPU ``mean`` of a vector."""
+    v = _f32(v)
+    out = torch.empty(1, dtype=torch.float32, device=v.device) if out is None else out
+    a, o = dl(v), dl(out)
+    check_call(_lib().fq_mean_kahan(a.ptr, o.ptr, current_stream()))
+    return out
+
+
+def input_range(x, n_samples=None, cur_max=None, per_sample=None):
+    """current_input_max = mean_n max_chw |x| in one launch.  convert_conv2d.py:56."""
+    x = _f32(x)
+    n_samples = x.shape[0] if n_samples is None else n_samples
+    cur_max = torch.empty(1, dtype=torch.float32, device=x.device) if cur_max is None else cur_max
+    a, c, p = dl(x), dl(cur_max), dl(per_sample)
+    check_call(_lib().fq_input_range(a.ptr, n_samples, ptr(p), c.ptr, workspace(x.device), current_stream()))
+    return cur_max
+
+
+def scale_from_max(max_, bits, signed, lo_mode, qparams=None, promotion=None):
+    """{d, s, lo, hi} from a device-resident range.  convert_conv2d.py:57-64 + ste_func.py:41."""
+    qparams = torch.empty(4, dtype=torch.float32, device=max_.device) if qparams is None else qparams
+    m, q = dl(_f32(max_, "max_")), dl(qparams)
+    check_call(_lib().fq_scale_from_max(m.ptr, bits, int(bool(signed)), lo_mode, _promo(promotion), q.ptr,
+                                        current_stream()))
+    return qparams
+
+
+# ---- K2 ------------------------------------------------------------------------------------------
+def _codes_like(x, codes_dtype):
+    return None if codes_dtype is None else torch.empty(x.shape, dtype=codes_dtype, device=x.device)
+
+
+def forward_scalar(x, qparams, out=None, codes_dtype=None):
+    """y = roundf(clip(x, lo, hi) / d) * s with device-resident {d, s, lo, hi}.  ste_func.py:41."""
+    x = _f32(x)
+    out = torch.empty_like(x) if out is None else out
+    codes = _codes_like(x, codes_dtype)
+    a, q, o, c = dl(x), dl(qparams), dl(out), dl(codes)
+    check_call(_lib().fq_forward_scalar(a.ptr, q.ptr, o.ptr, ptr(c), current_stream()))
+    return (out, codes) if codes_dtype is not None else out
+
+
+def forward_scalar_host(x, d, s, lo=0.0, hi=0.0, clip=True, out=None, codes_dtype=None):
+    """Same with host scalars; clip=False is ste_func.py:39."""
+    x = _f32(x)
+    out = torch.empty_like(x) if out is None else out
+    codes = _codes_like(x, codes_dtype)
+    a, o, c = dl(x), dl(out), dl(codes)
+    check_call(_lib().fq_forward_scalar_host(a.ptr, d, s, lo, hi, int(bool(clip)), o.ptr, ptr(c), current_stream()))
+    return (out, codes) if codes_dtype is not None else out
+
+
+def forward_rows(x, scale, out=None, codes_dtype=None):
+    """y[r] = roundf(x[r] / (scale[r] + 1e-10)) * scale[r].  ste_func.py:39 with an NDArray scale."""
+    x = _f32(x)
+    scale = _f32(scale, "scale").reshape(-1)
+    out = torch.empty_like(x) if out is None else out
+    codes = _codes_like(x, codes_dtype)
+    a, s, o, c = dl(x), dl(scale), dl(out), dl(codes)
+    check_call(_lib().fq_forward_rows(a.ptr, scale.numel(), s.ptr, o.ptr, ptr(c), current_stream()))
+    return (out, codes) if codes_dtype is not None else out
+
+
+def forward_online(x, bits=8, signed=False, lo_mode=LO_ZERO, input_max=None, quantize=True, n_samples=None,
+                   out=None, cur_max=None, qparams=None, per_sample=None, codes_dtype=None, promotion=None):
+    """The whole input path of a converted block in one launch (convert_conv2d.py:56-66).
+
+    Returns (y, cur_max, qparams[, codes]); y is None when ``quantize`` is False (range tracking only).
+    """
+    x = _f32(x)
+    n_samples = x.shape[0] if n_samples is None else n_samples
+    cur_max = torch.empty(1, dtype=torch.float32, device=x.device) if cur_max is None else cur_max
+    qparams = torch.empty(4, dtype=torch.float32, device=x.device) if qparams is None else qparams
+    y = None
+    if quantize:
+        y = torch.empty_like(x) if out is None else out
+    codes = _codes_like(x, codes_dtype) if quantize else None
+    a, im, yo, c, cm, q, ps = dl(x), dl(input_max), dl(y), dl(codes), dl(cur_max), dl(qparams), dl(per_sample)
+    check_call(_lib().fq_forward_online(a.ptr, n_samples, bits, int(bool(signed)), lo_mode, _promo(promotion),
+                                        ptr(im), ptr(yo), ptr(c), cm.ptr, q.ptr, ptr(ps), workspace(x.device),
+                                        current_stream()))
+    return (y, cur_max, qparams, codes) if codes_dtype is not None else (y, cur_max, qparams)
+
+
+def quant_weight(w, rows, bits, gamma=None, beta=None, mean=None, var=None, bias=None, out=None, bias_out=None,
+                 scale_out=None, codes_dtype=None):
+    """BN fold (optional) + per-row absmax + scale + quantise in one launch.
+
+    convert_conv2d.py:47-51, 70-95; bits <= 0 folds only (merge_bn.py:65-74).
+    Returns (w_q, bias_folded or None, scales or None[, codes]).
+    """
+    w = _f32(w, "w")
+    out = torch.empty_like(w) if out is None else out
+    fold = gamma is not None
+    if fold and bias_out is None:
+        bias_out = torch.empty(w.shape[0], dtype=torch.float32, device=w.device)
+    if bits > 0 and scale_out is None:
+        scale_out = torch.empty(rows, dtype=torch.float32, device=w.device)
+    codes = _codes_like(w, codes_dtype)
+    a = dl(w)
+    g, b, m, v, bi = dl(gamma), dl(beta), dl(mean), dl(var), dl(bias)
+    o, bo, so, c = dl(out), dl(bias_out), dl(scale_out), dl(codes)
+    check_call(_lib().fq_quant_weight(a.ptr, rows, bits, ptr(g), ptr(b), ptr(m), ptr(v), ptr(bi), o.ptr, ptr(bo),
+                                      ptr(so), ptr(c), workspace(w.device), current_stream()))
+    return (out, bias_out, scale_out, codes) if codes_dtype is not None else (out, bias_out, scale_out)
+
+
+# ---- K3 ------------------------------------------------------------------------------------------
+def ste_backward(dy, x=None, qparams=None, mode=STE_IDENTITY):
+    """ste_func.py:43-44.  Identity aliases dy (zero bytes moved); the clip mask is an extension."""
+    if mode == STE_IDENTITY:
+        return dy
+    dy = _f32(dy, "dy")
+    dx = torch.empty_like(dy)
+    g, a, q, o = dl(dy), dl(_f32(x)), dl(qparams), dl(dx)
+    check_call(_lib().fq_ste_backward(g.ptr, a.ptr, q.ptr, o.ptr, mode, current_stream()))
+    return dx
+
+
+# ---- K4 ------------------------------------------------------------------------------------------
+def ema_update(state, cur, momentum=0.9, scalar_cur=True, promotion=None):
+    """state <- (1 - m) * cur + m * state, in place.  convert.py:66-78."""
+    s, c = dl(state), dl(_f32(cur, "cur"))
+    check_call(_lib().fq_ema_update(s.ptr, c.ptr, float(momentum), int(bool(scalar_cur)), _promo(promotion),
+                                    current_stream()))
+    return state
+
+
+# ---- K5 ------------------------------------------------------------------------------------------
+def hist_nonzero(x, max_, bins, counts, promotion=None):
+    """counts[bin] += 1 over the clipped non-zero elements.  distribution_calibrate.py:39-45."""
+    a, m, c = dl(_f32(x)), dl(max_), dl(counts)
+    check_call(_lib().fq_hist_nonzero(a.ptr, m.ptr, bins, _promo(promotion), c.ptr, current_stream()))
+    return counts
+
+
+def hist_accumulate(counts, hist, first, seen_last=None):
+    """hist (+)= float32(counts); counts <- 0.  distribution_calibrate.py:47,103-104."""
+    c, h, s = dl(counts), dl(hist), dl(seen_last)
+    check_call(_lib().fq_hist_accumulate_f32(c.ptr, h.ptr, int(bool(first)), ptr(s), current_stream()))
+    return hist
+
+
+def kl_search(hist, levels, min_bins, bins, promotion=None, divergence=None):
+    """Best threshold bin per histogram (hist: [n_data] or [layers, n_data]).  :117-171.
+
+    Returns (best int32 [layers], divergence float64 [layers, bins])."""
+    hist = _f32(hist, "hist")
+    layers = 1 if hist.dim() == 1 else hist.shape[0]
+    best = torch.empty(layers, dtype=torch.int32, device=hist.device)
+    if divergence is None:
+        divergence = torch.full((layers, bins), float("nan"), dtype=torch.float64, device=hist.device)
+    h, b, d = dl(hist), dl(best), dl(divergence)
+    check_call(_lib().fq_kl_search(h.ptr, levels, min_bins, bins, _promo(promotion), b.ptr, d.ptr, current_stream()))
+    return best, divergence
+
+
+def kl_threshold(best, fm_max, bins, out=None):
+    """input_max = (best + 0.5) * (fm_max / bins).  simulate_quantization.py:310."""
+    out = torch.empty(best.numel(), dtype=torch.float32, device=best.device) if out is None else out
+    b, m, o = dl(best), dl(_f32(fm_max, "fm_max")), dl(out)
+    check_call(_lib().fq_kl_threshold(b.ptr, m.ptr, bins, o.ptr, current_stream()))
+    return out
+
+
+# ---- K6 ------------------------------------------------------------------------------------------
+def quantize_int8_export(w, range2):
+    """MXNet contrib.quantize(out_type='int8').  freeze.py:100-103 -> (int8, {-real, +real})."""
+    w = _f32(w, "w")
+    out = torch.empty(w.shape, dtype=torch.int8, device=w.device)
+    out_range = torch.empty(2, dtype=torch.float32, device=w.device)
+    a, r, o, orr = dl(w), dl(_f32(range2, "range2")), dl(out), dl(out_range)
+    check_call(_lib().fq_quantize_int8_export(a.ptr, r.ptr, o.ptr, orr.ptr, current_stream()))
+    return out, out_range
+
+
+def qconv_quantize(x, range2):
+    """nn/quantized_conv.py:54-61 -> (int32 codes, scale (1,))."""
+    x = _f32(x)
+    codes = torch.empty(x.shape, dtype=torch.int32, device=x.device)
+    scale = torch.empty(1, dtype=torch.float32, device=x.device)
+    a, r, c, s = dl(x), dl(_f32(range2, "range2")), dl(codes), dl(scale)
+    check_call(_lib().fq_qconv_quantize(a.ptr, r.ptr, c.ptr, s.ptr, current_stream()))
+    return codes, scale
+
+
+def qconv_dequantize(acc, s_in, s_w):
+    """nn/quantized_conv.py:74-76."""
+    acc = acc.contiguous()
+    y = torch.empty(acc.shape, dtype=torch.float32, device=acc.device)
+    a, si, sw, o = dl(acc), dl(s_in), dl(s_w), dl(y)
+    check_call(_lib().fq_qconv_dequantize(a.ptr, si.ptr, sw.ptr, o.ptr, current_stream()))
+    return y

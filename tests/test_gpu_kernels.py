@@ -1,0 +1,445 @@
+"""Parity tests proper: every kernel is called through the C ABI (ctypes -> libfq_b200.so) on the
+GPU and compared BIT FOR BIT with the CPU oracle on the same seeded inputs, and with the golden
+vectors the reference itself produced (tests/golden)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fq_oracle as O
+from oracle import golden_recipes as R
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+F32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from quantization.mxnet_b200 import ops as _ops
+    return _ops
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def bits_equal(a, b):
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype, (a.shape, b.shape, a.dtype, b.dtype)
+    if a.dtype.kind == "f":
+        ai = a.view(np.uint32 if a.dtype == np.float32 else np.uint64)
+        bi = b.view(np.uint32 if b.dtype == np.float32 else np.uint64)
+        # +0.0 / -0.0 are both acceptable nowhere: require identical bits except NaN payloads
+        same = (ai == bi) | (np.isnan(a) & np.isnan(b))
+    else:
+        same = a == b
+    if not same.all():
+        idx = np.argwhere(~same)[:5]
+        raise AssertionError("mismatch at %s: got %s want %s (%d of %d differ)" % (
+            idx.tolist(), a[tuple(idx.T)], b[tuple(idx.T)], (~same).sum(), same.size))
+
+
+def rng(seed):
+    return np.random.RandomState(seed)
+
+
+# ---------------------------------------------------------------------------------------------
+# K1
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,L", [(1, 1), (1, 1000), (1, 3_000_001), (128, 4096), (128, 50176), (1024, 9),
+                                    (7, 4099), (64, 36864), (256, 64), (3, 2047), (3, 2048), (512, 4608)])
+def test_absmax_rows(ops, rows, L):
+    x = (rng(rows * 7 + L).standard_normal((rows, L)) * 3).astype(F32)
+    got = host(ops.absmax_rows(dev(x), rows))
+    bits_equal(got, O.absmax_rows(x, rows))
+    # workspace invariant: a second call must give the same answer
+    bits_equal(host(ops.absmax_rows(dev(x), rows)), O.absmax_rows(x, rows))
+
+
+def test_absmax_unaligned_view(ops):
+    x = rng(5).standard_normal(100_003).astype(F32)
+    t = dev(x)[3:]          # 12-byte offset: scalar head path
+    bits_equal(host(ops.absmax_rows(t, 1)), O.absmax_rows(x[3:], 1))
+
+
+@pytest.mark.parametrize("n", [1, 5, 4096, 1_000_003])
+def test_minmax(ops, n):
+    x = rng(n).standard_normal(n).astype(F32)
+    lo, hi = O.minmax(x)
+    bits_equal(host(ops.minmax(dev(x))), np.array([lo, hi], dtype=F32))
+
+
+@pytest.mark.parametrize("n", [1, 2, 128, 256, 1000, 5000])
+def test_mean_kahan(ops, n):
+    v = np.abs(rng(n).standard_normal(n) * 10).astype(F32)
+    bits_equal(host(ops.mean_kahan(dev(v))), np.array([O.mean_kahan_f32(v)], dtype=F32))
+
+
+@pytest.mark.parametrize("shape", [(128, 16, 32, 32), (128, 64, 8, 8), (256, 64), (128, 1024), (2, 3, 5, 5),
+                                   (32, 32, 56, 56), (5, 7, 11, 13)])
+def test_input_range(ops, shape):
+    x = (rng(sum(shape)).standard_normal(shape) * 2).astype(F32)
+    cur, per = O.input_range(x)
+    ps = torch.empty(shape[0], dtype=torch.float32, device="cuda")
+    got = ops.input_range(dev(x), per_sample=ps)
+    bits_equal(host(got), np.array([cur], dtype=F32))
+    bits_equal(host(ps), per)
+
+
+@pytest.mark.parametrize("promotion", ["legacy", "nep50"])
+@pytest.mark.parametrize("signed", [False, True])
+def test_scale_from_max(ops, promotion, signed):
+    r = rng(11)
+    maxes = np.concatenate([np.abs(r.standard_normal(300)).astype(F32) * F32(7), np.array([0, 1e-38, 1e-30, 255, 6, 1e20], F32)])
+    for bits in (2, 3, 4, 5, 6, 8, 12, 16):
+        for lo_mode, layer in ((ops.LO_NEG_MAX if signed else ops.LO_ZERO, "conv"), (ops.LO_ZERO, "dense")):
+            for m in maxes[:: 7 if bits not in (4, 8) else 1]:
+                want = np.array(O.input_qparams(m, bits, signed, promotion, layer), dtype=F32)
+                got = host(ops.scale_from_max(dev(np.array([m], F32)), bits, signed, lo_mode, promotion=promotion))
+                bits_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------
+# K2
+# ---------------------------------------------------------------------------------------------
+def tie_heavy(seed, n, d):
+    """Values exactly on and next to rounding ties (k + 0.5) * d, plus random ones."""
+    r = rng(seed)
+    k = r.randint(-300, 300, n).astype(F32)
+    x = ((k + F32(0.5)) * F32(d)).astype(F32)
+    x[::3] = np.nextafter(x[::3], F32(np.inf))
+    x[1::3] = np.nextafter(x[1::3], F32(-np.inf))
+    x[::5] = (r.standard_normal(len(x[::5])) * 100 * d).astype(F32)
+    return x
+
+
+@pytest.mark.parametrize("bits,signed", [(8, False), (8, True), (4, False), (4, True), (2, True), (3, False),
+                                         (16, False), (16, True), (6, True), (5, False), (12, True)])
+@pytest.mark.parametrize("promotion", ["legacy", "nep50"])
+def test_forward_scalar_device_qparams(ops, bits, signed, promotion):
+    n = 70_001
+    for max_ in (F32(2.5), F32(0.0), F32(1e-30), F32(6.0), F32(317.77)):
+        d, s, lo, hi = O.input_qparams(max_, bits, signed, promotion)
+        x = tie_heavy(bits, n, float(d) if d > 0 else 1.0)
+        x[:4] = [max_, -max_, 0.0, -0.0]
+        y, code = O.fake_quant_scalar(x, d, s, lo, hi)
+        qp = ops.scale_from_max(dev(np.array([max_], F32)), bits, signed, ops.LO_NEG_MAX if signed else ops.LO_ZERO,
+                                promotion=promotion)
+        cdt = torch.int32
+        gy, gc = ops.forward_scalar(dev(x), qp, codes_dtype=cdt)
+        bits_equal(host(gy), y)
+        assert np.array_equal(host(gc), code.astype(np.int32))
+
+
+@pytest.mark.parametrize("cdt,bits,signed", [(torch.int8, 8, True), (torch.uint8, 8, False), (torch.int16, 16, True),
+                                             (torch.uint16, 16, False), (torch.float32, 8, False)])
+def test_forward_scalar_code_dtypes(ops, cdt, bits, signed):
+    x = (rng(3).standard_normal(40_000) * 2).astype(F32)
+    d, s, lo, hi = O.input_qparams(F32(2.0), bits, signed, "legacy")
+    y, code = O.fake_quant_scalar(x, d, s, lo, hi)
+    gy, gc = ops.forward_scalar_host(dev(x), float(d), float(s), float(lo), float(hi), True, codes_dtype=cdt)
+    bits_equal(host(gy), y)
+    gcn = gc.cpu().view(torch.int16).numpy().view(np.uint16) if cdt == torch.uint16 else host(gc)
+    assert np.array_equal(gcn.astype(np.int64), code.astype(np.int64))
+
+
+def test_forward_scalar_noclip_and_unaligned(ops):
+    x = (rng(4).standard_normal(10_007) * 5).astype(F32)
+    y, _ = O.fake_quant_scalar(x, F32(0.0173), F32(0.0172))
+    bits_equal(host(ops.forward_scalar_host(dev(x), 0.0173, 0.0172, clip=False)), y)
+    t = dev(x)[1:]           # misaligned input -> scalar kernel
+    y2, _ = O.fake_quant_scalar(x[1:], F32(0.0173), F32(0.0172), F32(-1), F32(1))
+    bits_equal(host(ops.forward_scalar_host(t, 0.0173, 0.0172, -1.0, 1.0, True)), y2)
+
+
+def test_forward_scalar_empty(ops):
+    x = torch.empty(0, dtype=torch.float32, device="cuda")
+    assert ops.forward_scalar_host(x, 1.0, 1.0).numel() == 0
+
+
+@pytest.mark.parametrize("rows,L", [(1, 5000), (64, 36864), (1024, 9), (512, 4608), (32, 1027), (10, 64), (7, 4099)])
+@pytest.mark.parametrize("bits", [8, 4, 2])
+def test_forward_rows(ops, rows, L, bits):
+    w = (rng(rows + L + bits).standard_normal((rows, L)) * 0.1).astype(F32)
+    w[0, 0] = 0
+    s, d, _ = O.weight_scales(w, rows, bits)
+    y, code = O.fake_quant_rows(w, rows, s, d)
+    gy, gc = ops.forward_rows(dev(w), dev(s), codes_dtype=torch.int8)
+    bits_equal(host(gy), y)
+    assert np.array_equal(host(gc), code.astype(np.int8))
+
+
+@pytest.mark.parametrize("shape", [(128, 16, 32, 32), (128, 64), (4, 3, 5, 5), (64, 32, 28, 28), (16, 96, 56, 56)])
+@pytest.mark.parametrize("bits,signed,layer", [(8, False, "conv"), (8, True, "conv"), (4, True, "dense"), (4, False, "conv")])
+@pytest.mark.parametrize("promotion", ["legacy", "nep50"])
+def test_forward_online(ops, shape, bits, signed, layer, promotion):
+    x = (rng(sum(shape) + bits).standard_normal(shape) * 1.7).astype(F32)
+    if not signed:
+        x = np.maximum(x, 0)
+    y, code, cur, qp = O.fake_quant_input(x, bits, signed, None, promotion, layer)
+    lo_mode = ops.LO_NEG_MAX if (signed and layer == "conv") else ops.LO_ZERO
+    gy, gcur, gqp, gc = ops.forward_online(dev(x), bits, signed, lo_mode, promotion=promotion, codes_dtype=torch.int32)
+    bits_equal(host(gcur), np.array([cur], F32))
+    bits_equal(host(gqp), np.array(qp, F32))
+    bits_equal(host(gy), y)
+    assert np.array_equal(host(gc), code.astype(np.int32))
+    # repeat: the workspace must have been left clean
+    gy2, _, _ = ops.forward_online(dev(x), bits, signed, lo_mode, promotion=promotion)
+    bits_equal(host(gy2), y)
+
+
+@pytest.mark.parametrize("shape", [(128, 16, 32, 32), (128, 64), (8, 32, 56, 56)])
+def test_forward_online_offline_range_and_tracking(ops, shape):
+    x = np.maximum(rng(9).standard_normal(shape), 0).astype(F32)
+    imax = F32(1.25)
+    y, code, cur, qp = O.fake_quant_input(x, 8, False, imax, "legacy", "conv")
+    gy, gcur, gqp = ops.forward_online(dev(x), 8, False, ops.LO_ZERO, input_max=dev(np.array([imax], F32)))
+    bits_equal(host(gy), y)
+    bits_equal(host(gcur), np.array([cur], F32))
+    bits_equal(host(gqp), np.array(qp, F32))
+    # range tracking only (quantize_input switched off, convert_conv2d.py:55-57)
+    gy, gcur, _ = ops.forward_online(dev(x), 8, False, ops.LO_ZERO, quantize=False)
+    assert gy is None
+    bits_equal(host(gcur), np.array([cur], F32))
+
+
+WEIGHT_SHAPES = [(64, 3, 7, 7), (32, 1, 3, 3), (512, 512, 3, 3), (1000, 1024), (16, 16, 1, 1), (10, 64), (256, 64, 1, 1)]
+
+
+@pytest.mark.parametrize("shape", WEIGHT_SHAPES)
+@pytest.mark.parametrize("quant_type", ["layer", "channel"])
+@pytest.mark.parametrize("bits", [8, 4])
+def test_quant_weight(ops, shape, quant_type, bits):
+    w = (rng(sum(shape)).standard_normal(shape) * 0.05).astype(F32)
+    y, code, s = O.fake_quant_weight(w, bits, quant_type)
+    rows = shape[0] if quant_type == "channel" else 1
+    gy, _, gs, gc = ops.quant_weight(dev(w), rows, bits, codes_dtype=torch.int8)
+    bits_equal(host(gs), s)
+    bits_equal(host(gy), y)
+    assert np.array_equal(host(gc), code.astype(np.int8))
+    gy2, _, _ = ops.quant_weight(dev(w), rows, bits)
+    bits_equal(host(gy2), y)
+
+
+@pytest.mark.parametrize("shape", [(64, 3, 7, 7), (32, 1, 3, 3), (256, 256, 3, 3), (128, 64, 1, 1)])
+@pytest.mark.parametrize("rows_kind", ["layer", "channel", "fold_only"])
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_quant_weight_with_bn_fold(ops, shape, rows_kind, with_bias):
+    r = rng(sum(shape) + 1)
+    cout = shape[0]
+    w = (r.standard_normal(shape) * 0.05).astype(F32)
+    gamma = (1 + 0.3 * r.standard_normal(cout)).astype(F32)
+    beta = (0.1 * r.standard_normal(cout)).astype(F32)
+    mean = (0.2 * r.standard_normal(cout)).astype(F32)
+    var = np.abs(1 + 0.5 * r.standard_normal(cout)).astype(F32)
+    var[0] = 0.0                                   # eps 1e-10 path
+    bias = (0.05 * r.standard_normal(cout)).astype(F32) if with_bias else None
+    w2, b2 = O.fold_bn(w, bias, gamma, beta, mean, var)
+    args = dict(gamma=dev(gamma), beta=dev(beta), mean=dev(mean), var=dev(var), bias=None if bias is None else dev(bias))
+    if rows_kind == "fold_only":
+        gy, gb, _ = ops.quant_weight(dev(w), 1, 0, **args)
+        bits_equal(host(gy), w2)
+        bits_equal(host(gb), b2)
+        return
+    qt = rows_kind
+    y, code, s = O.fake_quant_weight(w2, 4, qt)
+    rows = cout if qt == "channel" else 1
+    gy, gb, gs = ops.quant_weight(dev(w), rows, 4, **args)
+    bits_equal(host(gb), b2)
+    bits_equal(host(gs), s)
+    bits_equal(host(gy), y)
+
+
+def test_quant_weight_group_rows(ops):
+    # rows = G with 1 < G < Cout: an extension (the reference's broadcast only allows G in {1, Cout})
+    w = (rng(8).standard_normal((32, 4, 3, 3)) * 0.1).astype(F32)
+    s, d, _ = O.weight_scales(w, 4, 8)
+    y, _ = O.fake_quant_rows(w, 4, s, d)
+    gy, _, gs = ops.quant_weight(dev(w), 4, 8)
+    bits_equal(host(gs), s)
+    bits_equal(host(gy), y)
+
+
+# ---------------------------------------------------------------------------------------------
+# K3 / K4
+# ---------------------------------------------------------------------------------------------
+def test_ste_backward(ops):
+    x = (rng(1).standard_normal(50_001) * 2).astype(F32)
+    dy = rng(2).standard_normal(50_001).astype(F32)
+    t = dev(dy)
+    assert ops.ste_backward(t) is t                         # identity: aliased, as ste_func.py:43-44
+    qp = dev(np.array([0.01, 0.01, -1.5, 1.5], F32))
+    got = host(ops.ste_backward(t, dev(x), qp, mode=ops.STE_CLIP_MASK))
+    bits_equal(got, O.ste_backward(dy, x, F32(-1.5), F32(1.5), "mask"))
+
+
+@pytest.mark.parametrize("promotion", ["legacy", "nep50"])
+def test_ema_update(ops, promotion):
+    r = rng(6)
+    state = np.abs(r.standard_normal(53)).astype(F32)
+    state[:3] = 0
+    for step in range(5):
+        cur = np.abs(r.standard_normal(53) * 3).astype(F32)
+        want = O.ema_scalar(state, cur, 0.9, promotion)
+        t = dev(state)
+        ops.ema_update(t, dev(cur), 0.9, True, promotion=promotion)
+        bits_equal(host(t), want)
+        state = want
+    cur = r.standard_normal(2048).astype(F32)
+    st = r.standard_normal(2048).astype(F32)
+    t = dev(st)
+    ops.ema_update(t, dev(cur), 0.9, False)
+    bits_equal(host(t), O.ema_tensor(st, cur, 0.9))
+
+
+# ---------------------------------------------------------------------------------------------
+# K5
+# ---------------------------------------------------------------------------------------------
+def gpu_hist_batches(ops, batches, bins, promotion):
+    counts = torch.zeros(bins + 1, dtype=torch.int64, device="cuda")
+    hist = torch.zeros(bins + 1, dtype=torch.float32, device="cuda")
+    seen = torch.zeros(1, dtype=torch.int32, device="cuda")
+    mx = None
+    per_batch = []
+    for b, fm in enumerate(batches):
+        t = dev(fm)
+        if mx is None:
+            mx = ops.minmax(t)[1:2].clone()
+        ops.hist_nonzero(t, mx, bins, counts, promotion=promotion)
+        per_batch.append(host(counts).copy())
+        ops.hist_accumulate(counts, hist, b == 0, seen)
+        assert int(counts.abs().sum()) == 0
+    return per_batch, host(hist), host(mx)[0], int(seen[0])
+
+
+@pytest.mark.parametrize("name", sorted(R.hist_cases().keys()))
+def test_histogram_vs_reference_golden(ops, name):
+    g = np.load(os.path.join(GOLD, "hist_nep50.npz"))
+    batches = R.hist_cases()[name]
+    if str(g["hist/%s/error" % name]):
+        batches = batches[:1]
+    per_batch, hist, mx, seen = gpu_hist_batches(ops, batches, R.BINS, "nep50")
+    assert F32(mx) == g["hist/%s/max" % name]
+    for b in range(len(batches)):
+        want = g["hist/%s/batch%d" % (name, b)]
+        got = per_batch[b]
+        assert np.array_equal(got[: len(want)], want.astype(np.int64)) and got[len(want):].sum() == 0
+    if not str(g["hist/%s/error" % name]):
+        want = g["hist/%s/acc" % name]
+        bits_equal(hist[: len(want)], want)
+        assert seen == (len(want) == R.BINS + 1)
+
+
+@pytest.mark.parametrize("promotion", ["legacy", "nep50"])
+def test_histogram_vs_oracle_both_regimes(ops, promotion):
+    for seed, sc in ((1, 1.0), (2, 37.3), (3, 300.0), (4, 1e-3)):
+        x = R.relu_normal(seed, 200_003, sc)
+        want = O.histogram_counts(x, R.BINS, x.max(), promotion)
+        per_batch, _, _, _ = gpu_hist_batches(ops, [x], R.BINS, promotion)
+        assert np.array_equal(per_batch[0][: len(want)], want)
+
+
+_KL = [(n, l) for n, ls in R.KL_LEVELS.items() for l in ls]
+
+
+@pytest.mark.parametrize("name,levels", _KL)
+def test_kl_search_vs_reference_golden(ops, name, levels):
+    g = np.load(os.path.join(GOLD, "kl_nep50.npz"))
+    h = g["kl/%s/hist" % name]
+    best, div = ops.kl_search(dev(h), levels, levels, R.BINS, promotion="nep50")
+    assert int(best[0]) == int(g["kl/%s/L%d/best" % (name, levels)])
+    want = O.kl_divergences(h, levels, levels, R.BINS, "nep50")
+    got = host(div)[0]
+    ok = np.isclose(got[levels:], want[levels:], rtol=1e-11, atol=1e-13, equal_nan=True)
+    assert ok.all(), (np.argwhere(~ok)[:5].tolist(), got[levels:][~ok][:5], want[levels:][~ok][:5])
+
+
+@pytest.mark.parametrize("name", ["relu", "huge_counts", "lognormal", "non_integer", "len2049"])
+def test_kl_search_legacy_regime_vs_oracle(ops, name):
+    h = R.kl_hist_cases()[name]
+    levels = R.KL_LEVELS[name][0]
+    best, div = ops.kl_search(dev(h), levels, levels, R.BINS, promotion="legacy")
+    want = O.kl_divergences(h, levels, levels, R.BINS, "legacy")
+    assert int(best[0]) == O.kl_calibrate(h, levels, levels, R.BINS, "legacy")
+    assert np.isclose(host(div)[0][levels:], want[levels:], rtol=1e-11, atol=1e-13, equal_nan=True).all()
+
+
+def test_kl_search_batched_windows_and_threshold(ops):
+    g = np.load(os.path.join(GOLD, "kl_nep50.npz"))
+    names = ["relu", "outliers", "lognormal"]
+    hs = np.stack([g["kl/%s/hist" % n] for n in names])
+    best, _ = ops.kl_search(dev(hs), 256, 256, R.BINS, promotion="nep50")
+    want = [int(g["kl/%s/L256/best" % n]) for n in names]
+    assert host(best).tolist() == want
+    mx = np.array([4.2, 37.5, 0.013], F32)
+    th = host(ops.kl_threshold(best, dev(mx), R.BINS))
+    bits_equal(th, np.array([O.kl_threshold(b, m, R.BINS) for b, m in zip(want, mx)], F32))
+
+
+def test_kl_search_rejects_bad_arguments(ops):
+    from quantization.mxnet_b200._ffi import FQError
+    h = torch.ones(2048, device="cuda")
+    with pytest.raises(FQError, match="min_bins should be greater than levels"):
+        ops.kl_search(h, 256, 128, 2048)
+    with pytest.raises(FQError, match="no CPU path"):
+        ops.absmax_rows(torch.ones(8), 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# K6
+# ---------------------------------------------------------------------------------------------
+def test_int8_export_and_qconv(ops):
+    w = (rng(12).standard_normal((64, 32, 3, 3)) * 0.2).astype(F32)
+    mx = F32(np.abs(w).max())
+    q, lo, hi = O.quantize_int8_export(w, -mx, mx)
+    gq, gr = ops.quantize_int8_export(dev(w), dev(np.array([-mx, mx], F32)))
+    assert np.array_equal(host(gq), q)
+    bits_equal(host(gr), np.array([lo, hi], F32))
+
+    x = rng(13).uniform(size=(2, 2, 7, 7)).astype(F32)
+    for out_type in ("int8", "uint8"):
+        codes, scale = O.qconv_quantize_auto(x, out_type)
+        rg = np.array([-np.abs(x).max(), np.abs(x).max()], F32) if out_type == "int8" else np.array(O.minmax(x), F32)
+        gc, gs = ops.qconv_quantize(dev(x), dev(rg))
+        assert np.array_equal(host(gc), codes)
+        bits_equal(host(gs), np.array([scale], F32))
+    acc = rng(14).randint(-2 ** 20, 2 ** 20, (4, 8, 5, 5)).astype(np.int32)
+    s_in, s_w = F32(0.0123), F32(0.00071)
+    got = host(ops.qconv_dequantize(dev(acc), dev(np.array([s_in], F32)), dev(np.array([s_w], F32))))
+    bits_equal(got, O.qconv_dequantize(acc, F32(s_in * s_w)))
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size properties (BASELINE config sizes; the oracle would take too long there)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties(ops):
+    n_samples, chw = 128, 64 * 112 * 112            # largest MobileNet-1.0 layer input: 102,760,448 elements
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(n_samples, chw, device="cuda", generator=g).clamp_(min=0)
+    y, cur, qp = ops.forward_online(x, 8, False, ops.LO_ZERO)
+    per = x.abs().amax(dim=1)
+    assert torch.equal(ops.absmax_rows(x, n_samples), per)
+    assert abs(float(cur) - float(per.double().mean())) < 1e-5 * float(cur)
+    # idempotence: quantising a quantised tensor with the same qparams changes nothing
+    y2 = ops.forward_scalar(y, qp)
+    assert torch.equal(y, y2)
+    # at most 256 distinct levels, all inside [0, hi]
+    assert y.min() >= 0 and float(y.max()) <= float(qp[3]) * (1 + 1e-6)
+    assert torch.unique(y).numel() <= 256
+    # histogram: checksum of counts == number of clipped non-zero elements
+    counts = torch.zeros(R.BINS + 1, dtype=torch.int64, device="cuda")
+    mx = ops.minmax(x)[1:2].clone()
+    ops.hist_nonzero(x, mx, R.BINS, counts)
+    assert int(counts.sum()) == int((x != 0).sum())
+    # linearity: hist(x) + hist(x) == 2 * hist(x)
+    c1 = counts.clone()
+    ops.hist_nonzero(x, mx, R.BINS, counts)
+    assert torch.equal(counts, 2 * c1)
