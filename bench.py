@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""Headline benchmark: KL calibration of MobileNet-1.0 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One *step* = one calibration batch of 128 synthetic 224x224 images: the 27 quantised-layer inputs
+(639,172,608 fp32 elements, 2.56 GB -- far larger than the 126 MB L2, so no flush is needed) are
+histogrammed into 2048(+1) bins and folded into the running float32 histograms.  A calibration is
+K such steps followed by ONE KL threshold search over the 27 layers and the threshold update; that
+closing search runs INSIDE the timed region.  ``value`` times this with the layer inputs resident
+in HBM; ``e2e`` times the user-facing calls (``collect_feature_maps`` + ``kl_calibrate_all``) fed
+from pinned host images, network forward, H2D and D2H included.
+
+``--impl reference`` times the reference's own CPU path for the same work (the oracle port of
+distribution_calibrate.py, all host cores) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BINS, LEVELS = 2048, 256
+BATCH = 128
+MODEL = "mobilenet1.0"
+METRIC = "kl_calibration_images_per_sec"
+N_LAYERS = 27
+ELEMS_PER_IMAGE = 4_993_536          # sum of the 27 layer-input sizes for one 224x224 image
+
+
+def workload_config(n_gpus, extra=None):
+    cfg = {
+        "workload": "mobilenet1.0 KL calibration: per-channel int8 weights, offline uint8 inputs, 2048-bin "
+                    "histograms of the 27 quantised-layer inputs of a synthetic 128x3x224x224 batch per GPU, "
+                    "one KL threshold search (levels=256) closing every K-step calibration inside the timed region",
+        "batch_per_gpu": BATCH, "bins": BINS, "levels": LEVELS, "layers": N_LAYERS,
+        "elements_per_step_per_gpu": ELEMS_PER_IMAGE * BATCH,
+        "l2": "inputs (2.56 GB per step) exceed the 126 MB L2; no flush needed",
+        "parallelism": "batch sharded over %d GPU(s); NCCL max-all-reduce of first-batch ranges, sum-all-reduce "
+                       "of the int64 counts once per step" % n_gpus,
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side (oracle port): only used for cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------------
+def layer_shapes():
+    """(C, H, W) of the 27 quantised-layer inputs of mobilenet1.0 at 224x224 (first conv excluded)."""
+    dw = [32, 64, 128, 128, 256, 256] + [512] * 6 + [1024]
+    ch = [64, 128, 128, 256, 256, 512] + [512] * 5 + [1024, 1024]
+    st = [1, 2, 1, 2, 1, 2, 1, 1, 1, 1, 1, 2, 1]
+    hw = 112
+    shapes = []
+    for d, c, s in zip(dw, ch, st):
+        shapes.append((d, hw, hw))          # depthwise input
+        hw //= s
+        shapes.append((d, hw, hw))          # pointwise input
+    shapes.append((1024, 1, 1))             # dense input
+    assert sum(c * h * w for c, h, w in shapes) == ELEMS_PER_IMAGE
+    return shapes
+
+
+_CPU_FMS = []        # per-layer sample activations, generated once in the parent and inherited by fork
+
+
+def _cpu_layer_hist(args):
+    from oracle import fq_oracle as O
+    i, fm_max = args
+    h, m = O.discrete_histogram(_CPU_FMS[i], BINS, fm_max)
+    return h, m
+
+
+def _cpu_layer_kl(hist):
+    from oracle import fq_oracle as O
+    return O.kl_calibrate(hist, LEVELS, LEVELS, BINS)
+
+
+def cpu_calibration(sample_images, steps, procs):
+    """`steps` sample batches through the oracle port, then one KL search of the 27 layers.
+    Returns (histogram seconds, KL seconds) of wall clock with `procs` worker processes; the
+    synthetic layer inputs are generated before the clock starts (the GPU arm's are resident too)."""
+    import multiprocessing as mp
+    import numpy as np
+    del _CPU_FMS[:]
+    for i, shp in enumerate(layer_shapes()):
+        r = np.random.RandomState(100 + i)
+        _CPU_FMS.append(np.maximum(r.standard_normal((sample_images,) + shp), 0).astype(np.float32))
+    hists, maxes = [0] * N_LAYERS, [None] * N_LAYERS
+    hist_wall = 0.0
+    with mp.get_context("fork").Pool(procs) as pool:
+        pool.map(_cpu_layer_kl, [np.ones(BINS, np.float32)] * procs)     # import + page-in, untimed
+        for s in range(steps):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_layer_hist, [(i, maxes[i]) for i in range(N_LAYERS)], chunksize=1)
+            hist_wall += time.perf_counter() - t0
+            for i, (h, m) in enumerate(res):
+                if maxes[i] is None:
+                    maxes[i] = m
+                hists[i] = hists[i] + h
+        t0 = time.perf_counter()
+        best = pool.map(_cpu_layer_kl, hists, chunksize=1)
+        kl_wall = time.perf_counter() - t0
+    return hist_wall, kl_wall, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    procs = os.cpu_count() or 1
+    sample_images = 4
+    if args.warmup > 0:
+        cpu_calibration(1, min(args.warmup, 2), procs)
+    hist_wall, kl_wall, _ = cpu_calibration(sample_images, args.steps, procs)
+    total = hist_wall + kl_wall
+    value = sample_images * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, {"sample": "%d images per step instead of %d" % (sample_images, BATCH)}),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": procs, "kind": "port",
+                         "sample": "oracle port of distribution_calibrate.py (_discrete_histogram + kl_calibrate), "
+                                   "%d-image batches x %d steps, layers spread over %d processes; "
+                                   "hist %.2fs, KL search %.2fs" % (sample_images, args.steps, procs, hist_wall, kl_wall)},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+def build_net(device):
+    import torch
+    from torch import nn
+    from quantization.mxnet_b200 import model_zoo as Z
+    from quantization.mxnet_b200.quantize import convert
+    from quantization.mxnet_b200.quantize.initialize import qparams_init
+    torch.manual_seed(7)
+    net = Z.get_model(MODEL, classes=1000).to(device).eval()
+    fn = {nn.Conv2d: convert.gen_conv2d_converter(quant_type="channel"),
+          nn.Linear: convert.gen_dense_converter(quant_type="channel"), nn.ReLU: None, nn.BatchNorm2d: None}
+    convert.convert_model(net, exclude=Z.default_exclusions(net, MODEL), convert_fn=fn)
+    qparams_init(net)
+    return net
+
+
+def capture_layer_inputs(net, X):
+    import torch
+    blocks = net.collect_quantized_blocks()
+    acts, hooks = [], []
+    for b in blocks:
+        hooks.append(b.register_forward_hook(lambda m, x, y: acts.append(x[0].detach().contiguous())))
+    with torch.no_grad():
+        net(X)
+    for h in hooks:
+        h.remove()
+    return acts
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from quantization.mxnet_b200 import ops
+    from quantization.mxnet_b200.quantize.distribution_calibrate import collect_feature_maps, kl_calibrate_all
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    K, W = args.steps, max(args.warmup, 1)
+
+    net = build_net(dev)
+    net.disable_quantize()           # calibrate with fp32 inputs and weights (simulate_quantization.py:298)
+    g = torch.Generator(device="cpu").manual_seed(7 + rank)
+    X_host = torch.randn(BATCH, 3, 224, 224, generator=g).pin_memory()
+    X = X_host.to(dev)
+    acts = capture_layer_inputs(net, X)
+    n_elems = sum(a.numel() for a in acts)
+    assert len(acts) == N_LAYERS and n_elems == ELEMS_PER_IMAGE * BATCH, (len(acts), n_elems)
+
+    counts = torch.zeros(N_LAYERS, BINS + 1, dtype=torch.int64, device=dev)
+    hist = torch.zeros(N_LAYERS, BINS + 1, dtype=torch.float32, device=dev)
+    minmax = torch.zeros(N_LAYERS, 2, dtype=torch.float32, device=dev)
+    div = torch.empty(N_LAYERS, BINS, dtype=torch.float64, device=dev)
+    thresholds = torch.empty(N_LAYERS, dtype=torch.float32, device=dev)
+    launches = [0]
+
+    def step(first, ev=None):
+        if first:
+            for i, a in enumerate(acts):
+                ops.minmax(a, out=minmax[i])
+            if world > 1:
+                mx = minmax[:, 1].contiguous()
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                minmax[:, 1].copy_(mx)
+        if ev is not None:
+            ev[0].record()
+        for i, a in enumerate(acts):
+            ops.hist_nonzero(a, minmax[i, 1:2], BINS, counts[i], promotion="nep50")
+        if ev is not None:
+            ev[1].record()
+        if world > 1:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        ops.hist_accumulate(counts.view(-1), hist.view(-1), first)
+        launches[0] += N_LAYERS + 1
+
+    def kl_close():
+        best, _ = ops.kl_search(hist[:, :BINS], LEVELS, LEVELS, BINS, promotion="nep50", divergence=div)
+        ops.kl_threshold(best, minmax[:, 1].contiguous(), BINS, out=thresholds)
+        launches[0] += 3
+        return best
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(W):
+        step(w == 0)
+    kl_close()
+    barrier()
+
+    clocks = ClockSampler(local).start() if rank == 0 else None
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t_start, t_kl, t_end = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    launches[0] = 0
+    barrier()
+    t_start.record()
+    for k in range(K):
+        step(False, evs[k])
+    t_kl.record()
+    best = kl_close()
+    t_end.record()
+    barrier()
+    total_ms = t_start.elapsed_time(t_end)
+    kl_ms = t_kl.elapsed_time(t_end)
+    hist_ms = sum(a.elapsed_time(b) for a, b in evs)
+    tm = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tm)
+    value = world * BATCH * K / (total_ms_max * 1e-3)
+
+    # ---- e2e through the public API with host buffers -------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        class Loader:
+            def __init__(self, n):
+                self.n = n
+
+            def __len__(self):
+                return self.n
+
+            def __iter__(self):
+                for _ in range(self.n):
+                    yield X_host, None
+
+        def calibrate(nb):
+            hc, mc = collect_feature_maps(net, BINS, Loader(nb), ctx=dev, tqdm_desc="e2e")
+            b, th = kl_calibrate_all(hc, LEVELS, LEVELS, BINS, fm_max=mc)
+            return th.cpu()
+        os.environ.setdefault("TQDM_DISABLE", "1")
+        calibrate(2)
+        barrier()
+        t0 = time.perf_counter()
+        th = calibrate(K)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * BATCH * K / float(tt), "unit": "images/s",
+               "h2d_bytes_per_step": X_host.numel() * 4,
+               "d2h_bytes_per_step": (N_LAYERS * (BINS + 1) * 4 + N_LAYERS * 12 + N_LAYERS * 4) / K,
+               "ms_per_step": 1e3 * float(tt) / K,
+               "api": "quantize.distribution_calibrate.collect_feature_maps + kl_calibrate_all on the torch "
+                      "mobilenet1.0 (fp32 cuDNN forward included), pinned host images"}
+        barrier()
+    clock_info = clocks.stop() if clocks is not None else None
+
+    if rank == 0:
+        import numpy as np
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_kind = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_kind = 6650.0, "fallback"
+        per_launch_bytes = 4.0 * n_elems / N_LAYERS
+        per_launch_s = hist_ms * 1e-3 / (K * N_LAYERS)
+        achieved = per_launch_bytes / per_launch_s / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "hist_kernel_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        # CPU baseline on a bounded sample (single process = what the reference's NumPy code uses)
+        cpu = None
+        if not args.no_cpu:
+            sample_images, cpu_steps = 2, 1
+            hw, klw, cpu_best = cpu_calibration(sample_images, cpu_steps, 1)
+            # same amortisation as the GPU arm: K batches share one KL search
+            per_image = hw / (sample_images * cpu_steps) + klw / (BATCH * K)
+            cpu = {"value": 1.0 / per_image, "unit": "images/s", "cores": 1, "kind": "port",
+                   "sample": "oracle port of distribution_calibrate.py on %d synthetic images x 27 layers "
+                             "(hist %.2fs) + KL search of 27 layers (%.2fs) amortised over K=%d batches of %d" %
+                             (sample_images, hw, klw, K, BATCH)}
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "roofline": {"bound": "hbm", "kernel": "fq::hist_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
+                         "frac_of_nominal_8000": achieved / 8000.0,
+                         "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_us": per_launch_s * 1e6},
+            "breakdown_ms": {"hist_per_step": hist_ms / K, "kl_search_once": kl_ms, "total": total_ms_max},
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clock_info, "gpu_launches": launches[0],
+            "kl_best_bins_head": [int(b) for b in best[:4].cpu()],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,184 @@
+"""Conv2D converter (convert_conv2d.py of the reference) over torch.nn.Conv2d.
+
+The patched forward keeps the reference's control flow and per-block state (``quantize_args``,
+``fixed_params`` tri-state, ``enable_quantize``, ``quantize_input``, ``quantize_input_offline``,
+``current_input_max``, Parameter ``input_max``; fake-BN ``gamma/beta/running_mean/running_var``),
+but each tensor is touched by ONE fused kernel launch and nothing is read back to the host:
+``current_input_max`` is a (1,) device tensor instead of a Python float.
+"""
+import types
+from collections import namedtuple
+
+import torch
+from torch import nn
+
+from ... import ops
+
+__all__ = ['gen_conv2d_converter']
+
+QuantizedArgs = namedtuple("ConvQuantizedArgs",
+                           "quantize_input in_signed in_width "
+                           "wt_width quant_type "
+                           "fake_bn wino_quantize")
+
+
+class _InputPath(torch.autograd.Function):
+    """convert_conv2d.py:56-66 in one launch; backward = identity (ste_func.py:43-44)."""
+
+    @staticmethod
+    def forward(ctx, x, m, lo_mode):
+        qa = m.quantize_args
+        y, _, _ = ops.forward_online(
+            x, qa.in_width, qa.in_signed, lo_mode,
+            input_max=m.input_max.data if m.quantize_input_offline else None,
+            quantize=True, cur_max=m.current_input_max, qparams=m._fq_qparams,
+            per_sample=getattr(m, "_fq_per_sample", None))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, None, None
+
+
+class _WeightPath(torch.autograd.Function):
+    """convert_conv2d.py:47-51 (fake-BN fold) + :70-95 (range, scale, fake-quant) in one launch.
+
+    Backward: identity through the quantiser, then the fold's chain rule in the op order MXNet's
+    autograd would replay ((W * gamma) / sd ; gamma * (b - mean) / sd + beta)."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, gamma, beta, mean, var, rows, bits):
+        fold = gamma is not None
+        wq, bq, _ = ops.quant_weight(weight, rows, bits, gamma, beta, mean, var, bias)
+        ctx.fold = fold
+        ctx.has_bias = bias is not None
+        if fold:
+            ctx.save_for_backward(weight, bias if bias is not None else torch.zeros_like(gamma), gamma, mean, var)
+            return wq, bq
+        return wq, bias
+
+    @staticmethod
+    def backward(ctx, dwq, dbq):
+        if not ctx.fold:
+            return dwq, dbq, None, None, None, None, None, None
+        weight, bias, gamma, mean, var = ctx.saved_tensors
+        cout = weight.shape[0]
+        sd = torch.sqrt(var + 1e-10)
+        da = dwq.reshape(cout, -1) / sd.reshape(-1, 1)
+        dweight = (da * gamma.reshape(-1, 1)).reshape(weight.shape)
+        dgamma = (da * weight.reshape(cout, -1)).sum(dim=1)
+        dbias = dbeta = None
+        if dbq is not None:
+            dn = dbq / sd
+            dgamma = dgamma + dn * (bias - mean)
+            dbias = dn * gamma if ctx.has_bias else None
+            dbeta = dbq
+        return dweight, dbias, dgamma, dbeta, None, None, None, None
+
+
+def _weight_rows(m):
+    qt = m.quantize_args.quant_type
+    if qt == 'channel':
+        return m.out_channels
+    if qt == 'group':
+        return m.groups
+    return 1
+
+
+def _conv2d_forward(self, x):
+    qa = self.quantize_args
+    weight, bias = self.weight, self.bias
+    fold = self.fixed_params != 1 and qa.fake_bn
+    if qa.wino_quantize != 'none' and qa.quant_type == 'channel' and tuple(self.kernel_size) == (3, 3):
+        raise NotImplementedError("Winograd-domain weight quantisation is outside the B200 hot path (SURVEY 8f)")
+
+    if self.enable_quantize:
+        # Quantize input (convert_conv2d.py:55-66)
+        if qa.quantize_input:
+            if self.quantize_input:
+                lo_mode = ops.LO_NEG_MAX if qa.in_signed else ops.LO_ZERO
+                x = _InputPath.apply(x, self, lo_mode)
+            else:       # the range is still tracked (convert_conv2d.py:56)
+                ops.forward_online(x.detach(), qa.in_width, qa.in_signed, ops.LO_ZERO, quantize=False,
+                                   cur_max=self.current_input_max, per_sample=getattr(self, "_fq_per_sample", None))
+        # Simulate quantization for weight (:69-97)
+        if self.fixed_params != 1:
+            if fold:
+                weight_q, bias = _WeightPath.apply(weight, bias, self.gamma, self.beta, self.running_mean,
+                                                   self.running_var, _weight_rows(self), qa.wt_width)
+            else:
+                weight_q, bias = _WeightPath.apply(weight, bias, None, None, None, None, _weight_rows(self),
+                                                   qa.wt_width)
+        else:
+            weight_q = weight
+    else:
+        if fold:       # fold only (:47-51 runs even when quantisation is disabled)
+            weight_q, bias = _WeightPath.apply(weight, bias, self.gamma, self.beta, self.running_mean,
+                                               self.running_var, 1, 0)
+        else:
+            weight_q = weight
+
+    if self.fixed_params == 0:      # :101-105
+        self.fixed_params = 1
+        with torch.no_grad():
+            self.weight.copy_(weight_q)
+            if bias is not None:
+                self.bias.copy_(bias)
+
+    # Normal convolution
+    return self.origin_forward(x, weight_q, bias)
+
+
+def _add_quantize_input_params(m):
+    m.quantize_input_offline = False
+    dev = m.weight.device
+    # non-persistent buffers follow .cuda()/.to() but stay out of the state dict, like the reference's
+    # plain attribute (current_input_max is not checkpointed)
+    m.register_buffer("current_input_max", torch.zeros(1, dtype=torch.float32, device=dev), persistent=False)
+    m.register_parameter("input_max", nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev),
+                                                   requires_grad=False))
+    m.register_buffer("_fq_qparams", torch.zeros(4, dtype=torch.float32, device=dev), persistent=False)
+
+
+def _add_fake_bn_params(m):
+    c, dev = m.out_channels, m.weight.device
+    m.register_parameter("gamma", nn.Parameter(torch.ones(c, device=dev)))
+    m.register_parameter("beta", nn.Parameter(torch.zeros(c, device=dev)))
+    m.register_parameter("running_mean", nn.Parameter(torch.zeros(c, device=dev), requires_grad=False))
+    m.register_parameter("running_var", nn.Parameter(torch.ones(c, device=dev), requires_grad=False))
+
+
+def _add_fake_bn_ema_hook(m):
+    """convert_conv2d.py:144-154: batch statistics of the RAW convolution output for the EMA."""
+    def _ema_hook(m, x):
+        with torch.no_grad():
+            y = m.origin_forward(x[0], m.weight, m.bias)
+            num_samples = y.shape[0] * y.shape[2] * y.shape[3]
+            m.current_mean = y.sum(dim=(0, 2, 3)) / num_samples
+            diff_square = (y - m.current_mean.reshape(1, -1, 1, 1)) ** 2
+            m.current_var = diff_square.sum(dim=(0, 2, 3)) / num_samples
+    m.register_forward_pre_hook(_ema_hook)
+
+
+def gen_conv2d_converter(weight_width=8, quant_type="layer",
+                         quantize_input=True, input_signed=False, input_width=8,
+                         fake_bn=False, wino_quantize="none"):
+    assert wino_quantize in ("none", "F23", "F43", "F63")
+
+    def _converter(m):
+        assert isinstance(m, nn.Conv2d)
+
+        if quantize_input:
+            _add_quantize_input_params(m)
+        if fake_bn:
+            _add_fake_bn_params(m)
+            _add_fake_bn_ema_hook(m)
+        m.origin_forward = m._conv_forward
+        m.forward = types.MethodType(_conv2d_forward, m)
+        m.quantize_args = QuantizedArgs(in_signed=input_signed, in_width=input_width, wt_width=weight_width,
+                                        quantize_input=quantize_input, fake_bn=fake_bn, quant_type=quant_type,
+                                        wino_quantize=wino_quantize)
+        m.fixed_params = -1
+        m.enable_quantize = True
+        m.quantize_input = quantize_input
+    return _converter

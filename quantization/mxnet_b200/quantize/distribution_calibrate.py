@@ -1,0 +1,199 @@
+"""KL calibration (quantize/distribution_calibrate.py of the reference), device resident.
+
+The reference copies every hooked layer input to the host (``x.asnumpy()``), histograms it with six
+single-threaded NumPy passes and searches the threshold in a pure-Python O(bins^2) loop.  Here the
+forward hook launches one histogram kernel on the activation where it lives (4 B/element, read
+once), per-batch counts of ALL layers are folded into the float32 histograms by one launch, and the
+KL search runs one CUDA block per candidate threshold.  With ``torch.distributed`` initialised the
+batch is sharded across ranks: first-batch maxima are max-all-reduced and the integer counts
+sum-all-reduced once per batch, so every rank ends with bit-identical histograms.
+
+Reference behaviours kept: the first batch's max is frozen for all later batches (:97-101); zeros
+are ignored (:40); float32 accumulation in batch order (:47,:103-104); the 2049th bin when
+``max_ >= 256`` (and the ValueError when only some batches have it); the asserts of :35-36.
+"""
+import numpy as np
+import torch
+from tqdm import tqdm
+
+from .. import ops
+
+__all__ = ['collect_feature_maps', 'kl_calibrate', 'kl_calibrate_all']
+
+
+def _dist_group(group):
+    import torch.distributed as dist
+    if group is not None:
+        return dist, group
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist, dist.group.WORLD
+    return None, None
+
+
+class _Collector(dict):
+    """dict(block -> numpy value) that also keeps the device-resident stack (``.device``) so that a
+    following :func:`kl_calibrate_all` does not upload anything."""
+    device = None
+    order = ()
+
+
+def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", group=None):
+    """
+    Collect feature maps and record discrete histograms.
+    :param net: converted torch.nn.Module
+    :param bins: int
+        Number of bins to generate discrete histograms.
+    :param loader: iterable of (X, y) batches
+    :param ctx: torch.device (or None: keep X where it is)
+    :return: (hist_collector, fm_max_collector) keyed by block, values numpy float32 histogram /
+        numpy.float32 max, as in the reference.
+    """
+    quantized_blocks = net.collect_quantized_blocks()
+    n_blk = len(quantized_blocks)
+    index = {id(b): i for i, b in enumerate(quantized_blocks)}
+    dist, group = _dist_group(group)
+
+    state = {}      # allocated on the first hooked tensor's device
+
+    def _alloc(dev):
+        state["counts"] = torch.zeros(n_blk, bins + 1, dtype=torch.int64, device=dev)
+        state["hist"] = torch.zeros(n_blk, bins + 1, dtype=torch.float32, device=dev)
+        state["minmax"] = torch.zeros(n_blk, 2, dtype=torch.float32, device=dev)
+        state["seen_last"] = torch.zeros(1, dtype=torch.int32, device=dev)
+        state["seen_hist"] = []
+
+    """ Add hooks to quantized blocks """
+    hooks = []
+    first_batch = {}        # block index -> inputs seen in batch 0 (kept until its max is known)
+    called = set()
+    n_batches = 0
+
+    def _collect(m, x, y):
+        x = x[0].detach()
+        if not state:
+            _alloc(x.device)
+        i = index[id(m)]
+        called.add(i)
+        if n_batches == 0:
+            first_batch.setdefault(i, []).append(x)
+        else:
+            ops.hist_nonzero(x, state["minmax"][i, 1:2], bins, state["counts"][i])
+    for blk in quantized_blocks:
+        hooks.append(blk.register_forward_hook(_collect))
+
+    """ Collect feature maps """
+    try:
+        with tqdm(total=len(loader), desc=tqdm_desc, disable=None) as pbar, torch.no_grad():
+            for X, _ in loader:
+                if ctx is not None:
+                    X = X.to(ctx, non_blocking=True)
+                _ = net(X)
+                if n_batches == 0:
+                    # First chunk: min/max of everything the block saw, then its histogram
+                    for i, xs in first_batch.items():
+                        mm = state["minmax"][i]
+                        ops.minmax(xs[0], out=mm)
+                        for extra in xs[1:]:
+                            mm2 = ops.minmax(extra)
+                            mm[0:1].copy_(torch.minimum(mm[0:1], mm2[0:1]))
+                            mm[1:2].copy_(torch.maximum(mm[1:2], mm2[1:2]))
+                    if dist is not None:
+                        mx = state["minmax"][:, 1].contiguous()
+                        mn = state["minmax"][:, 0].contiguous()
+                        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+                        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
+                        state["minmax"][:, 1].copy_(mx)
+                        state["minmax"][:, 0].copy_(mn)
+                    for i, xs in first_batch.items():
+                        for x in xs:
+                            ops.hist_nonzero(x, state["minmax"][i, 1:2], bins, state["counts"][i])
+                    first_batch.clear()
+                if state:
+                    if dist is not None:
+                        dist.all_reduce(state["counts"], op=dist.ReduceOp.SUM, group=group)
+                    # hist_collector[m] = last_hist + hist.astype(float32), all blocks in one launch
+                    state["seen_last"].zero_()
+                    _accumulate(state, n_batches == 0, bins)
+                n_batches += 1
+                pbar.update(1)
+    finally:
+        """ Delete hooks """
+        for h in hooks:
+            h.remove()
+
+    hist_collector, fm_max_collector = _Collector(), _Collector()
+    if not state:
+        return hist_collector, fm_max_collector
+
+    # one device->host transfer for everything, then the reference's deferred checks
+    hist = state["hist"].cpu().numpy()
+    minmax = state["minmax"].cpu().numpy()
+    seen = torch.stack(state["seen_hist"]).cpu().numpy() if state["seen_hist"] else np.zeros((0, n_blk), np.int32)
+    for i, m in enumerate(quantized_blocks):
+        if i not in called:
+            continue
+        assert minmax[i, 0] >= 0., "Activation should >=0"
+        assert minmax[i, 1] > 0, "Bad distribution: all zero-value"
+        col = seen[:, i]
+        if col.any() and not col.all():
+            # np.bincount gave 2049 bins for some batches and 2048 for others: `last_hist + hist` raises
+            raise ValueError("operands could not be broadcast together with shapes (%d,) (%d,)" % (bins, bins + 1))
+        n = bins + 1 if col.any() else bins
+        hist_collector[m] = hist[i, :n].copy()
+        fm_max_collector[m] = np.float32(minmax[i, 1])
+    hist_collector.device = state["hist"]
+    hist_collector.order = tuple(quantized_blocks)
+    fm_max_collector.device = state["minmax"][:, 1].contiguous()
+    fm_max_collector.order = tuple(quantized_blocks)
+    return hist_collector, fm_max_collector
+
+
+def _accumulate(state, first, bins):
+    counts, hist = state["counts"], state["hist"]
+    n_blk = counts.shape[0]
+    # per-block flag "this batch produced a 2049th bin" (deferred length check)
+    state["seen_hist"].append((counts[:, bins] != 0).to(torch.int32))
+    ops.hist_accumulate(counts.view(-1), hist.view(-1), first, None)
+    assert n_blk == hist.shape[0]
+
+
+def kl_calibrate(data, levels, min_bins, bins):
+    """
+    KL-divergence calibration for offline-quantization (one histogram).
+    :param data: numpy.ndarray or torch.Tensor, discrete histogram (length bins or bins + 1)
+    :return: int, best threshold bin.
+    """
+    assert min_bins >= levels, f"min_bins should be greater than levels ({min_bins} vs. {levels})"
+    if isinstance(data, np.ndarray):
+        data = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).cuda()
+    best, _ = ops.kl_search(data.reshape(1, -1), levels, min_bins, bins)
+    return int(best[0])
+
+
+def kl_calibrate_all(hists, levels, min_bins, bins, fm_max=None):
+    """All layers at once: ``hists`` is a [layers, n] tensor (or a hist_collector from
+    :func:`collect_feature_maps`).  Returns int32 best bins on the device and, when ``fm_max`` is
+    given, the float32 thresholds ``(best + 0.5) * (fm_max / bins)`` (simulate_quantization.py:310)."""
+    assert min_bins >= levels, f"min_bins should be greater than levels ({min_bins} vs. {levels})"
+    if isinstance(hists, _Collector):
+        dev_h = hists.device
+        lens = {len(v) for v in hists.values()}
+        # a stack can only be searched in one launch when every histogram has the same length
+        if len(lens) == 1:
+            n = lens.pop()
+            hists = dev_h[:, :n].contiguous()
+        else:
+            outs = [kl_calibrate_all(dev_h[i:i + 1, :len(hists[m])].contiguous(), levels, min_bins, bins)
+                    for i, m in enumerate(hists.order)]
+            best = torch.cat(outs)
+            return (best, ops.kl_threshold(best, _max_of(fm_max), bins)) if fm_max is not None else best
+    best, _ = ops.kl_search(hists, levels, min_bins, bins)
+    if fm_max is None:
+        return best
+    return best, ops.kl_threshold(best, _max_of(fm_max), bins)
+
+
+def _max_of(fm_max):
+    if isinstance(fm_max, _Collector):
+        return fm_max.device
+    return fm_max

@@ -1,0 +1,305 @@
+"""Drop-in API on the GPU vs. the oracle: the converted networks of BASELINE's configs run the
+reference's flows (simulate_quantization.py) with every fake-quant tensor checked bit for bit."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from oracle import fq_oracle as O
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def Q():
+    import types
+    from quantization.mxnet_b200 import model_zoo, ops
+    from quantization.mxnet_b200.quantize import convert, distribution_calibrate, freeze, initialize, utils
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return types.SimpleNamespace(zoo=model_zoo, ops=ops, convert=convert, dc=distribution_calibrate, freeze=freeze,
+                                 init=initialize, utils=utils)
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def build(Q, name, classes, seed=7, **conv_kwargs):
+    torch.manual_seed(seed)
+    net = Q.zoo.get_model(name, classes=classes).eval()
+    # non-trivial BatchNorm statistics so that folding is exercised
+    g = torch.Generator().manual_seed(seed + 1)
+    for m in net.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.running_mean.copy_(0.1 * torch.randn(m.num_features, generator=g))
+            m.running_var.copy_(1 + 0.2 * torch.rand(m.num_features, generator=g))
+            m.weight.data.copy_(1 + 0.1 * torch.randn(m.num_features, generator=g))
+            m.bias.data.copy_(0.1 * torch.randn(m.num_features, generator=g))
+    ref = copy.deepcopy(net)
+    net = net.cuda()
+    dense_kwargs = {k: v for k, v in conv_kwargs.items() if k in ("weight_width", "input_signed", "input_width",
+                                                                  "quantize_input", "quant_type")}
+    fn = {nn.Conv2d: Q.convert.gen_conv2d_converter(**conv_kwargs), nn.Linear: Q.convert.gen_dense_converter(**dense_kwargs),
+          nn.ReLU: None, nn.BatchNorm2d: Q.convert.bypass_bn if conv_kwargs.get("fake_bn") else None}
+    Q.convert.convert_model(net, exclude=Q.zoo.default_exclusions(net, name), convert_fn=fn)
+    Q.init.qparams_init(net)
+    return net, ref
+
+
+def capture(net):
+    """Record (input, quantised input, quantised weight, bias) of every converted block."""
+    rec = {}
+    for b in net.collect_quantized_blocks():
+        orig = b.origin_forward
+
+        def wrapped(x, w, bias, _b=b, _orig=orig):
+            rec[_b.name]["xq"] = x.detach().cpu().numpy()
+            rec[_b.name]["wq"] = w.detach().cpu().numpy()
+            rec[_b.name]["bias"] = None if bias is None else bias.detach().cpu().numpy()
+            return _orig(x, w, bias)
+        b.origin_forward = wrapped
+        b.register_forward_pre_hook(lambda m, x: rec.setdefault(m.name, {}).update(x=x[0].detach().cpu().numpy()))
+    return rec
+
+
+def test_config1_cifar_resnet20_online_uint8_layerwise_and_logits(Q):
+    net, ref = build(Q, "cifar_resnet20_v1", 10)
+    rec = capture(net)
+    net.fix_params()
+    net.quantize_input(enable=True, online=True)          # simulate_quantization.py:346-347
+    X = torch.randn(128, 3, 32, 32, generator=torch.Generator().manual_seed(7))
+    with torch.no_grad():
+        logits = net(X.cuda()).cpu().numpy()
+    blocks = net.collect_quantized_blocks()
+    assert len(blocks) == 20
+    ref_blocks = {m.name: m for m in ref.modules() if hasattr(m, "name")}
+    for b in blocks:
+        r = rec[b.name]
+        layer = "dense" if isinstance(b, nn.Linear) else "conv"
+        y, _, cur, _ = O.fake_quant_input(r["x"], 8, False, None, "legacy", layer)
+        assert np.array_equal(bits(r["xq"]), bits(y)), b.name
+        assert F32(b.current_input_max.item()) == cur, b.name
+        wq, _, _ = O.fake_quant_weight(ref_blocks[b.name].weight.detach().numpy(), 8, "layer")
+        assert np.array_equal(bits(r["wq"]), bits(wq)), b.name
+        if isinstance(b, nn.Conv2d):
+            assert b.fixed_params == 1                     # weights cached (convert_conv2d.py:101-105)
+            assert np.array_equal(bits(b.weight.detach().cpu().numpy()), bits(wq))
+
+    # end-to-end: the same pipeline on the CPU with the oracle doing every fake-quant
+    def pre(m, x):
+        layer = "dense" if isinstance(m, nn.Linear) else "conv"
+        y, _, _, _ = O.fake_quant_input(x[0].numpy(), 8, False, None, "legacy", layer)
+        return (torch.from_numpy(y),)
+    for b in blocks:
+        rb = ref_blocks[b.name]
+        rb.weight.data = torch.from_numpy(O.fake_quant_weight(rb.weight.detach().numpy(), 8, "layer")[0])
+        rb.register_forward_pre_hook(pre)
+    with torch.no_grad():
+        want = ref(X).numpy()
+    # cuDNN and the CPU convolution sum in different orders; 1e-5 relative is north_star's bound
+    err = np.abs(logits - want).max() / np.abs(want).max()
+    assert err < 1e-5, err
+
+    # second forward: weights are fixed now, only the input path runs
+    with torch.no_grad():
+        again = net(X.cuda()).cpu().numpy()
+    assert np.array_equal(bits(again), bits(logits))
+
+
+def test_config4_like_fake_bn_per_group_4bit_ema(Q):
+    """resnet-style fake-BN + merge, 4-bit per-group weights, EMA ("naive") calibration: §3.3 flow."""
+    net, ref = build(Q, "cifar_resnet20_v1", 10, weight_width=4, quant_type="group", fake_bn=True)
+    rec = capture(net)
+    ref_blocks = {m.name: m for m in ref.modules() if hasattr(m, "name")}
+    blocks = net.collect_quantized_blocks()
+    convs = [b for b in blocks if isinstance(b, nn.Conv2d)]
+    assert all(b.bias is not None for b in convs)              # initialize.py:65-70
+    net.quantize_input(enable=True, online=True)
+    state = {b.name: np.zeros(1, F32) for b in blocks}
+    g = torch.Generator().manual_seed(3)
+    for it in range(3):
+        X = torch.randn(32, 3, 32, 32, generator=g)
+        prev = {b.name: (b.running_mean.detach().cpu().numpy().copy(), b.running_var.detach().cpu().numpy().copy())
+                for b in convs}
+        with torch.no_grad():
+            net(X.cuda())
+        net.update_ema()
+        for b in blocks:
+            cur = O.input_range(rec[b.name]["x"])[0]
+            state[b.name] = O.ema_scalar(state[b.name], np.array([cur], F32), 0.9, "legacy")
+            assert np.array_equal(bits(b.input_max.detach().cpu().numpy()), bits(state[b.name])), (it, b.name)
+        for b in convs:     # fake-BN running statistics (convert.py:75-78)
+            want_m = O.ema_tensor(prev[b.name][0], b.current_mean.cpu().numpy(), 0.9)
+            want_v = O.ema_tensor(prev[b.name][1], b.current_var.cpu().numpy(), 0.9)
+            assert np.array_equal(bits(b.running_mean.detach().cpu().numpy()), bits(want_m)), b.name
+            assert np.array_equal(bits(b.running_var.detach().cpu().numpy()), bits(want_v)), b.name
+    for b in convs:
+        bn = ref_blocks[b.name.replace("conv", "batchnorm")]
+        assert np.array_equal(b.gamma.detach().cpu().numpy(), bn.weight.detach().numpy())
+        # weight path of the last forward used the running statistics as they were BEFORE the last update
+        rb = ref_blocks[b.name]
+        w2, b2 = O.fold_bn(rb.weight.detach().numpy(), None if rb.bias is None else rb.bias.detach().numpy(),
+                           bn.weight.detach().numpy(), bn.bias.detach().numpy(), prev[b.name][0], prev[b.name][1])
+        wq, _, _ = O.fake_quant_weight(w2, 4, "group", groups=1)
+        assert np.array_equal(bits(rec[b.name]["wq"]), bits(wq)), b.name
+        assert np.array_equal(bits(rec[b.name]["bias"]), bits(b2)), b.name
+    # switch to offline inputs with fixed params, as the example does (:336-338)
+    net.fix_params()
+    net.quantize_input(enable=True, online=False)
+    X = torch.randn(32, 3, 32, 32, generator=g)
+    with torch.no_grad():
+        net(X.cuda())
+    for b in blocks:
+        layer = "dense" if isinstance(b, nn.Linear) else "conv"
+        y, _, _, _ = O.fake_quant_input(rec[b.name]["x"], 8, False, state[b.name][0], "legacy", layer)
+        assert np.array_equal(bits(rec[b.name]["xq"]), bits(y)), b.name
+    assert all(b.fixed_params == 1 for b in convs)
+
+
+def test_fake_bn_fold_and_weight_quant_match_oracle(Q):
+    net, ref = build(Q, "cifar_resnet20_v1", 10, weight_width=4, quant_type="channel", fake_bn=True)
+    rec = capture(net)
+    ref_blocks = {m.name: m for m in ref.modules() if hasattr(m, "name")}
+    X = torch.randn(8, 3, 32, 32, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        net(X.cuda())
+    for b in net.collect_quantized_blocks():
+        if not isinstance(b, nn.Conv2d):
+            continue
+        rb, bn = ref_blocks[b.name], ref_blocks[b.name.replace("conv", "batchnorm")]
+        w2, b2 = O.fold_bn(rb.weight.detach().numpy(), None, bn.weight.detach().numpy(), bn.bias.detach().numpy(),
+                           bn.running_mean.numpy(), bn.running_var.numpy())
+        wq, _, _ = O.fake_quant_weight(w2, 4, "channel")
+        assert np.array_equal(bits(rec[b.name]["wq"]), bits(wq)), b.name
+        assert np.array_equal(bits(rec[b.name]["bias"]), bits(b2)), b.name
+
+
+def test_config2_like_kl_calibration_flow(Q):
+    """collect_feature_maps + kl_calibrate on the converted net vs. the oracle on the same activations."""
+    Q.ops.set_promotion("nep50")          # the regime the golden hist/KL vectors were produced in
+    try:
+        net, _ = build(Q, "cifar_resnet20_v1", 10, quant_type="channel")
+        net.disable_quantize()
+        g = torch.Generator().manual_seed(11)
+        batches = [torch.randn(16, 3, 32, 32, generator=g) * (1.0 + 0.3 * i) for i in range(3)]
+        loader = [(b, None) for b in batches]
+        hist_c, max_c = Q.dc.collect_feature_maps(net, 2048, loader, torch.device("cuda"))
+        # gather the same activations with plain hooks
+        acts = {}
+        hooks = [b.register_forward_hook(lambda m, x, y: acts.setdefault(m.name, []).append(x[0].cpu().numpy()))
+                 for b in net.collect_quantized_blocks()]
+        with torch.no_grad():
+            for b in batches:
+                net(b.cuda())
+        for h in hooks:
+            h.remove()
+        blocks = net.collect_quantized_blocks()
+        assert set(hist_c.keys()) == set(blocks)
+        for b in blocks:
+            want_h, want_m = O.accumulate_histograms(acts[b.name], 2048, "nep50")
+            assert np.array_equal(hist_c[b], want_h), b.name
+            assert max_c[b] == want_m
+        for b in blocks[:4] + blocks[-2:]:
+            best = Q.dc.kl_calibrate(hist_c[b], 256, 256, 2048)
+            assert best == O.kl_calibrate(hist_c[b], 256, 256, 2048, "nep50"), b.name
+        best_all, th = Q.dc.kl_calibrate_all(hist_c, 256, 256, 2048, fm_max=max_c)
+        for i, b in enumerate(blocks[:4]):
+            assert int(best_all[i]) == Q.dc.kl_calibrate(hist_c[b], 256, 256, 2048)
+            assert F32(th[i].item()) == O.kl_threshold(int(best_all[i]), max_c[b], 2048)
+    finally:
+        Q.ops.set_promotion("legacy")
+
+
+def test_collect_feature_maps_rejects_negative_activations(Q):
+    net, _ = build(Q, "cifar_resnet20_v1", 10)
+    net.disable_quantize()
+    # include the block right after the un-activated first BatchNorm: its input has negatives
+    first = net.features[2][0].body[0]
+    Q.convert.gen_conv2d_converter()(first)
+    with pytest.raises(AssertionError, match="Activation should >=0"):
+        Q.dc.collect_feature_maps(net, 2048, [(torch.randn(4, 3, 32, 32), None)], torch.device("cuda"))
+
+
+def test_config3_like_qat_step_gradients(Q):
+    """Identity STE: gradients equal those of a torch graph whose fake-quant is y = x + (fq(x) - x).detach()."""
+    torch.manual_seed(0)
+    conv = nn.Conv2d(8, 16, 3, padding=1).cuda()
+    lin = nn.Linear(16, 10).cuda()
+    ref_conv, ref_lin = copy.deepcopy(conv), copy.deepcopy(lin)
+    Q.convert.gen_conv2d_converter(weight_width=4, input_width=4, quant_type="channel")(conv)
+    Q.convert.gen_dense_converter(weight_width=4, input_width=4)(lin)
+    for m in (conv, lin):
+        m.name = "x"
+    x = torch.rand(4, 8, 6, 6, device="cuda", requires_grad=True)
+    out = lin(torch.relu(conv(x)).mean(dim=(2, 3)))
+    out.square().sum().backward()
+
+    def fq_in(t, layer):
+        y = O.fake_quant_input(t.detach().cpu().numpy(), 4, False, None, "legacy", layer)[0]
+        return t + (torch.from_numpy(y).cuda() - t).detach()
+
+    def fq_w(w, qt):
+        y = O.fake_quant_weight(w.detach().cpu().numpy(), 4, qt)[0]
+        return w + (torch.from_numpy(y).cuda() - w).detach()
+    x2 = x.detach().clone().requires_grad_(True)
+    h = torch.relu(nn.functional.conv2d(fq_in(x2, "conv"), fq_w(ref_conv.weight, "channel"), ref_conv.bias, padding=1)).mean(dim=(2, 3))
+    out2 = nn.functional.linear(fq_in(h, "dense"), fq_w(ref_lin.weight, "layer"), ref_lin.bias)
+    out2.square().sum().backward()
+    assert torch.equal(out, out2)
+    assert torch.equal(x.grad, x2.grad)
+    assert torch.equal(conv.weight.grad, ref_conv.weight.grad)
+    assert torch.equal(lin.weight.grad, ref_lin.weight.grad)
+
+
+def test_merge_bn_matches_oracle_and_bypasses_bn(Q):
+    net, ref = build(Q, "mobilenet1.0", 10)
+    ref_blocks = {m.name: m for m in ref.modules() if hasattr(m, "name")}
+    X = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(2)).cuda()
+    plain = Q.zoo.get_model("mobilenet1.0", classes=10).eval().cuda()
+    plain.load_state_dict({k: v for k, v in ref.state_dict().items()})
+    with torch.no_grad():
+        before = plain(X)
+    Q.freeze.merge_bn(plain)
+    for m in plain.modules():
+        if isinstance(m, nn.Conv2d):
+            rb, bn = ref_blocks[m.name], ref_blocks[m.name.replace("conv", "batchnorm")]
+            w2, b2 = O.fold_bn(rb.weight.detach().numpy(), None, bn.weight.detach().numpy(), bn.bias.detach().numpy(),
+                               bn.running_mean.numpy(), bn.running_var.numpy())
+            assert np.array_equal(bits(m.weight.detach().cpu().numpy()), bits(w2)), m.name
+            assert np.array_equal(bits(m.bias.detach().cpu().numpy()), bits(b2)), m.name
+    with torch.no_grad():
+        after = plain(X)
+    # BN eps (1e-5) vs the fold's 1e-10: close, not identical -- what tests/test_merge_bn.py eyeballs
+    assert torch.allclose(before, after, rtol=1e-3, atol=1e-4)
+
+
+def test_linear_quantize_ste_call_shapes(Q):
+    from quantization.mxnet_b200.quantize.convert import LinearQuantizeSTE
+    x = torch.randn(6, 5, 3, 3, device="cuda")
+    xn = x.cpu().numpy()
+    s = np.float32(0.05)
+    y = LinearQuantizeSTE(s, np.float32(1.0), np.float32(-1.0))(x)
+    d64 = np.float32(np.float64(s) + 1e-10)
+    assert np.array_equal(bits(y.cpu().numpy()), bits(O.fake_quant_scalar(xn, d64, s, -1.0, 1.0)[0]))
+    y = LinearQuantizeSTE(0.05, 1.0)(x)                     # clip_min defaults to 0 (ste_func.py:34)
+    assert np.array_equal(bits(y.cpu().numpy()),
+                          bits(O.fake_quant_scalar(xn, np.float32(0.05 + 1e-10), np.float32(0.05), 0.0, 1.0)[0]))
+    sc = torch.rand(6, 1, 1, 1, device="cuda") * 0.1
+    y = LinearQuantizeSTE(sc)(x)
+    assert np.array_equal(bits(y.cpu().numpy()), bits(O.fake_quant_rows(xn, 6, sc.cpu().numpy())[0]))
+    xg = x.clone().requires_grad_(True)
+    LinearQuantizeSTE(0.05, 1.0)(xg).sum().backward()
+    assert torch.equal(xg.grad, torch.ones_like(xg))        # identity backward, even where clipped
+
+
+def test_collect_qparams_and_state_dict(Q):
+    net, _ = build(Q, "cifar_resnet20_v1", 10)
+    qp = Q.utils.collect_qparams(net)
+    assert len(qp) == 20 and all(k.endswith("_input_max") for k in qp)
+    sd = net.state_dict()
+    assert sum(k.endswith("input_max") for k in sd) == 20
+    assert not any("current_input_max" in k for k in sd)

@@ -1,0 +1,133 @@
+"""Host-side mirror of the reference's Python API, checked without launching any kernel."""
+import pytest
+import torch
+from torch import nn
+
+from quantization.mxnet_b200 import model_zoo as Z
+from quantization.mxnet_b200.gluon_compat import NameScope, assign_names, collect_params
+from quantization.mxnet_b200.quantize import collect_qparams, convert
+from quantization.mxnet_b200.quantize.initialize import qparams_init
+
+
+def small_net():
+    sc = NameScope("net0_")
+    net = nn.Sequential(sc(nn.Conv2d(3, 8, 3, bias=False)), sc(nn.BatchNorm2d(8)), sc(nn.ReLU()),
+                        sc(nn.Conv2d(8, 8, 3, groups=8, bias=False)), sc(nn.BatchNorm2d(8)), sc(nn.ReLU()),
+                        sc(nn.AdaptiveAvgPool2d(1)), sc(nn.Flatten()), sc(nn.Linear(8, 4)))
+    return net
+
+
+def test_gluon_style_names_pair_conv_with_batchnorm():
+    net = small_net()
+    names = [m.name for m in net]
+    assert names[:6] == ["net0_conv0", "net0_batchnorm0", "net0_relu0", "net0_conv1", "net0_batchnorm1", "net0_relu1"]
+    assert names[-1] == "net0_dense0"
+    p = collect_params(net)
+    assert "net0_batchnorm1_gamma" in p and "net0_batchnorm1_running_var" in p and "net0_conv0_weight" in p
+    assert list(collect_params(net, "net0_batchnorm0_").keys()) == [
+        "net0_batchnorm0_gamma", "net0_batchnorm0_beta", "net0_batchnorm0_running_mean", "net0_batchnorm0_running_var"]
+    plain = nn.Sequential(nn.Conv2d(1, 1, 1), nn.BatchNorm2d(1))
+    assign_names(plain, "x0_")
+    assert [m.name for m in plain] == ["x0_conv0", "x0_batchnorm0"]
+
+
+def test_convert_model_bookkeeping_matches_reference():
+    net = small_net()
+    ret = convert.convert_model(net, exclude=[net[0]])
+    assert ret is None                                      # convert.py:121 returns nothing
+    blocks = net.collect_quantized_blocks()
+    assert [b.name for b in blocks] == ["net0_conv1", "net0_dense0"]      # apply order, excluded conv missing
+    conv, dense = blocks
+    assert conv.quantize_args._fields == ("quantize_input", "in_signed", "in_width", "wt_width", "quant_type",
+                                          "fake_bn", "wino_quantize")
+    assert dense.quantize_args._fields == ("in_signed", "in_width", "wt_width", "quantize_input", "quant_type")
+    assert tuple(conv.quantize_args) == (True, False, 8, 8, "layer", False, "none")
+    assert conv.fixed_params == -1 and not hasattr(dense, "fixed_params")
+    assert conv.enable_quantize and conv.quantize_input and conv.quantize_input_offline is False
+    assert tuple(conv.input_max.shape) == (1,) and conv.input_max.requires_grad is False
+    assert float(conv.current_input_max) == 0.0
+    assert hasattr(conv, "origin_forward") and not hasattr(net[0], "quantize_args")
+    for name in ("update_ema", "collect_quantized_blocks", "quantize_input", "enable_quantize", "disable_quantize",
+                 "fix_params"):
+        assert callable(getattr(net, name))
+
+    net.quantize_input(enable=True, online=False)
+    assert all(b.quantize_input and b.quantize_input_offline for b in blocks)
+    net.quantize_input(enable=False)
+    assert not any(b.quantize_input for b in blocks)
+    net.disable_quantize()
+    assert not any(b.enable_quantize for b in blocks)
+    net.enable_quantize()
+    net.fix_params()
+    assert conv.fixed_params == 0 and not hasattr(dense, "fixed_params")   # Dense is never fixed (convert.py:117-121)
+    assert list(collect_qparams(net).keys()) == ["net0_conv1_input_max", "net0_dense0_input_max"]
+
+
+def test_convert_fn_is_exact_type_match_and_custom_fn_wins():
+    class MyConv(nn.Conv2d):
+        pass
+    net = nn.Sequential(MyConv(1, 1, 1), nn.Conv2d(1, 1, 1), nn.Conv2d(1, 1, 1))
+    assign_names(net)
+    marker = []
+    convert.convert_model(net, custom_fn={net[2]: lambda m: marker.append(m)})
+    assert not hasattr(net[0], "quantize_args")             # subclass: convert_fn.get(type(m)) misses
+    assert hasattr(net[1], "quantize_args")
+    assert marker == [net[2]] and not hasattr(net[2], "quantize_args")
+
+
+def test_quantize_input_asserts_when_block_was_converted_without_it():
+    net = small_net()
+    fn = {nn.Conv2d: convert.gen_conv2d_converter(quantize_input=False), nn.Linear: convert.gen_dense_converter()}
+    convert.convert_model(net, convert_fn=fn)
+    with pytest.raises(AssertionError):
+        net.quantize_input(enable=True)
+    net.quantize_input(enable=False)
+    assert not hasattr(net[0], "input_max")
+
+
+def test_dense_group_maps_to_channel_and_wino_choices():
+    lin = nn.Linear(4, 4)
+    convert.gen_dense_converter(quant_type="group")(lin)
+    assert lin.quantize_args.quant_type == "channel"        # convert_dense.py:83-84
+    with pytest.raises(AssertionError):
+        convert.gen_conv2d_converter(wino_quantize="F99")
+    with pytest.raises(AssertionError):
+        convert.gen_conv2d_converter()(nn.Linear(2, 2))
+
+
+def test_qparams_init_fake_bn_adopts_sibling_batchnorm():
+    net = small_net()
+    with torch.no_grad():
+        net[4].weight.fill_(1.5)
+        net[4].bias.fill_(-0.25)
+        net[4].running_mean.fill_(0.125)
+        net[4].running_var.fill_(2.0)
+    fn = {nn.Conv2d: convert.gen_conv2d_converter(fake_bn=True), nn.Linear: convert.gen_dense_converter(),
+          nn.BatchNorm2d: convert.bypass_bn}
+    convert.convert_model(net, exclude=[net[0], net[1]], convert_fn=fn)
+    conv = net[3]
+    assert conv.bias is None and tuple(conv.gamma.shape) == (8,)
+    assert conv.gamma.requires_grad and conv.beta.requires_grad and not conv.running_var.requires_grad
+    with torch.no_grad():
+        conv.input_max.fill_(3.0)
+    qparams_init(net)
+    assert float(conv.input_max) == 0.0
+    assert torch.all(conv.gamma == 1.5) and torch.all(conv.beta == -0.25)
+    assert torch.all(conv.running_mean == 0.125) and torch.all(conv.running_var == 2.0)
+    assert conv.bias is not None and torch.all(conv.bias == 0)          # initialize.py:65-70
+    x = torch.randn(2, 8, 5, 5)
+    assert net[4](x) is x and net[1](x) is not x                        # bypassed vs excluded BatchNorm
+
+
+@pytest.mark.parametrize("name,n_conv,n_dense", [("cifar_resnet20_v1", 19, 1), ("mobilenet1.0", 26, 1),
+                                                 ("mobilenetv2_1.0", 52, 0), ("resnet50_v1", 52, 1)])
+def test_model_zoo_quantised_block_counts(name, n_conv, n_dense):
+    net = Z.get_model(name, classes=10)
+    convert.convert_model(net, exclude=Z.default_exclusions(net, name))
+    blocks = net.collect_quantized_blocks()
+    assert sum(isinstance(b, nn.Conv2d) for b in blocks) == n_conv
+    assert sum(isinstance(b, nn.Linear) for b in blocks) == n_dense
+    params = collect_params(net)
+    for b in blocks:
+        if isinstance(b, nn.Conv2d):
+            assert b.name.replace("conv", "batchnorm") + "_gamma" in params, b.name
