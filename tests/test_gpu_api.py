@@ -57,9 +57,10 @@ def capture(net):
         orig = b.origin_forward
 
         def wrapped(x, w, bias, _b=b, _orig=orig):
-            rec[_b.name]["xq"] = x.detach().cpu().numpy()
-            rec[_b.name]["wq"] = w.detach().cpu().numpy()
-            rec[_b.name]["bias"] = None if bias is None else bias.detach().cpu().numpy()
+            r = rec.setdefault(_b.name, {})     # (the fake-BN EMA pre-hook calls this too, with raw weights)
+            r["xq"] = x.detach().cpu().numpy()
+            r["wq"] = w.detach().cpu().numpy()
+            r["bias"] = None if bias is None else bias.detach().cpu().numpy()
             return _orig(x, w, bias)
         b.origin_forward = wrapped
         b.register_forward_pre_hook(lambda m, x: rec.setdefault(m.name, {}).update(x=x[0].detach().cpu().numpy()))
@@ -89,20 +90,26 @@ def test_config1_cifar_resnet20_online_uint8_layerwise_and_logits(Q):
             assert b.fixed_params == 1                     # weights cached (convert_conv2d.py:101-105)
             assert np.array_equal(bits(b.weight.detach().cpu().numpy()), bits(wq))
 
-    # end-to-end: the same pipeline on the CPU with the oracle doing every fake-quant
+    # end-to-end: the same pipeline with the ORACLE doing every fake-quant.  The convolutions are
+    # framework calls on both sides (cuDNN here and there), so any difference comes from the path
+    # under test; north_star's bound is 1e-5 relative.
     def pre(m, x):
         layer = "dense" if isinstance(m, nn.Linear) else "conv"
-        y, _, _, _ = O.fake_quant_input(x[0].numpy(), 8, False, None, "legacy", layer)
-        return (torch.from_numpy(y),)
+        y, _, _, _ = O.fake_quant_input(x[0].cpu().numpy(), 8, False, None, "legacy", layer)
+        return (torch.from_numpy(y).to(x[0].device),)
     for b in blocks:
         rb = ref_blocks[b.name]
         rb.weight.data = torch.from_numpy(O.fake_quant_weight(rb.weight.detach().numpy(), 8, "layer")[0])
         rb.register_forward_pre_hook(pre)
     with torch.no_grad():
-        want = ref(X).numpy()
-    # cuDNN and the CPU convolution sum in different orders; 1e-5 relative is north_star's bound
+        want = ref.cuda()(X.cuda()).cpu().numpy()
     err = np.abs(logits - want).max() / np.abs(want).max()
     assert err < 1e-5, err
+    # against a CPU convolution the summation order differs by ulps, which can flip a rounding tie in
+    # a later layer by one quantisation step: the logits then agree only to about that step
+    with torch.no_grad():
+        want_cpu = ref.cpu()(X).numpy()
+    assert np.abs(logits - want_cpu).max() / np.abs(want_cpu).max() < 2e-2
 
     # second forward: weights are fixed now, only the input path runs
     with torch.no_grad():
@@ -250,9 +257,10 @@ def test_config3_like_qat_step_gradients(Q):
     out2 = nn.functional.linear(fq_in(h, "dense"), fq_w(ref_lin.weight, "layer"), ref_lin.bias)
     out2.square().sum().backward()
     assert torch.equal(out, out2)
-    assert torch.equal(x.grad, x2.grad)
-    assert torch.equal(conv.weight.grad, ref_conv.weight.grad)
-    assert torch.equal(lin.weight.grad, ref_lin.weight.grad)
+    # cuDNN's backward kernels may pick different (atomics-based) algorithms per call: compare to fp32 accuracy
+    for got, want in ((x.grad, x2.grad), (conv.weight.grad, ref_conv.weight.grad), (lin.weight.grad, ref_lin.weight.grad),
+                      (conv.bias.grad, ref_conv.bias.grad)):
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-7)
 
 
 def test_merge_bn_matches_oracle_and_bypasses_bn(Q):
