@@ -71,6 +71,7 @@ typedef struct {
 #define FQ_QP_LO 2
 #define FQ_QP_HI 3
 
+#define FQ_MAX_BATCH 64     /* tensors one multi-tensor launch takes */
 #define FQ_MAX_ROWS 65536   /* rows (samples / channels / groups) a fused kernel accepts */
 
 /* ---- library ---- */
@@ -142,6 +143,12 @@ FQ_API int fq_ema_update(const DLTensor* state, const DLTensor* cur, double mome
 /* counts[bin] += 1 for every clipped non-zero element; counts is uint64/int64 [bins+1].  :39-45 */
 FQ_API int fq_hist_nonzero(const DLTensor* x, const DLTensor* max_, int bins, int promotion,
                     const DLTensor* counts, void* stream);
+/* The same for n_tensors (<= FQ_MAX_BATCH per launch, more are chunked) layer inputs in ONE launch: the
+ * thread blocks are shared out in proportion to the tensor sizes, so small layers cost no launch of their own.
+ * xs[i]: float32, 16-byte aligned; its frozen max is maxes[i * max_stride + max_offset];
+ * counts: (u)int64 [n_tensors, bins+1]. */
+FQ_API int fq_hist_nonzero_multi(const DLTensor* const* xs, int n_tensors, const DLTensor* maxes, int max_stride,
+                                 int max_offset, int bins, int promotion, const DLTensor* counts, void* stream);
 /* hist = (first ? 0 : hist) + float32(counts); counts <- 0; seen_last[0] |= counts[bins] != 0.  :47,103-104 */
 FQ_API int fq_hist_accumulate_f32(const DLTensor* counts, const DLTensor* hist, int first,
                            const DLTensor* seen_last, void* stream);

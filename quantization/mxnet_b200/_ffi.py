@@ -69,6 +69,8 @@ SIGNATURES = {
     "fq_ste_backward": (_c.c_int, [P, P, P, P, _c.c_int, _c.c_void_p]),
     "fq_ema_update": (_c.c_int, [P, P, _c.c_double, _c.c_int, _c.c_int, _c.c_void_p]),
     "fq_hist_nonzero": (_c.c_int, [P, P, _c.c_int, _c.c_int, P, _c.c_void_p]),
+    "fq_hist_nonzero_multi": (_c.c_int, [_c.POINTER(P), _c.c_int, P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, P,
+                                         _c.c_void_p]),
     "fq_hist_accumulate_f32": (_c.c_int, [P, P, _c.c_int, P, _c.c_void_p]),
     "fq_kl_search": (_c.c_int, [P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, P, P, _c.c_void_p]),
     "fq_kl_threshold": (_c.c_int, [P, P, _c.c_int, P, _c.c_void_p]),

@@ -23,26 +23,22 @@ __global__ void ema_kernel(float* __restrict__ state, const float* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // histogram of the clipped non-zero values
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) hist_kernel(const float* __restrict__ x, int64_t n, int64_t per_block,
-                                                        const float* __restrict__ max_dev, int bins, int promotion,
-                                                        unsigned long long* __restrict__ counts, int vectorised) {
-  extern __shared__ unsigned int sh[];     // bins + 1 private counters
+// One slice of one tensor into the block-private histogram `sh`, then one atomic per non-empty bin.
+__device__ __forceinline__ void hist_slice(const float* __restrict__ x, int64_t begin, int64_t end, float max_,
+                                           int bins, int promotion, unsigned long long* __restrict__ counts,
+                                           unsigned int* sh, bool vectorised, int64_t n, int64_t stride0,
+                                           int64_t stride) {
   for (int b = threadIdx.x; b <= bins; b += blockDim.x) sh[b] = 0u;
-  const float max_ = __ldg(max_dev);
   // scales = bins / (max_ + 1e-5)      distribution_calibrate.py:41
   const float sc = (promotion == FQ_PROMOTION_LEGACY) ? (float)((double)bins / ((double)max_ + 1e-5))
                                                       : __fdiv_rn((float)bins, __fadd_rn(max_, 1e-5f));
   __syncthreads();
   auto one = [&](float v) {
-    v = fminf(fmaxf(v, 0.f), max_);                         // ndarray.clip(0, max_)
-    if (v != 0.f) {                                          // zeros are ignored (:40)
-      const int b = (int)__fmul_rn(v, sc);                   // astype(int32): truncation
-      if (b >= 0 && b <= bins) atomicAdd(&sh[b], 1u);
-    }
+    v = fminf(fmaxf(v, 0.f), max_);                         // ndarray.clip(0, max_); NaN -> 0 -> ignored
+    // zeros are ignored (:40); 0 < v <= max_ keeps trunc(v * sc) inside [0, bins]
+    if (v != 0.f) atomicAdd(&sh[min((unsigned int)__float2int_rz(__fmul_rn(v, sc)), (unsigned int)bins)], 1u);
   };
   if (vectorised) {
-    const int64_t begin = (int64_t)blockIdx.x * per_block;
-    const int64_t end = min(n, begin + per_block);
     for_range<false, false>(
         x, begin, end,
         [&](int64_t, float4 v) {
@@ -53,13 +49,43 @@ __global__ void __launch_bounds__(kThreads) hist_kernel(const float* __restrict_
         },
         [&](int64_t, float v) { one(v); });
   } else {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) one(x[i]);
+    for (int64_t i = stride0; i < n; i += stride) one(x[i]);
   }
   __syncthreads();
   for (int b = threadIdx.x; b <= bins; b += blockDim.x) {
     const unsigned int c = sh[b];
     if (c) atomicAdd(&counts[b], (unsigned long long)c);
   }
+}
+
+__global__ void __launch_bounds__(kThreads) hist_kernel(const float* __restrict__ x, int64_t n, int64_t per_block,
+                                                        const float* __restrict__ max_dev, int bins, int promotion,
+                                                        unsigned long long* __restrict__ counts, int vectorised) {
+  extern __shared__ unsigned int sh[];     // bins + 1 private counters
+  const int64_t begin = (int64_t)blockIdx.x * per_block;
+  hist_slice(x, begin, min(n, begin + per_block), __ldg(max_dev), bins, promotion, counts, sh, vectorised != 0, n,
+             (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+}
+
+// Multi-tensor variant: block -> (tensor, slice) through a table passed by value.
+struct HistBatch {
+  const float* x[FQ_MAX_BATCH];
+  int64_t n[FQ_MAX_BATCH];
+  int64_t per_block[FQ_MAX_BATCH];
+  int first_block[FQ_MAX_BATCH + 1];
+  int count;
+};
+
+__global__ void __launch_bounds__(kThreads) hist_multi_kernel(const __grid_constant__ HistBatch tb,
+                                                              const float* __restrict__ maxes, int max_stride,
+                                                              int max_offset, int bins, int promotion,
+                                                              unsigned long long* __restrict__ counts) {
+  extern __shared__ unsigned int sh[];
+  int t = 0;
+  while (t + 1 < tb.count && (int)blockIdx.x >= tb.first_block[t + 1]) ++t;
+  const int64_t begin = (int64_t)((int)blockIdx.x - tb.first_block[t]) * tb.per_block[t];
+  hist_slice(tb.x[t], begin, min(tb.n[t], begin + tb.per_block[t]), __ldg(maxes + (int64_t)t * max_stride + max_offset),
+             bins, promotion, counts + (int64_t)t * (bins + 1), sh, true, 0, 0, 0);
 }
 
 __global__ void hist_accumulate_kernel(unsigned long long* __restrict__ counts, float* __restrict__ hist, int nb,
@@ -248,6 +274,56 @@ int fq_hist_nonzero(const DLTensor* x_, const DLTensor* max__, int bins, int pro
       x.as<const float>(), x.numel, per_block, mx.as<const float>(), bins, promotion,
       counts.as<unsigned long long>(), vec);
   FQ_LAUNCH_CHECK("hist_kernel");
+  return 0;
+}
+
+int fq_hist_nonzero_multi(const DLTensor* const* xs, int n_tensors, const DLTensor* maxes_, int max_stride,
+                          int max_offset, int bins, int promotion, const DLTensor* counts_, void* stream) {
+  const char* who = "fq_hist_nonzero_multi";
+  View mx, counts;
+  FQ_REQUIRE(xs != nullptr && n_tensors >= 1, "%s: no tensors", who);
+  FQ_TRY(view_of(maxes_, "fq_hist_nonzero_multi: maxes", false, &mx));
+  FQ_TRY(view_of(counts_, "fq_hist_nonzero_multi: counts", false, &counts));
+  FQ_REQUIRE(bins >= 1 && bins <= 8192, "%s: bins=%d outside [1, 8192]", who, bins);
+  FQ_REQUIRE(mx.is_f32() && max_stride >= 1 && max_offset >= 0 &&
+                 mx.numel >= (int64_t)(n_tensors - 1) * max_stride + max_offset + 1,
+             "%s: maxes must be float32 with an entry for every tensor", who);
+  FQ_REQUIRE((counts.code == kDLInt || counts.code == kDLUInt) && counts.bits == 64 &&
+                 counts.numel == (int64_t)n_tensors * (bins + 1),
+             "%s: counts must be (u)int64 [n_tensors, bins+1]", who);
+  FQ_REQUIRE(promotion == FQ_PROMOTION_LEGACY || promotion == FQ_PROMOTION_NEP50, "%s: bad promotion", who);
+  const int budget = sm_count() * 8;
+  for (int base = 0; base < n_tensors; base += FQ_MAX_BATCH) {
+    const int cnt = (n_tensors - base < FQ_MAX_BATCH) ? n_tensors - base : FQ_MAX_BATCH;
+    HistBatch tb = {};
+    int64_t total = 0;
+    for (int i = 0; i < cnt; ++i) {
+      View x;
+      FQ_TRY(view_of(xs[base + i], "fq_hist_nonzero_multi: x", false, &x));
+      FQ_REQUIRE(x.is_f32() && aligned16(x.data), "%s: tensor %d must be float32 and 16-byte aligned", who, base + i);
+      tb.x[i] = x.as<const float>();
+      tb.n[i] = x.numel;
+      total += x.numel;
+    }
+    int blocks = 0;
+    for (int i = 0; i < cnt; ++i) {
+      tb.first_block[i] = blocks;
+      if (tb.n[i] == 0) {
+        tb.per_block[i] = 0;
+        continue;
+      }
+      int share = (int)((double)budget * (double)tb.n[i] / (double)(total > 0 ? total : 1));
+      if (share < 1) share = 1;
+      blocks += slice_grid(tb.n[i], share, &tb.per_block[i]);
+    }
+    tb.first_block[cnt] = blocks;
+    tb.count = cnt;
+    if (blocks == 0) continue;
+    hist_multi_kernel<<<blocks, kThreads, sizeof(unsigned int) * (bins + 1), (cudaStream_t)stream>>>(
+        tb, mx.as<const float>() + (int64_t)base * max_stride, max_stride, max_offset, bins, promotion,
+        counts.as<unsigned long long>() + (int64_t)base * (bins + 1));
+    FQ_LAUNCH_CHECK("hist_multi_kernel");
+  }
   return 0;
 }
 

@@ -105,10 +105,34 @@ __device__ __forceinline__ float clipf(float x, float lo, float hi) {
   return x > hi ? hi : (x < lo ? lo : x);
 }
 
-// clip -> IEEE divide -> roundf.  Returns the integer-valued "code".
+// IEEE divide -> roundf: the integer-valued "code", by the book.
 __device__ __forceinline__ float quant_code(float x, float d) {
   return round_half_away(__fdiv_rn(x, d));
 }
+
+// The same code in ~6 instructions instead of ~20.  With r = RN(1/d) and q0 = RN(v * r),
+//   |q0 - RN(v / d)| <= (3u + u^2) |v / d|  <  0.38 * 2^-21 * |q0|        (u = 2^-24, no underflow in r),
+// so whenever q0 is farther than 2^-21 |q0| from every rounding boundary k + 0.5, q0 and the IEEE
+// quotient lie between the same two boundaries and roundf(v / d) == rintf(q0) (neither is a tie).
+// Anything closer (a few elements per million), NaN/Inf, and divisors outside [1e-30, 1e30] take
+// the IEEE divide.  Bit-exactness therefore does not rest on the fast path being correctly rounded.
+struct QDiv {
+  float d, r, guard;       // guard = 2^-21 on the fast path, +inf to force the IEEE divide
+  __device__ __forceinline__ static QDiv make(float d) {
+    QDiv q;
+    q.d = d;
+    q.r = __frcp_rn(d);
+    q.guard = (d >= 1e-30f && d <= 1e30f) ? 4.76837158203125e-7f : INFINITY;
+    return q;
+  }
+  __device__ __forceinline__ float code(float v) const {
+    const float q0 = __fmul_rn(v, r);
+    const float t = rintf(q0);
+    const float e = fabsf(__fsub_rn(q0, t));                         // distance to the integer, <= 0.5
+    if (__fsub_rn(0.5f, e) > __fmul_rn(fabsf(q0), guard)) return t;  // false for NaN
+    return quant_code(v, d);
+  }
+};
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

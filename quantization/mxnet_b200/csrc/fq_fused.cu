@@ -55,8 +55,9 @@ __device__ __forceinline__ void put_code4(void* p, int kind, int64_t i, float4 c
 template <bool REVERSE>
 __device__ __forceinline__ void quantise_slice(const InputArgs& a, int64_t begin, int64_t end, float d, float s,
                                                float lo, float hi) {
+  const QDiv qd = QDiv::make(d);
   auto one = [&](float v, float& c) {
-    c = quant_code(clipf(v, lo, hi), d);
+    c = qd.code(clipf(v, lo, hi));
     return __fmul_rn(c, s);
   };
   for_range<REVERSE, false>(
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(kThreads) input_path_kernel(InputArgs a) {
       compute_qparams(a.fin.input_max[0], a.fin.bits, a.fin.is_signed, a.fin.lo_mode, a.fin.promotion, qp);
     __syncthreads();
     const float d = qp[0], s = qp[1], lo = qp[2], hi = qp[3];
+    const QDiv qd = QDiv::make(d);
     if (a.L < 2048) {
       // short rows: per-warp row maxima first, then the slice is quantised out of L1/L2
       absmax_segments<true>(a.x, begin, end, a.L, a.ws, red);
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(kThreads) input_path_kernel(InputArgs a) {
         float m = 0.f;
         auto one = [&](float v, float& c) {
           m = fmaxf(m, fabsf(v));
-          c = quant_code(clipf(v, lo, hi), d);
+          c = qd.code(clipf(v, lo, hi));
           return __fmul_rn(c, s);
         };
         for_range<false, false>(
@@ -160,6 +162,11 @@ struct WeightArgs {
   float* bias_out;
   float* scale_out;
   Workspace* ws;
+};
+
+struct RowQ {      // per-row quantiser: multiplier s_r and the divisor context of d_r = s_r + 1e-10
+  float s;
+  QDiv q;
 };
 
 // per-channel fold factors: W' = (W * gamma) / sqrtf(var + 1e-10)      convert_conv2d.py:50
@@ -282,17 +289,20 @@ __global__ void __launch_bounds__(kThreads) weight_path_kernel(WeightArgs a) {
       a, begin, end,
       [&](int64_t c) {   // {s_r, d_r}: convert_conv2d.py:76 / ste_func.py:39
         const float s = __fdiv_rn(__uint_as_float(__ldcg(&a.ws->rowmax[c / ch_per_row])), qmax);
-        return make_float2(s, __fadd_rn(s, 1e-10f));
+        RowQ rq;
+        rq.s = s;
+        rq.q = QDiv::make(__fadd_rn(s, 1e-10f));
+        return rq;
       },
-      [&](float2 sd, int64_t i, float4 v) {
-        float4 q = make_float4(quant_code(v.x, sd.y), quant_code(v.y, sd.y), quant_code(v.z, sd.y), quant_code(v.w, sd.y));
+      [&](const RowQ& rq, int64_t i, float4 v) {
+        float4 q = make_float4(rq.q.code(v.x), rq.q.code(v.y), rq.q.code(v.z), rq.q.code(v.w));
         st_stream(reinterpret_cast<float4*>(a.w_out + i),
-                  make_float4(__fmul_rn(q.x, sd.x), __fmul_rn(q.y, sd.x), __fmul_rn(q.z, sd.x), __fmul_rn(q.w, sd.x)));
+                  make_float4(__fmul_rn(q.x, rq.s), __fmul_rn(q.y, rq.s), __fmul_rn(q.z, rq.s), __fmul_rn(q.w, rq.s)));
         if (a.code_kind) put_code4(a.codes, a.code_kind, i, q);
       },
-      [&](float2 sd, int64_t i, float v) {
-        const float q = quant_code(v, sd.y);
-        a.w_out[i] = __fmul_rn(q, sd.x);
+      [&](const RowQ& rq, int64_t i, float v) {
+        const float q = rq.q.code(v);
+        a.w_out[i] = __fmul_rn(q, rq.s);
         if (a.code_kind) put_code1(a.codes, a.code_kind, i, q);
       },
       true);

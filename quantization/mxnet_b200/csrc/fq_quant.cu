@@ -42,9 +42,11 @@ struct ScalarQuant {
   float d, s, lo, hi;
   float* y;
   Code code;
+  QDiv q;
+  __device__ __forceinline__ void prepare() { q = QDiv::make(d); }
   __device__ __forceinline__ float one(float x, float& c) const {
     if (CLIP) x = clipf(x, lo, hi);
-    c = quant_code(x, d);
+    c = q.code(x);
     return __fmul_rn(c, s);
   }
   __device__ __forceinline__ void vec(int64_t i, float4 v) const {
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(kThreads) forward_scalar_kernel(const float* _
     op.lo = __ldg(qp_dev + FQ_QP_LO);
     op.hi = __ldg(qp_dev + FQ_QP_HI);
   }
+  op.prepare();
   if (vectorised) {
     const int64_t begin = (int64_t)blockIdx.x * per_block;
     const int64_t end = min(n, begin + per_block);
@@ -97,6 +100,7 @@ __global__ void __launch_bounds__(kThreads) forward_rows_kernel(const float* __r
       ScalarQuant<false, Code> op;
       op.s = __ldg(scale + r);
       op.d = __fadd_rn(op.s, 1e-10f);
+      op.prepare();
       op.lo = op.hi = 0.f;
       op.y = y;
       op.code = code;
@@ -217,10 +221,10 @@ static int forward_scalar_impl(const char* who, const DLTensor* x_, const float*
   return with_code_sink(who, codes, n, [&](auto sink) -> int {
     using Code = decltype(sink);
     if (clip) {
-      ScalarQuant<true, Code> op{d, s, lo, hi, y.as<float>(), sink};
+      ScalarQuant<true, Code> op{d, s, lo, hi, y.as<float>(), sink, QDiv()};
       forward_scalar_kernel<true, Code><<<grid, kThreads, 0, st>>>(x.as<const float>(), n, per_block, qp_dev, op, vec);
     } else {
-      ScalarQuant<false, Code> op{d, s, lo, hi, y.as<float>(), sink};
+      ScalarQuant<false, Code> op{d, s, lo, hi, y.as<float>(), sink, QDiv()};
       forward_scalar_kernel<false, Code><<<grid, kThreads, 0, st>>>(x.as<const float>(), n, per_block, qp_dev, op, vec);
     }
     FQ_LAUNCH_CHECK("forward_scalar_kernel");

@@ -195,6 +195,17 @@ def hist_nonzero(x, max_, bins, counts, promotion=None):
     return counts
 
 
+def hist_nonzero_multi(xs, maxes, max_stride, max_offset, bins, counts, promotion=None):
+    """Histograms of several layer inputs in one launch; ``counts`` is int64 [len(xs), bins + 1] and the
+    frozen max of ``xs[i]`` is ``maxes.view(-1)[i * max_stride + max_offset]``."""
+    args = [dl(_f32(x)) for x in xs]
+    arr = (_ffi.P * len(args))(*[_ffi._c.pointer(a.t) for a in args])
+    m, c = dl(maxes), dl(counts)
+    check_call(_lib().fq_hist_nonzero_multi(arr, len(args), m.ptr, max_stride, max_offset, bins, _promo(promotion),
+                                            c.ptr, current_stream()))
+    return counts
+
+
 def hist_accumulate(counts, hist, first, seen_last=None):
     """hist (+)= float32(counts); counts <- 0.  distribution_calibrate.py:47,103-104."""
     c, h, s = dl(counts), dl(hist), dl(seen_last)

@@ -66,6 +66,7 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
     hooks = []
     first_batch = {}        # block index -> inputs seen in batch 0 (kept until its max is known)
     called = set()
+    pending = {}            # block index -> this batch's input, for the single multi-tensor launch
     n_batches = 0
 
     def _collect(m, x, y):
@@ -76,6 +77,8 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
         called.add(i)
         if n_batches == 0:
             first_batch.setdefault(i, []).append(x)
+        elif x.data_ptr() % 16 == 0 and i not in pending:
+            pending[i] = x          # histogrammed together with the other layers after the forward
         else:
             ops.hist_nonzero(x, state["minmax"][i, 1:2], bins, state["counts"][i])
     for blk in quantized_blocks:
@@ -108,6 +111,16 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
                         for x in xs:
                             ops.hist_nonzero(x, state["minmax"][i, 1:2], bins, state["counts"][i])
                     first_batch.clear()
+                if pending:
+                    # every layer of the batch in ONE launch, blocks shared out by tensor size
+                    order = sorted(pending)
+                    if order == list(range(n_blk)):
+                        ops.hist_nonzero_multi([pending[i] for i in order], state["minmax"], 2, 1, bins,
+                                               state["counts"])
+                    else:
+                        for i in order:
+                            ops.hist_nonzero(pending[i], state["minmax"][i, 1:2], bins, state["counts"][i])
+                    pending.clear()
                 if state:
                     if dist is not None:
                         dist.all_reduce(state["counts"], op=dist.ReduceOp.SUM, group=group)

@@ -347,6 +347,20 @@ def test_histogram_vs_oracle_both_regimes(ops, promotion):
         assert np.array_equal(per_batch[0][: len(want)], want)
 
 
+def test_histogram_multi_tensor_equals_single(ops):
+    shapes = [(128, 32, 14, 14), (128, 1024), (7, 3, 5, 5), (64, 64, 28, 28), (1,), (128, 256, 7, 7)] * 12   # 72 > FQ_MAX_BATCH
+    xs = [dev(R.relu_normal(40 + i, int(np.prod(s)), 1.0 + 0.5 * i).reshape(s)) for i, s in enumerate(shapes)]
+    minmax = torch.stack([ops.minmax(x) for x in xs])
+    minmax[3, 1] *= 0.5                                   # a frozen max smaller than the data: clipping
+    want = torch.zeros(len(xs), R.BINS + 1, dtype=torch.int64, device="cuda")
+    for i, x in enumerate(xs):
+        ops.hist_nonzero(x, minmax[i, 1:2], R.BINS, want[i])
+    got = torch.zeros_like(want)
+    ops.hist_nonzero_multi(xs, minmax, 2, 1, R.BINS, got)
+    assert torch.equal(got, want)
+    assert int(got.sum()) == sum(int((x != 0).sum()) for x in xs)
+
+
 _KL = [(n, l) for n, ls in R.KL_LEVELS.items() for l in ls]
 
 
