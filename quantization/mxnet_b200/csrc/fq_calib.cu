@@ -35,7 +35,7 @@ __device__ __forceinline__ void hist_slice(const float* __restrict__ x, int64_t 
   __syncthreads();
   auto one = [&](float v) {
     v = fminf(fmaxf(v, 0.f), max_);                         // ndarray.clip(0, max_); NaN -> 0 -> ignored
-    // zeros are ignored (:40); 0 < v <= max_ keeps trunc(v * sc) inside [0, bins]
+    // zeros are ignored (:40); 0 < v <= max_ keeps trunc(v * sc) inside [0, bins] (clamped anyway)
     if (v != 0.f) atomicAdd(&sh[min((unsigned int)__float2int_rz(__fmul_rn(v, sc)), (unsigned int)bins)], 1u);
   };
   if (vectorised) {

@@ -125,12 +125,29 @@ struct QDiv {
     q.guard = (d >= 1e-30f && d <= 1e30f) ? 4.76837158203125e-7f : INFINITY;
     return q;
   }
+  // near(q0, t): true when q0 is within the guard band of a rounding boundary (or NaN)
+  __device__ __forceinline__ bool near_tie(float q0, float t) const {
+    const float e = __fsub_rn(q0, t);                                  // |e| = distance to the integer, <= 0.5
+    return !(__fmaf_rn(fabsf(q0), guard, fabsf(e)) < 0.5f);            // true for NaN as well
+  }
   __device__ __forceinline__ float code(float v) const {
     const float q0 = __fmul_rn(v, r);
     const float t = rintf(q0);
-    const float e = fabsf(__fsub_rn(q0, t));                         // distance to the integer, <= 0.5
-    if (__fsub_rn(0.5f, e) > __fmul_rn(fabsf(q0), guard)) return t;  // false for NaN
+    if (!near_tie(q0, t)) return t;
     return quant_code(v, d);
+  }
+  // Four at once: straight-line fast path for the whole vector, one branch for the rare fix-up.
+  __device__ __forceinline__ float4 code4(float4 v) const {
+    const float q0 = __fmul_rn(v.x, r), q1 = __fmul_rn(v.y, r), q2 = __fmul_rn(v.z, r), q3 = __fmul_rn(v.w, r);
+    float4 t = make_float4(rintf(q0), rintf(q1), rintf(q2), rintf(q3));
+    const bool n0 = near_tie(q0, t.x), n1 = near_tie(q1, t.y), n2 = near_tie(q2, t.z), n3 = near_tie(q3, t.w);
+    if (n0 | n1 | n2 | n3) {
+      if (n0) t.x = quant_code(v.x, d);
+      if (n1) t.y = quant_code(v.y, d);
+      if (n2) t.z = quant_code(v.z, d);
+      if (n3) t.w = quant_code(v.w, d);
+    }
+    return t;
   }
 };
 
@@ -191,6 +208,38 @@ __device__ __forceinline__ void for_range(const float* __restrict__ x, int64_t b
     const int64_t j = REVERSE ? (nvec - 1 - i) : i;
     vf(base + 4 * j, KEEP ? ld_keep(p4 + j) : ld_stream(p4 + j));
   }
+}
+
+// Tile-interleaved walk over a 16 B aligned x[0, n): tile k of 4 * kThreads * kUnroll elements goes to
+// block k % gridDim.x, so at any moment the resident blocks stream one contiguous window of the
+// tensor (DRAM row locality for the mixed read/write streams of the elementwise kernels) instead of
+// gridDim.x far-apart slices.  REVERSE starts from the last tile (second pass: newest lines first).
+constexpr int64_t kTileElems = 4LL * kThreads * kUnroll;
+
+template <bool REVERSE, bool KEEP, class VF, class SF>
+__device__ __forceinline__ void for_tiles(const float* __restrict__ x, int64_t n, VF vf, SF sf) {
+  const int64_t nvec = n >> 2;
+  const int64_t ntiles = (n + kTileElems - 1) / kTileElems;
+  const float4* p4 = reinterpret_cast<const float4*>(x);
+  for (int64_t k = blockIdx.x; k < ntiles; k += gridDim.x) {
+    const int64_t tile = REVERSE ? (ntiles - 1 - k) : k;
+    const int64_t v0 = tile * (kTileElems / 4) + threadIdx.x;
+    float4 v[kUnroll];
+    if (v0 + (int64_t)(kUnroll - 1) * kThreads < nvec) {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) v[u] = KEEP ? ld_keep(p4 + v0 + u * kThreads) : ld_stream(p4 + v0 + u * kThreads);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) vf(4 * (v0 + u * kThreads), v[u]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t j = v0 + u * kThreads;
+        if (j < nvec) vf(4 * j, KEEP ? ld_keep(p4 + j) : ld_stream(p4 + j));
+      }
+    }
+  }
+  const int64_t tail0 = nvec << 2;
+  if (blockIdx.x == 0 && threadIdx.x < n - tail0) sf(tail0 + threadIdx.x, x[tail0 + threadIdx.x]);
 }
 
 // Grid-wide barrier for cooperative (co-resident) launches.  The last arriver runs `fn` (whole block)

@@ -12,6 +12,7 @@
 namespace fq {
 
 enum InputMode { kRangeOnly = 0, kOnline = 1, kOfflineTrack = 2 };
+constexpr int64_t kOnlineSplitElems = 1LL << 24;     // 64 MB of fp32: half of the 126 MB L2
 
 struct InputArgs {
   const float* x;
@@ -63,12 +64,9 @@ __device__ __forceinline__ void quantise_slice(const InputArgs& a, int64_t begin
   for_range<REVERSE, false>(
       a.x, begin, end,
       [&](int64_t i, float4 v) {
-        float4 c, o;
-        o.x = one(v.x, c.x);
-        o.y = one(v.y, c.y);
-        o.z = one(v.z, c.z);
-        o.w = one(v.w, c.w);
-        st_stream(reinterpret_cast<float4*>(a.y + i), o);
+        const float4 c = qd.code4(make_float4(clipf(v.x, lo, hi), clipf(v.y, lo, hi), clipf(v.z, lo, hi), clipf(v.w, lo, hi)));
+        st_stream(reinterpret_cast<float4*>(a.y + i),
+                  make_float4(__fmul_rn(c.x, s), __fmul_rn(c.y, s), __fmul_rn(c.z, s), __fmul_rn(c.w, s)));
         if (a.code_kind) put_code4(a.codes, a.code_kind, i, c);
       },
       [&](int64_t i, float v) {
@@ -79,7 +77,7 @@ __device__ __forceinline__ void quantise_slice(const InputArgs& a, int64_t begin
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads) input_path_kernel(InputArgs a) {
+__global__ void __launch_bounds__(kThreads, 6) input_path_kernel(InputArgs a) {
   __shared__ float red[32];
   __shared__ unsigned int s_last;
   const int64_t begin = (int64_t)blockIdx.x * a.per_block;
@@ -110,12 +108,11 @@ __global__ void __launch_bounds__(kThreads) input_path_kernel(InputArgs a) {
         for_range<false, false>(
             a.x, b0, b1,
             [&](int64_t i, float4 v) {
-              float4 c, o;
-              o.x = one(v.x, c.x);
-              o.y = one(v.y, c.y);
-              o.z = one(v.z, c.z);
-              o.w = one(v.w, c.w);
-              st_stream(reinterpret_cast<float4*>(a.y + i), o);
+              m = absmax4(m, v);
+              const float4 c =
+                  qd.code4(make_float4(clipf(v.x, lo, hi), clipf(v.y, lo, hi), clipf(v.z, lo, hi), clipf(v.w, lo, hi)));
+              st_stream(reinterpret_cast<float4*>(a.y + i),
+                        make_float4(__fmul_rn(c.x, s), __fmul_rn(c.y, s), __fmul_rn(c.z, s), __fmul_rn(c.w, s)));
               if (a.code_kind) put_code4(a.codes, a.code_kind, i, c);
             },
             [&](int64_t i, float v) {
@@ -146,6 +143,86 @@ __global__ void __launch_bounds__(kThreads) input_path_kernel(InputArgs a) {
     finish_rows(a.ws, a.rows, a.fin);
     if (threadIdx.x == 0) a.ws->ticket = 0;
   }
+}
+
+// Offline range + tracking for long rows (L >= one tile, so a tile meets at most two rows): one tile per
+// block like the plain quantiser, the per-row maxima ride along -- block reduction, then an atomicMax only
+// when the tile beats the row's running maximum (after the first few tiles almost never).
+__global__ void __launch_bounds__(kThreads, 6) offline_track_tiles_kernel(InputArgs a) {
+  __shared__ float red[2][kThreads / 32];
+  __shared__ float qp[4];
+  if (threadIdx.x == 0)
+    compute_qparams(a.fin.input_max[0], a.fin.bits, a.fin.is_signed, a.fin.lo_mode, a.fin.promotion, qp);
+  __syncthreads();
+  const float s = qp[1], lo = qp[2], hi = qp[3];
+  const QDiv qd = QDiv::make(qp[0]);
+  const int64_t nvec = a.n >> 2;
+  const float4* p4 = reinterpret_cast<const float4*>(a.x);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t tile = blockIdx.x; tile * (kTileElems / 4) < nvec; tile += gridDim.x) {
+    const int64_t row0 = (tile * kTileElems) / a.L;
+    const int64_t boundary = (row0 + 1) * a.L;
+    const int64_t v0 = tile * (kTileElems / 4) + threadIdx.x;
+    float4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t j = v0 + u * kThreads;
+      v[u] = j < nvec ? ld_stream(p4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t j = v0 + u * kThreads;
+      const int64_t i = 4 * j;
+      if (i + 3 < boundary) {
+        m0 = absmax4(m0, v[u]);
+      } else if (i >= boundary) {
+        m1 = absmax4(m1, v[u]);
+      } else {
+        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (i + t < boundary) m0 = fmaxf(m0, fabsf(e[t]));
+          else m1 = fmaxf(m1, fabsf(e[t]));
+        }
+      }
+      if (j < nvec) {
+        const float4 c = qd.code4(make_float4(clipf(v[u].x, lo, hi), clipf(v[u].y, lo, hi), clipf(v[u].z, lo, hi),
+                                              clipf(v[u].w, lo, hi)));
+        st_stream(reinterpret_cast<float4*>(a.y + i),
+                  make_float4(__fmul_rn(c.x, s), __fmul_rn(c.y, s), __fmul_rn(c.z, s), __fmul_rn(c.w, s)));
+        if (a.code_kind) put_code4(a.codes, a.code_kind, i, c);
+      }
+    }
+    m0 = warp_max(m0);
+    m1 = warp_max(m1);
+    __syncthreads();
+    if (lane == 0) {
+      red[0][warp] = m0;
+      red[1][warp] = m1;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      float m = 0.f;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) m = fmaxf(m, red[threadIdx.x][w]);
+      const int64_t r = row0 + threadIdx.x;
+      if (r < a.rows && m > __uint_as_float(__ldcg(&a.ws->rowmax[r]))) atomicMax(&a.ws->rowmax[r], __float_as_uint(m));
+    }
+  }
+  const int64_t tail0 = nvec << 2;
+  if (blockIdx.x == 0 && threadIdx.x < a.n - tail0) {
+    const int64_t i = tail0 + threadIdx.x;
+    const float x = a.x[i];
+    atomicMax(&a.ws->rowmax[i / a.L], __float_as_uint(fabsf(x)));
+    const float c = qd.code(clipf(x, lo, hi));
+    a.y[i] = __fmul_rn(c, s);
+    if (a.code_kind) put_code1(a.codes, a.code_kind, i, c);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) finish_rows_kernel(Workspace* ws, int64_t rows, FinishParams fin) {
+  finish_rows(ws, rows, fin);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -213,7 +290,7 @@ __device__ __forceinline__ void for_channels(const WeightArgs& a, int64_t begin,
 }
 
 template <bool FOLD>
-__global__ void __launch_bounds__(kThreads) weight_path_kernel(WeightArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) weight_path_kernel(WeightArgs a) {
   __shared__ float red[32];
   __shared__ unsigned int s_last;
   const int64_t begin = (int64_t)blockIdx.x * a.per_block;
@@ -295,7 +372,7 @@ __global__ void __launch_bounds__(kThreads) weight_path_kernel(WeightArgs a) {
         return rq;
       },
       [&](const RowQ& rq, int64_t i, float4 v) {
-        float4 q = make_float4(rq.q.code(v.x), rq.q.code(v.y), rq.q.code(v.z), rq.q.code(v.w));
+        const float4 q = rq.q.code4(v);
         st_stream(reinterpret_cast<float4*>(a.w_out + i),
                   make_float4(__fmul_rn(q.x, rq.s), __fmul_rn(q.y, rq.s), __fmul_rn(q.z, rq.s), __fmul_rn(q.w, rq.s)));
         if (a.code_kind) put_code4(a.codes, a.code_kind, i, q);
@@ -411,11 +488,27 @@ int fq_forward_online(const DLTensor* x_, int64_t n_samples, int bits, int is_si
   a.codes = codes.null ? nullptr : codes.data;
   FQ_TRY(code_kind_of(who, codes, x.numel, &a.code_kind) == 0);
 
+  if (!imax.null && a.L >= kTileElems) {   // offline range + tracking, long rows: streaming tile kernel
+    offline_track_tiles_kernel<<<tile_grid(a.n, 1 << 30), kThreads, 0, st>>>(a);
+    FQ_LAUNCH_CHECK("offline_track_tiles_kernel");
+    finish_rows_kernel<<<1, kThreads, 0, st>>>(a.ws, a.rows, a.fin);
+    FQ_LAUNCH_CHECK("finish_rows_kernel");
+    return 0;
+  }
   if (!imax.null) {   // offline range, current range still tracked: one pass
     const int grid = slice_grid(a.n, sm_count() * 8, &a.per_block);
     input_path_kernel<kOfflineTrack><<<grid, kThreads, 0, st>>>(a);
     FQ_LAUNCH_CHECK("input_path_kernel<offline>");
     return 0;
+  }
+  if (a.n >= kOnlineSplitElems) {
+    // Far larger than what L2 can hold between the passes: the cooperative kernel has nothing to gain, so
+    // run the range pass (which finishes with the Kahan mean and the scale on the device) and then the
+    // plain streaming quantiser; both run at copy speed and there is still no host round trip.
+    const int grid = slice_grid(a.n, sm_count() * 8, &a.per_block);
+    input_path_kernel<kRangeOnly><<<grid, kThreads, 0, st>>>(a);
+    FQ_LAUNCH_CHECK("input_path_kernel<range>");
+    return fq_forward_scalar(x_, qparams_, y_, codes_, stream);
   }
   int max_blocks = 0;
   FQ_TRY(coop_blocks(input_path_kernel<kOnline>, &max_blocks) == 0);

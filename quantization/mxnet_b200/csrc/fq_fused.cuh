@@ -26,6 +26,13 @@ inline int slice_grid(int64_t n, int max_blocks, int64_t* per_block) {
   return (int)((n + pb - 1) / pb > 0 ? (n + pb - 1) / pb : 1);
 }
 
+// Grid for the tile-interleaved elementwise kernels: one block per tile up to max_blocks.
+inline int tile_grid(int64_t n, int max_blocks) {
+  int64_t tiles = (n + kTileElems - 1) / kTileElems;
+  if (tiles < 1) tiles = 1;
+  return (int)(tiles > max_blocks ? max_blocks : tiles);
+}
+
 inline bool check_quant_args(const char* who, int bits, int lo_mode, int promotion) {
   if (bits < 2 || bits > 24) {
     set_error("%s: bits=%d outside [2, 24]", who, bits);

@@ -50,12 +50,10 @@ struct ScalarQuant {
     return __fmul_rn(c, s);
   }
   __device__ __forceinline__ void vec(int64_t i, float4 v) const {
-    float4 c, o;
-    o.x = one(v.x, c.x);
-    o.y = one(v.y, c.y);
-    o.z = one(v.z, c.z);
-    o.w = one(v.w, c.w);
-    st_stream(reinterpret_cast<float4*>(y + i), o);
+    if (CLIP) v = make_float4(clipf(v.x, lo, hi), clipf(v.y, lo, hi), clipf(v.z, lo, hi), clipf(v.w, lo, hi));
+    const float4 c = q.code4(v);
+    st_stream(reinterpret_cast<float4*>(y + i),
+              make_float4(__fmul_rn(c.x, s), __fmul_rn(c.y, s), __fmul_rn(c.z, s), __fmul_rn(c.w, s)));
     code.put4(i, c);
   }
   __device__ __forceinline__ void sca(int64_t i, float v) const {
@@ -65,10 +63,14 @@ struct ScalarQuant {
   }
 };
 
+// One tile of 4 * kThreads * kUnroll elements per block, no loop: like a plain copy kernel the grid
+// is as large as the tensor, registers stay low enough for 6+ resident blocks per SM and every
+// thread has kUnroll 16 B loads in flight before it touches the data.
 template <bool CLIP, class Code>
-__global__ void __launch_bounds__(kThreads) forward_scalar_kernel(const float* __restrict__ x, int64_t n,
-                                                                  int64_t per_block, const float* __restrict__ qp_dev,
-                                                                  ScalarQuant<CLIP, Code> op, int vectorised) {
+__global__ void __launch_bounds__(kThreads, 6) forward_scalar_kernel(const float* __restrict__ x, int64_t n,
+                                                                     int64_t per_block,
+                                                                     const float* __restrict__ qp_dev,
+                                                                     ScalarQuant<CLIP, Code> op, int vectorised) {
   if (qp_dev != nullptr) {
     op.d = __ldg(qp_dev + FQ_QP_D);
     op.s = __ldg(qp_dev + FQ_QP_S);
@@ -77,10 +79,25 @@ __global__ void __launch_bounds__(kThreads) forward_scalar_kernel(const float* _
   }
   op.prepare();
   if (vectorised) {
-    const int64_t begin = (int64_t)blockIdx.x * per_block;
-    const int64_t end = min(n, begin + per_block);
-    for_range<false, false>(
-        x, begin, end, [&](int64_t i, float4 v) { op.vec(i, v); }, [&](int64_t i, float v) { op.sca(i, v); });
+    const int64_t nvec = n >> 2;
+    const float4* p4 = reinterpret_cast<const float4*>(x);
+    for (int64_t tile = blockIdx.x; tile * (kTileElems / 4) < nvec; tile += gridDim.x) {
+      const int64_t v0 = tile * (kTileElems / 4) + threadIdx.x;
+      if (v0 + (kUnroll - 1) * kThreads < nvec) {
+        float4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream(p4 + v0 + u * kThreads);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) op.vec(4 * (v0 + u * kThreads), v[u]);
+      } else {
+        for (int u = 0; u < kUnroll; ++u) {
+          const int64_t j = v0 + u * kThreads;
+          if (j < nvec) op.vec(4 * j, ld_stream(p4 + j));
+        }
+      }
+    }
+    const int64_t tail0 = nvec << 2;
+    if (blockIdx.x == 0 && threadIdx.x < n - tail0) op.sca(tail0 + threadIdx.x, x[tail0 + threadIdx.x]);
   } else {   // some pointer is not 16 B aligned: plain scalar grid-stride loop
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
       op.sca(i, x[i]);
@@ -88,6 +105,67 @@ __global__ void __launch_bounds__(kThreads) forward_scalar_kernel(const float* _
 }
 
 // ---- per-row scale tensor (weights): y = roundf(x / (s_r + 1e-10)) * s_r -------------------------
+// Long rows (L >= one tile, so a tile meets at most two rows): one tile per block like the scalar kernel,
+// with the two candidate rows' quantisers held in registers.
+template <class Code>
+__global__ void __launch_bounds__(kThreads, 6) forward_rows_tiles_kernel(const float* __restrict__ x, int64_t n,
+                                                                         int64_t L, const float* __restrict__ scale,
+                                                                         float* __restrict__ y, Code code) {
+  const int64_t nvec = n >> 2;
+  const float4* p4 = reinterpret_cast<const float4*>(x);
+  const int64_t rows = n / L;
+  for (int64_t tile = blockIdx.x; tile * (kTileElems / 4) < nvec; tile += gridDim.x) {
+    const int64_t first = tile * kTileElems;
+    const int64_t row0 = first / L;
+    const int64_t boundary = (row0 + 1) * L;
+    const float s0 = __ldg(scale + row0);
+    const float s1 = __ldg(scale + min(row0 + 1, rows - 1));
+    const QDiv q0 = QDiv::make(__fadd_rn(s0, 1e-10f)), q1 = QDiv::make(__fadd_rn(s1, 1e-10f));
+    const int64_t v0 = tile * (kTileElems / 4) + threadIdx.x;
+    float4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t j = v0 + u * kThreads;
+      v[u] = j < nvec ? ld_stream(p4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t j = v0 + u * kThreads;
+      if (j >= nvec) continue;
+      const int64_t i = 4 * j;
+      float4 c, o;
+      if (i + 3 < boundary) {
+        c = q0.code4(v[u]);
+        o = make_float4(__fmul_rn(c.x, s0), __fmul_rn(c.y, s0), __fmul_rn(c.z, s0), __fmul_rn(c.w, s0));
+      } else if (i >= boundary) {
+        c = q1.code4(v[u]);
+        o = make_float4(__fmul_rn(c.x, s1), __fmul_rn(c.y, s1), __fmul_rn(c.z, s1), __fmul_rn(c.w, s1));
+      } else {       // the float4 straddles the row boundary (L % 4 != 0)
+        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        float cc[4], oo[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const bool lo_row = i + t < boundary;
+          cc[t] = lo_row ? q0.code(e[t]) : q1.code(e[t]);
+          oo[t] = __fmul_rn(cc[t], lo_row ? s0 : s1);
+        }
+        c = make_float4(cc[0], cc[1], cc[2], cc[3]);
+        o = make_float4(oo[0], oo[1], oo[2], oo[3]);
+      }
+      st_stream(reinterpret_cast<float4*>(y + i), o);
+      code.put4(i, c);
+    }
+  }
+  const int64_t tail0 = nvec << 2;
+  if (blockIdx.x == 0 && threadIdx.x < n - tail0) {
+    const int64_t i = tail0 + threadIdx.x;
+    const float s = __ldg(scale + i / L);
+    const float c = quant_code(x[i], __fadd_rn(s, 1e-10f));
+    y[i] = __fmul_rn(c, s);
+    code.put1(i, c);
+  }
+}
+
 template <class Code>
 __global__ void __launch_bounds__(kThreads) forward_rows_kernel(const float* __restrict__ x, int64_t n, int64_t L,
                                                                 int64_t per_block, const float* __restrict__ scale,
@@ -119,21 +197,39 @@ __global__ void __launch_bounds__(kThreads) forward_rows_kernel(const float* __r
 }
 
 // ---- STE backward with the clip mask (extension; the reference's backward is the identity) ------
-__global__ void __launch_bounds__(kThreads) ste_mask_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                                            const float* __restrict__ qp, float* __restrict__ dx,
-                                                            int64_t n, int64_t per_block, int vectorised) {
+__global__ void __launch_bounds__(kThreads, 6) ste_mask_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                               const float* __restrict__ qp, float* __restrict__ dx,
+                                                               int64_t n, int64_t per_block, int vectorised) {
   const float lo = __ldg(qp + FQ_QP_LO), hi = __ldg(qp + FQ_QP_HI);
   auto m = [&](float g, float v) { return (v >= lo && v <= hi) ? g : 0.f; };
   if (vectorised) {
-    const int64_t begin = (int64_t)blockIdx.x * per_block;
-    const int64_t end = min(n, begin + per_block);
-    for_range<false, false>(
-        dy, begin, end,
-        [&](int64_t i, float4 g) {
-          const float4 v = ld_stream(reinterpret_cast<const float4*>(x + i));
-          st_stream(reinterpret_cast<float4*>(dx + i), make_float4(m(g.x, v.x), m(g.y, v.y), m(g.z, v.z), m(g.w, v.w)));
-        },
-        [&](int64_t i, float g) { dx[i] = m(g, x[i]); });
+    const int64_t nvec = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(dy);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (int64_t tile = blockIdx.x; tile * (kTileElems / 4) < nvec; tile += gridDim.x) {
+      const int64_t v0 = tile * (kTileElems / 4) + threadIdx.x;
+      float4 g[kUnroll / 2], v[kUnroll / 2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {       // two half tiles: 2 x (kUnroll/2) x 2 loads in flight per thread
+#pragma unroll
+        for (int u = 0; u < kUnroll / 2; ++u) {
+          const int64_t j = v0 + (h * (kUnroll / 2) + u) * kThreads;
+          if (j < nvec) {
+            g[u] = ld_stream(g4 + j);
+            v[u] = ld_stream(x4 + j);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll / 2; ++u) {
+          const int64_t j = v0 + (h * (kUnroll / 2) + u) * kThreads;
+          if (j < nvec)
+            st_stream(reinterpret_cast<float4*>(dx) + j,
+                      make_float4(m(g[u].x, v[u].x), m(g[u].y, v[u].y), m(g[u].z, v[u].z), m(g[u].w, v[u].w)));
+        }
+      }
+    }
+    const int64_t tail0 = nvec << 2;
+    if (blockIdx.x == 0 && threadIdx.x < n - tail0) dx[tail0 + threadIdx.x] = m(dy[tail0 + threadIdx.x], x[tail0 + threadIdx.x]);
   } else {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
       dx[i] = m(dy[i], x[i]);
@@ -215,8 +311,8 @@ static int forward_scalar_impl(const char* who, const DLTensor* x_, const float*
   if (x.numel == 0) return 0;
   const int64_t n = x.numel;
   const int vec = aligned16(x.data) && aligned16(y.data) && (codes.null || aligned16(codes.data));
-  int64_t per_block;
-  const int grid = vec ? slice_grid(n, sm_count() * 8, &per_block) : ew_grid(n);
+  int64_t per_block = 0;
+  const int grid = vec ? tile_grid(n, 1 << 30) : ew_grid(n);      // one tile per block
   cudaStream_t st = (cudaStream_t)stream;
   return with_code_sink(who, codes, n, [&](auto sink) -> int {
     using Code = decltype(sink);
@@ -269,6 +365,12 @@ int fq_forward_rows(const DLTensor* x_, int64_t rows, const DLTensor* scale_, co
   const int grid = (vec && L >= 1024) ? slice_grid(n, sm_count() * 8, &per_block) : ew_grid(n);
   cudaStream_t st = (cudaStream_t)stream;
   return with_code_sink("fq_forward_rows", codes, n, [&](auto sink) -> int {
+    if (vec && L >= kTileElems) {
+      forward_rows_tiles_kernel<<<tile_grid(n, 1 << 30), kThreads, 0, st>>>(x.as<const float>(), n, L,
+                                                                          sc.as<const float>(), y.as<float>(), sink);
+      FQ_LAUNCH_CHECK("forward_rows_tiles_kernel");
+      return 0;
+    }
     forward_rows_kernel<<<grid, kThreads, 0, st>>>(x.as<const float>(), n, L, per_block, sc.as<const float>(),
                                                    y.as<float>(), sink, vec);
     FQ_LAUNCH_CHECK("forward_rows_kernel");
@@ -296,7 +398,7 @@ int fq_ste_backward(const DLTensor* dy_, const DLTensor* x_, const DLTensor* qpa
   if (dy.numel == 0) return 0;
   const int vec = aligned16(dy.data) && aligned16(x.data) && aligned16(dx.data);
   int64_t per_block = 0;
-  const int grid = vec ? slice_grid(dy.numel, sm_count() * 8, &per_block) : ew_grid(dy.numel);
+  const int grid = vec ? tile_grid(dy.numel, 1 << 30) : ew_grid(dy.numel);
   ste_mask_kernel<<<grid, kThreads, 0, st>>>(dy.as<const float>(), x.as<const float>(), qp.as<const float>(),
                                              dx.as<float>(), dy.numel, per_block, vec);
   FQ_LAUNCH_CHECK("ste_mask_kernel");
