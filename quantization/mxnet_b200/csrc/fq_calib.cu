@@ -102,46 +102,52 @@ __global__ void hist_accumulate_kernel(unsigned long long* __restrict__ counts, 
 // ---------------------------------------------------------------------------------------------
 // KL threshold search: one block per candidate bin count i
 // ---------------------------------------------------------------------------------------------
+// The three left-to-right sums per candidate (Python's builtin sum: tail/total of P, the sum of Q, the
+// divergence) are strictly sequential chains, so the kernel is bound by how many chains are in flight,
+// not by bandwidth: small blocks (kKlThreads) and a small footprint (Q and the level buckets in shared
+// memory, the histogram read through L1) keep ~12 candidates resident per SM; the tail chain and the
+// prefix chain of P run on different warps at the same time.
+constexpr int kKlThreads = 64;
+
 template <bool LEGACY>
-__global__ void __launch_bounds__(kThreads) kl_candidate_kernel(const float* __restrict__ hist_all, int n_data,
-                                                                int levels, int min_bins, int bins,
-                                                                double* __restrict__ div_all) {
+__global__ void __launch_bounds__(kKlThreads) kl_candidate_kernel(const float* __restrict__ hist_all, int n_data,
+                                                                  int levels, int min_bins, int bins,
+                                                                  double* __restrict__ div_all) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int i = min_bins + blockIdx.x;
-  const float* hist = hist_all + (int64_t)blockIdx.y * n_data;
+  const float* __restrict__ H = hist_all + (int64_t)blockIdx.y * n_data;
   double* div = div_all + (int64_t)blockIdx.y * bins;
   double* cand = reinterpret_cast<double*>(smem_raw);                 // [levels]
   double* Q = cand + levels;                                          // [bins]
-  float* H = reinterpret_cast<float*>(Q + bins);                      // [n_data]
-  float* ref = H + ((n_data + 3) & ~3);                               // [bins]
   __shared__ float s_last, s_total;
-  __shared__ double s_qsum;
+  __shared__ double s_tail, s_prefix, s_qsum;
   const int tid = threadIdx.x, nt = blockDim.x;
-
-  for (int j = tid; j < n_data; j += nt) H[j] = hist[j];
-  __syncthreads();
 
   // P: tail mass folded into bin i-1, then normalised.  Python's builtin sum is strictly left to
   // right; its accumulator is float32 under NEP 50 and float64 under legacy promotion (:143-145).
-  if (tid == 0) {
+  if (tid == 0) {            // sum(data[i:])
     if (LEGACY) {
       double tail = 0.0;
-      for (int j = i; j < n_data; ++j) tail = __dadd_rn(tail, (double)H[j]);
-      const float last = (float)__dadd_rn((double)H[i - 1], tail);
-      double tot = 0.0;
-      for (int j = 0; j < i - 1; ++j) tot = __dadd_rn(tot, (double)H[j]);
-      tot = __dadd_rn(tot, (double)last);
-      s_last = last;
-      s_total = (float)tot;                  // float32 array /= float64 scalar: the scalar is cast first
+#pragma unroll 8
+      for (int j = i; j < n_data; ++j) tail = __dadd_rn(tail, (double)__ldg(H + j));
+      s_tail = tail;
     } else {
       float tail = 0.f;
-      for (int j = i; j < n_data; ++j) tail = __fadd_rn(tail, H[j]);
-      const float last = __fadd_rn(H[i - 1], tail);
-      float tot = 0.f;
-      for (int j = 0; j < i - 1; ++j) tot = __fadd_rn(tot, H[j]);
-      tot = __fadd_rn(tot, last);
-      s_last = last;
-      s_total = tot;
+#pragma unroll 8
+      for (int j = i; j < n_data; ++j) tail = __fadd_rn(tail, __ldg(H + j));
+      s_tail = (double)tail;
+    }
+  } else if (tid == 32) {    // the first i-1 terms of sum(ref_distribution), which the tail does not touch
+    if (LEGACY) {
+      double pre = 0.0;
+#pragma unroll 8
+      for (int j = 0; j < i - 1; ++j) pre = __dadd_rn(pre, (double)__ldg(H + j));
+      s_prefix = pre;
+    } else {
+      float pre = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < i - 1; ++j) pre = __fadd_rn(pre, __ldg(H + j));
+      s_prefix = (double)pre;
     }
   }
   // Q buckets: cand[k] = sum of hist[j] with floor(j*levels/i) == k, float64, ascending j (:149-152)
@@ -149,14 +155,25 @@ __global__ void __launch_bounds__(kThreads) kl_candidate_kernel(const float* __r
     const int j0 = (int)(((long long)k * i + levels - 1) / levels);
     const int j1 = (int)(((long long)(k + 1) * i + levels - 1) / levels);
     double c = 0.0;
-    for (int j = j0; j < j1 && j < i; ++j) c = __dadd_rn(c, (double)H[j]);
+    for (int j = j0; j < j1 && j < i; ++j) c = __dadd_rn(c, (double)__ldg(H + j));
     cand[k] = c;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (LEGACY) {
+      const float last = (float)__dadd_rn((double)__ldg(H + i - 1), s_tail);
+      s_last = last;
+      s_total = (float)__dadd_rn(s_prefix, (double)last);   // float32 array /= float64 scalar: the scalar is cast first
+    } else {
+      const float last = __fadd_rn(__ldg(H + i - 1), (float)s_tail);
+      s_last = last;
+      s_total = __fadd_rn((float)s_prefix, last);
+    }
   }
   __syncthreads();
   const float total = s_total, last = s_last;
   for (int j = tid; j < i; j += nt) {
-    const float p = __fdiv_rn(j == i - 1 ? last : H[j], total);
-    ref[j] = p;
+    const float p = __fdiv_rn(j == i - 1 ? last : __ldg(H + j), total);
     // linear interpolation between the neighbouring buckets (:154-158), no FMA contraction
     const double t = __ddiv_rn((double)((long long)j * levels), (double)i);
     const int fl = (int)t;
@@ -169,6 +186,7 @@ __global__ void __launch_bounds__(kThreads) kl_candidate_kernel(const float* __r
   __syncthreads();
   if (tid == 0) {
     double qs = 0.0;
+#pragma unroll 8
     for (int j = 0; j < i; ++j) qs = __dadd_rn(qs, Q[j]);
     s_qsum = qs;
   }
@@ -178,7 +196,7 @@ __global__ void __launch_bounds__(kThreads) kl_candidate_kernel(const float* __r
     const double qn = __ddiv_rn(Q[j], qsum);
     double term = 0.0;                                       // entries with Q == 0 are dropped (:164-165)
     if (qn != 0.0) {
-      const double p = (double)ref[j];
+      const double p = (double)__fdiv_rn(j == i - 1 ? last : __ldg(H + j), total);
       term = __dmul_rn(p, log(__ddiv_rn(p, qn)));
     }
     Q[j] = term;
@@ -186,6 +204,7 @@ __global__ void __launch_bounds__(kThreads) kl_candidate_kernel(const float* __r
   __syncthreads();
   if (tid == 0) {
     double d = 0.0;
+#pragma unroll 8
     for (int j = 0; j < i; ++j) d = __dadd_rn(d, Q[j]);
     div[i] = d;
   }
@@ -365,10 +384,10 @@ int fq_kl_search(const DLTensor* hist_, int levels, int min_bins, int bins, int 
   cudaStream_t st = (cudaStream_t)stream;
   const int ncand = bins - min_bins;
   if (ncand > 0) {
-    const size_t smem = sizeof(double) * (levels + bins) + sizeof(float) * (((n_data + 3) & ~3) + bins);
+    const size_t smem = sizeof(double) * (levels + bins);
     auto kern = (promotion == FQ_PROMOTION_LEGACY) ? kl_candidate_kernel<true> : kl_candidate_kernel<false>;
     FQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(ncand, layers), kThreads, smem, st>>>(hist.as<const float>(), n_data, levels, min_bins, bins,
+    kern<<<dim3(ncand, layers), kKlThreads, smem, st>>>(hist.as<const float>(), n_data, levels, min_bins, bins,
                                                       dv.as<double>());
     FQ_LAUNCH_CHECK("kl_candidate_kernel");
   }

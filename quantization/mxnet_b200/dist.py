@@ -1,0 +1,133 @@
+"""Data-parallel plumbing for calibration and QAT: one process per GPU, batch sharded by sample,
+weights replicated.  Every statistic on this path is a max, an integer sum or a mean of
+per-sample maxima, so the collectives below make an N-GPU run reproduce the single-GPU result:
+
+  first-batch maxima (KL)      all_reduce(MAX)   [L]          exact
+  per-batch histogram counts   all_reduce(SUM)   [L, bins+1]  exact (int64)
+  per-sample input maxima      all_gather        [N]          exact; the Kahan mean then runs on every rank
+  QAT gradients                all_reduce(SUM)/R one flat fp32 bucket
+
+All messages are tiny (<= 442 KB) except the gradient bucket; they go through torch.distributed
+(NCCL over NVLink on GPUs, gloo in the CPU tests).  Nothing here launches a kernel of its own.
+"""
+import torch
+import torch.distributed as dist
+
+__all__ = ["active_group", "shard_batch", "sync_first_batch_minmax", "sync_counts", "gather_per_sample",
+           "GradBucket", "broadcast_parameters", "enable_data_parallel", "disable_data_parallel"]
+
+
+def active_group(group=None):
+    """The process group to use, or None when running single-process."""
+    if group is not None:
+        return group
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.group.WORLD
+    return None
+
+
+def shard_batch(x, rank=None, world=None, group=None):
+    """Contiguous N/R samples for this rank (N must divide evenly, as per-GPU batches are fixed)."""
+    g = active_group(group)
+    if rank is None:
+        rank = dist.get_rank(g) if g is not None else 0
+    if world is None:
+        world = dist.get_world_size(g) if g is not None else 1
+    n = x.shape[0]
+    if n % world != 0:
+        raise ValueError("batch of %d samples does not split over %d ranks" % (n, world))
+    per = n // world
+    return x[rank * per:(rank + 1) * per]
+
+
+def sync_first_batch_minmax(minmax, group=None):
+    """minmax: [L, 2] = {min, max} per layer of this rank's shard of batch 0 -> global, in place."""
+    g = active_group(group)
+    if g is None:
+        return minmax
+    mn = minmax[:, 0].contiguous()
+    mx = minmax[:, 1].contiguous()
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=g)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=g)
+    minmax[:, 0].copy_(mn)
+    minmax[:, 1].copy_(mx)
+    return minmax
+
+
+def sync_counts(counts, group=None):
+    """counts: int64 [L, bins+1] of this rank's shard -> global integer counts, in place (one collective)."""
+    g = active_group(group)
+    if g is not None:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=g)
+    return counts
+
+
+def gather_per_sample(per_sample, group=None):
+    """[N/R] per-sample maxima of this rank -> [N] in rank (= sample) order on every rank."""
+    g = active_group(group)
+    if g is None:
+        return per_sample
+    world = dist.get_world_size(g)
+    out = torch.empty(world * per_sample.numel(), dtype=per_sample.dtype, device=per_sample.device)
+    dist.all_gather_into_tensor(out, per_sample.contiguous(), group=g)
+    return out
+
+
+def broadcast_parameters(net, src=0, group=None):
+    g = active_group(group)
+    if g is None:
+        return
+    with torch.no_grad():
+        for t in list(net.parameters()) + list(net.buffers()):
+            dist.broadcast(t.data, src=src, group=g)
+
+
+class GradBucket:
+    """All gradients of a net in ONE flat fp32 buffer: a single all-reduce per QAT step."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = None
+
+    def all_reduce_mean(self):
+        g = active_group(self.group)
+        if g is None or not self.params:
+            return
+        dev = self.params[0].device
+        if self.flat is None or self.flat.device != dev:
+            self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None:
+                self.flat[off:off + n].zero_()
+            else:
+                self.flat[off:off + n].copy_(p.grad.reshape(-1))
+            off += n
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=g)
+        self.flat.div_(dist.get_world_size(g))
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None:
+                p.grad = self.flat[off:off + n].reshape(p.shape).clone()
+            else:
+                p.grad.copy_(self.flat[off:off + n].reshape(p.shape))
+            off += n
+
+
+def enable_data_parallel(net, group=None):
+    """Make every converted block compute its ONLINE input range over the global batch: the block keeps
+    its shard's per-sample maxima, all-gathers them and runs the reference's Kahan mean on every rank."""
+    g = active_group(group)
+    for m in net.collect_quantized_blocks():
+        m._fq_dist_group = g
+    return net
+
+
+def disable_data_parallel(net):
+    for m in net.collect_quantized_blocks():
+        m._fq_dist_group = None
+    return net

@@ -1,0 +1,124 @@
+"""nn/quantized_conv.py of the reference: a stand-alone Conv2D that really quantises to integers
+(8-bit hard-coded, no zero point) and dequantises the int32 accumulator.
+
+On the hot path: ``quantize`` / ``_quantize`` / ``dequantize`` -- range reduction and
+integer codes run in the CUDA kernels.  The convolution itself stays a framework call on
+integer-valued float tensors, exactly as the reference computes it with ``F.dot`` on float32 casts
+(nn/quantized_conv.py:149-153); an int8 tensor-core convolution is outside the north star.
+The reference's im2col output-size quirk (``(H - kh + 1) // sh``, :49) is not reproduced: the
+framework convolution yields the correct number of windows.
+"""
+import torch
+from torch import nn
+
+from .. import ops
+
+__all__ = ['Conv2D']
+
+
+def _int2tuple(x):
+    return (x, ) * 2 if isinstance(x, int) else tuple(x)
+
+
+def _quantize(x, min_range, max_range):
+    """clip -> scale (max/127 if symmetric else (max-min)/255) -> round -> int32 codes.  (:54-61)
+    ``min_range`` / ``max_range``: Python numbers or a (2,) device tensor in ``min_range``."""
+    if isinstance(min_range, torch.Tensor) and max_range is None:
+        rng = min_range
+    else:
+        rng = torch.tensor([float(min_range), float(max_range)], dtype=torch.float32, device=x.device)
+    return ops.qconv_quantize(x, rng)
+
+
+def quantize(x, out_type='int8'):
+    """(:63-72) int8: symmetric around 0 with max |x|; uint8: [min x, max x] without a zero point."""
+    if out_type == 'int8':
+        mx = ops.absmax_rows(x, 1)
+        rng = torch.cat([-mx, mx])
+    elif out_type == 'uint8':
+        rng = ops.minmax(x)
+    else:
+        raise ValueError("unknown out type: ", out_type)
+    return ops.qconv_quantize(x, rng)
+
+
+def dequantize(x, scale):
+    """(:74-76) float(x) * scale; ``scale`` may be the product tensor or a pair (s_in, s_w)."""
+    if isinstance(scale, tuple):
+        return ops.qconv_dequantize(x, scale[0], scale[1])
+    one = torch.ones(1, dtype=torch.float32, device=x.device)
+    return ops.qconv_dequantize(x, scale, one)
+
+
+class Conv2D(nn.Module):
+    def __init__(self, channels, kernel_size, strides, padding, in_channels, groups=1,
+                 activation=None, use_bias=True, quantized=False,
+                 input_dtype='float32', weight_dtype='float32',
+                 weight_initializer=None, bias_initializer='zero',
+                 prefix=None, params=None):
+        super(Conv2D, self).__init__()
+        self._channels = channels
+        self._in_channels = in_channels
+        self._groups = groups
+        assert in_channels % groups == 0 and channels % groups == 0
+        self._kernel_size = _int2tuple(kernel_size)
+        self._strides = _int2tuple(strides)
+        self._padding = _int2tuple(padding)
+        self._quantized = quantized
+        self._input_dtype = input_dtype
+        self._weight_dtype = weight_dtype
+        self._input_range = None
+        self._weight_range = None
+
+        self.weight = nn.Parameter(torch.empty(channels, in_channels // groups, *self._kernel_size))
+        nn.init.uniform_(self.weight, -0.07, 0.07)          # mxnet's default Uniform(0.07)
+        self.bias = nn.Parameter(torch.zeros(channels)) if use_bias else None
+        self.act = nn.ReLU() if activation == 'relu' else None
+        if activation not in (None, 'relu'):
+            raise NotImplementedError("activation %r" % (activation,))
+
+    def forward(self, inputs):
+        weight, bias = self.weight, self.bias
+        ph, pw = self._padding
+        inputs = nn.functional.pad(inputs, (pw, pw, ph, ph))
+        if self._quantized:
+            if self._input_range is None:
+                inputs_q, in_scale = quantize(inputs, self._input_dtype)
+            else:
+                inputs_q, in_scale = _quantize(inputs, *self._input_range)
+            if self._weight_range is None:
+                weight_q, w_scale = quantize(weight.detach(), self._weight_dtype)
+            else:
+                weight_q, w_scale = _quantize(weight.detach(), *self._weight_range)
+            bias_q = None
+            if bias is not None:
+                # b_scale = s_in * s_w; clip to +-b_scale * 2^31; round; int32   (:122-127)
+                b_scale = in_scale * w_scale
+                b_max = b_scale * float(2 ** 31)
+                _, bias_q = ops.forward_scalar(bias.detach(), torch.cat([b_scale, b_scale, -b_max, b_max]),
+                                               codes_dtype=torch.int32)
+            # the reference multiplies float32 casts of the integer codes and casts the result to int32
+            acc = nn.functional.conv2d(inputs_q.float(), weight_q.float(), None, self._strides, 0, 1, self._groups)
+            acc = acc.to(torch.int32)
+            if bias_q is not None:
+                acc = acc + bias_q.reshape(1, -1, 1, 1)
+            if self.act is not None:
+                acc = torch.clamp(acc, min=0)
+            return dequantize(acc.contiguous(), (in_scale, w_scale))
+        y = nn.functional.conv2d(inputs, weight, bias, self._strides, 0, 1, self._groups)
+        return self.act(y) if self.act is not None else y
+
+    def __repr__(self):
+        s = '{name}({mapping}, kernel_size={ks}, stride={st}'
+        if self._padding != (0,) * len(self._kernel_size):
+            s += ', padding={}'.format(self._padding)
+        if self._groups != 1:
+            s += ', groups={}'.format(self._groups)
+        if self.bias is None:
+            s += ', bias=False'
+        if self.act:
+            s += ', {}'.format(self.act)
+        s += ')'
+        shape = self.weight.shape
+        return s.format(name=self.__class__.__name__, ks=self._kernel_size, st=self._strides,
+                        mapping='{0} -> {1}'.format(shape[1] if shape[1] else None, shape[0]))

@@ -22,22 +22,45 @@ QuantizedArgs = namedtuple("ConvQuantizedArgs",
                            "fake_bn wino_quantize")
 
 
+def _track_range(x, m):
+    """current_input_max of this block (convert_conv2d.py:56).  With data parallelism the shard's
+    per-sample maxima are all-gathered and the Kahan mean is taken over the global batch on every rank."""
+    group = getattr(m, "_fq_dist_group", None)
+    if group is None:
+        return False
+    from ... import dist as fqdist
+    per = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    ops.input_range(x, cur_max=m.current_input_max, per_sample=per)
+    ops.mean_kahan(fqdist.gather_per_sample(per, group), out=m.current_input_max)
+    return True
+
+
 class _InputPath(torch.autograd.Function):
     """convert_conv2d.py:56-66 in one launch; backward = identity (ste_func.py:43-44)."""
 
     @staticmethod
     def forward(ctx, x, m, lo_mode):
         qa = m.quantize_args
+        if _track_range(x, m):      # data parallel: range over the global batch, then the plain quantiser
+            max_ = m.input_max.data if m.quantize_input_offline else m.current_input_max
+            ops.scale_from_max(max_, qa.in_width, qa.in_signed, lo_mode, qparams=m._fq_qparams)
+            return ops.forward_scalar(x, m._fq_qparams)
         y, _, _ = ops.forward_online(
             x, qa.in_width, qa.in_signed, lo_mode,
             input_max=m.input_max.data if m.quantize_input_offline else None,
-            quantize=True, cur_max=m.current_input_max, qparams=m._fq_qparams,
-            per_sample=getattr(m, "_fq_per_sample", None))
+            quantize=True, cur_max=m.current_input_max, qparams=m._fq_qparams)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         return dy, None, None
+
+
+def _range_only(x, m):
+    """quantize_input switched off: the range is still tracked (convert_conv2d.py:55-57)."""
+    if not _track_range(x, m):
+        ops.forward_online(x, m.quantize_args.in_width, m.quantize_args.in_signed, ops.LO_ZERO, quantize=False,
+                           cur_max=m.current_input_max)
 
 
 class _WeightPath(torch.autograd.Function):
@@ -99,8 +122,7 @@ def _conv2d_forward(self, x):
                 lo_mode = ops.LO_NEG_MAX if qa.in_signed else ops.LO_ZERO
                 x = _InputPath.apply(x, self, lo_mode)
             else:       # the range is still tracked (convert_conv2d.py:56)
-                ops.forward_online(x.detach(), qa.in_width, qa.in_signed, ops.LO_ZERO, quantize=False,
-                                   cur_max=self.current_input_max, per_sample=getattr(self, "_fq_per_sample", None))
+                _range_only(x.detach(), self)
         # Simulate quantization for weight (:69-97)
         if self.fixed_params != 1:
             if fold:

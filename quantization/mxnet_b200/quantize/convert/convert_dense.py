@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from ... import ops
-from .convert_conv2d import _InputPath, _WeightPath
+from .convert_conv2d import _InputPath, _WeightPath, _range_only
 
 __all__ = ['gen_dense_converter']
 
@@ -27,8 +27,7 @@ def _dense_forward(self, x):
             if self.quantize_input:
                 x = _InputPath.apply(x, self, ops.LO_ZERO)
             else:
-                ops.forward_online(x.detach(), qa.in_width, qa.in_signed, ops.LO_ZERO, quantize=False,
-                                   cur_max=self.current_input_max, per_sample=getattr(self, "_fq_per_sample", None))
+                _range_only(x.detach(), self)
         rows = self.out_features if qa.quant_type == 'channel' else 1
         weight_q, _ = _WeightPath.apply(weight, None, None, None, None, None, rows, qa.wt_width)
     else:

@@ -16,18 +16,10 @@ import numpy as np
 import torch
 from tqdm import tqdm
 
+from .. import dist as fqdist
 from .. import ops
 
 __all__ = ['collect_feature_maps', 'kl_calibrate', 'kl_calibrate_all']
-
-
-def _dist_group(group):
-    import torch.distributed as dist
-    if group is not None:
-        return dist, group
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        return dist, dist.group.WORLD
-    return None, None
 
 
 class _Collector(dict):
@@ -51,7 +43,7 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
     quantized_blocks = net.collect_quantized_blocks()
     n_blk = len(quantized_blocks)
     index = {id(b): i for i, b in enumerate(quantized_blocks)}
-    dist, group = _dist_group(group)
+    group = fqdist.active_group(group)
 
     state = {}      # allocated on the first hooked tensor's device
 
@@ -100,13 +92,7 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
                             mm2 = ops.minmax(extra)
                             mm[0:1].copy_(torch.minimum(mm[0:1], mm2[0:1]))
                             mm[1:2].copy_(torch.maximum(mm[1:2], mm2[1:2]))
-                    if dist is not None:
-                        mx = state["minmax"][:, 1].contiguous()
-                        mn = state["minmax"][:, 0].contiguous()
-                        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-                        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
-                        state["minmax"][:, 1].copy_(mx)
-                        state["minmax"][:, 0].copy_(mn)
+                    fqdist.sync_first_batch_minmax(state["minmax"], group)
                     for i, xs in first_batch.items():
                         for x in xs:
                             ops.hist_nonzero(x, state["minmax"][i, 1:2], bins, state["counts"][i])
@@ -122,8 +108,7 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
                             ops.hist_nonzero(pending[i], state["minmax"][i, 1:2], bins, state["counts"][i])
                     pending.clear()
                 if state:
-                    if dist is not None:
-                        dist.all_reduce(state["counts"], op=dist.ReduceOp.SUM, group=group)
+                    fqdist.sync_counts(state["counts"], group)
                     # hist_collector[m] = last_hist + hist.astype(float32), all blocks in one launch
                     state["seen_last"].zero_()
                     _accumulate(state, n_batches == 0, bins)

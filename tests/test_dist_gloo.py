@@ -1,0 +1,116 @@
+"""world_size-2 gloo tests of the data-parallel host logic (quantization.mxnet_b200.dist): sharding by
+sample plus the max / integer-sum / gather collectives must reproduce what the oracle computes on the
+whole batch.  The per-shard statistics are computed by the oracle here (no GPU in this container);
+on the GPU box test_gpu_dist.py runs the same logic with the CUDA kernels over NCCL."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import fq_oracle as O
+
+BINS = 2048
+WORLD = 2
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _batches():
+    r = np.random.RandomState(5)
+    # two layers, three batches of 8 samples; batch 1 exceeds batch 0's max (frozen max -> clipping)
+    return [[np.maximum(r.standard_normal((8, 4, 6, 6)) * (1 + 0.5 * b), 0).astype(np.float32),
+             np.maximum(r.standard_normal((8, 16)) * (2 + b), 0).astype(np.float32)] for b in range(3)]
+
+
+def _worker(rank, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    from quantization.mxnet_b200 import dist as fqdist
+    try:
+        batches = _batches()
+        n_layers = 2
+        hist = np.zeros((n_layers, BINS + 1), np.float32)
+        minmax = torch.zeros(n_layers, 2)
+        for b, layers in enumerate(batches):
+            shards = [fqdist.shard_batch(torch.from_numpy(x)).numpy() for x in layers]
+            assert all(s.shape[0] == 4 for s in shards)
+            if b == 0:
+                for l, s in enumerate(shards):
+                    minmax[l, 0], minmax[l, 1] = float(s.min()), float(s.max())
+                fqdist.sync_first_batch_minmax(minmax)
+            counts = torch.zeros(n_layers, BINS + 1, dtype=torch.int64)
+            for l, s in enumerate(shards):
+                c = O.histogram_counts(s, BINS, np.float32(minmax[l, 1].item()), "nep50")
+                counts[l, :len(c)] = torch.from_numpy(c)
+            fqdist.sync_counts(counts)
+            f = counts.numpy().astype(np.float32)
+            hist = f if b == 0 else hist + f
+
+            # online input range: all-gather of the per-sample maxima, canonical Kahan mean on every rank
+            per = torch.from_numpy(O.absmax_rows(shards[0], shards[0].shape[0]))
+            allmax = fqdist.gather_per_sample(per).numpy()
+            want_cur, want_per = O.input_range(layers[0])
+            assert np.array_equal(allmax, want_per)
+            assert O.mean_kahan_f32(allmax) == want_cur
+
+        for l in range(n_layers):
+            want_h, want_m = O.accumulate_histograms([b[l] for b in batches], BINS, "nep50")
+            assert np.float32(minmax[l, 1].item()) == want_m
+            assert np.array_equal(hist[l, :len(want_h)], want_h) and hist[l, len(want_h):].sum() == 0
+
+        # QAT gradient bucket: mean over ranks of per-rank gradients
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+        fqdist.broadcast_parameters(net)
+        w0 = [p.detach().clone() for p in net.parameters()]
+        x = torch.arange(8, dtype=torch.float32).reshape(2, 4) + rank
+        net(x).sum().backward()
+        local = [p.grad.clone() for p in net.parameters()]
+        bucket = fqdist.GradBucket(net.parameters())
+        bucket.all_reduce_mean()
+        gathered = [torch.zeros_like(torch.cat([g.reshape(-1) for g in local])) for _ in range(WORLD)]
+        dist.all_gather(gathered, torch.cat([g.reshape(-1) for g in local]))
+        want = (gathered[0] + gathered[1]) / WORLD
+        got = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+        assert torch.equal(got, want)
+        assert all(torch.equal(a, b.detach()) for a, b in zip(w0, net.parameters()))
+        out.put((rank, "ok"))
+    except Exception as e:          # surface the failure in the parent
+        import traceback
+        out.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_calibration_and_qat_collectives():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, port, out)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results
+
+
+def test_single_process_helpers_are_no_ops():
+    from quantization.mxnet_b200 import dist as fqdist
+    assert fqdist.active_group() is None
+    x = torch.arange(12.).reshape(6, 2)
+    assert torch.equal(fqdist.shard_batch(x), x)
+    assert torch.equal(fqdist.shard_batch(x, rank=1, world=3), x[2:4])
+    c = torch.ones(2, 5, dtype=torch.int64)
+    assert fqdist.sync_counts(c) is c
+    assert torch.equal(fqdist.gather_per_sample(x[:, 0]), x[:, 0])

@@ -311,3 +311,36 @@ def test_collect_qparams_and_state_dict(Q):
     sd = net.state_dict()
     assert sum(k.endswith("input_max") for k in sd) == 20
     assert not any("current_input_max" in k for k in sd)
+
+
+def test_qconv2d_integer_path_matches_oracle_and_tracks_float_conv(Q):
+    """tests/test_quantized_conv.py of the reference: int path vs float conv vs simulated conv."""
+    from quantization.mxnet_b200.nn import Conv2D as MyConv
+    torch.manual_seed(1)
+    for groups, use_bias in ((1, True), (2, True), (1, False)):
+        x = torch.rand(2, 2, 5, 5, device="cuda")
+        conv = MyConv(10, 3, 1, 1, in_channels=2, groups=groups, use_bias=use_bias, input_dtype='uint8',
+                      weight_dtype='int8', quantized=True).cuda()
+        if use_bias:
+            conv.bias.data.uniform_(-0.1, 0.1)
+        with torch.no_grad():
+            y = conv(x)
+        # oracle: same integer pipeline in NumPy + framework conv on the integer-valued floats
+        xp = torch.nn.functional.pad(x, (1, 1, 1, 1)).cpu().numpy()
+        xq, s_in = O.qconv_quantize_auto(xp, "uint8")
+        wq, s_w = O.qconv_quantize_auto(conv.weight.detach().cpu().numpy(), "int8")
+        acc = torch.nn.functional.conv2d(torch.from_numpy(xq.astype(np.float32)), torch.from_numpy(wq.astype(np.float32)),
+                                         None, 1, 0, 1, groups).to(torch.int32).numpy()
+        if use_bias:
+            bs = F32(s_in * s_w)
+            b = conv.bias.detach().cpu().numpy()
+            bq = O.roundf((O.clip(b, -bs * F32(2 ** 31), bs * F32(2 ** 31)) / bs).astype(F32)).astype(np.int32)
+            acc = acc + bq.reshape(1, -1, 1, 1)
+        want = O.qconv_dequantize(acc, F32(s_in * s_w))
+        assert np.array_equal(bits(y.cpu().numpy()), bits(want))
+        # and it approximates the float convolution (what the reference's script prints)
+        ref = torch.nn.functional.conv2d(x, conv.weight, conv.bias, 1, 1, 1, groups)
+        assert (y - ref).abs().max() < 0.02 * ref.abs().max()
+        conv._quantized = False
+        with torch.no_grad():
+            assert torch.allclose(conv(x), ref, atol=1e-6)

@@ -1,0 +1,120 @@
+"""N=2 NCCL run of the sharded calibration / online range on real GPUs: results must equal the
+single-GPU results on the whole batch bit for bit.  Needs two visible GPUs (gpurun --gpus 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+WORLD = 2
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _build(device):
+    from torch import nn
+    from quantization.mxnet_b200 import model_zoo as Z
+    from quantization.mxnet_b200.quantize import convert
+    from quantization.mxnet_b200.quantize.initialize import qparams_init
+    torch.manual_seed(7)
+    net = Z.get_model("cifar_resnet20_v1", classes=10).eval().to(device)
+    convert.convert_model(net, exclude=Z.default_exclusions(net, "cifar_resnet20_v1"))
+    qparams_init(net)
+    return net
+
+
+def _data():
+    g = torch.Generator().manual_seed(3)
+    return [torch.randn(16, 3, 32, 32, generator=g) * (1 + 0.3 * i) for i in range(3)]
+
+
+def _worker(rank, port, out):
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=WORLD, device_id=dev)
+        torch.backends.cudnn.allow_tf32 = False
+        from quantization.mxnet_b200 import dist as fqdist
+        from quantization.mxnet_b200.quantize.distribution_calibrate import collect_feature_maps, kl_calibrate_all
+        net = _build(dev)
+        batches = _data()
+        # --- KL calibration on shards
+        net.disable_quantize()
+        loader = [(fqdist.shard_batch(b), None) for b in batches]
+        hist, fmax = collect_feature_maps(net, 2048, loader, dev)
+        best = kl_calibrate_all(hist, 256, 256, 2048)
+        blocks = net.collect_quantized_blocks()
+        res = {"hist": np.stack([np.pad(hist[m], (0, 2049 - len(hist[m]))) for m in blocks]),
+               "max": np.array([fmax[m] for m in blocks]), "best": best.cpu().numpy()}
+        # --- online input quantisation with the global Kahan mean
+        net.enable_quantize()
+        net.quantize_input(True, online=True)
+        fqdist.enable_data_parallel(net)
+        with torch.no_grad():
+            logits = net(fqdist.shard_batch(batches[0]).to(dev))
+        res["cur"] = np.array([m.current_input_max.item() for m in blocks], np.float32)
+        res["logits"] = logits.cpu().numpy()
+        out.put((rank, res))
+        dist.destroy_process_group()
+    except Exception as e:
+        import traceback
+        out.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_calibration_equals_single_gpu():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, port, out)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    results = dict(out.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(isinstance(v, dict) for v in results.values()), results
+
+    # single-GPU reference on the whole batches
+    from quantization.mxnet_b200.quantize.distribution_calibrate import collect_feature_maps, kl_calibrate_all
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device("cuda", 0)
+    net = _build(dev)
+    batches = _data()
+    net.disable_quantize()
+    hist, fmax = collect_feature_maps(net, 2048, [(b, None) for b in batches], dev)
+    best = kl_calibrate_all(hist, 256, 256, 2048).cpu().numpy()
+    blocks = net.collect_quantized_blocks()
+    want_hist = np.stack([np.pad(hist[m], (0, 2049 - len(hist[m]))) for m in blocks])
+    net.enable_quantize()
+    net.quantize_input(True, online=True)
+    with torch.no_grad():
+        logits = net(batches[0].to(dev)).cpu().numpy()
+    cur = np.array([m.current_input_max.item() for m in blocks], np.float32)
+    for r in range(WORLD):
+        # the first converted block sees identical inputs on both paths: bit-exact everything
+        assert np.array_equal(results[r]["hist"][0], want_hist[0])
+        assert results[r]["max"][0] == np.float32(fmax[blocks[0]])
+        assert results[r]["cur"][0] == cur[0]
+        # deeper layers: cuDNN may pick a different algorithm for a batch of 8 than for 16, so inputs can
+        # differ by ulps; integer statistics must still agree to a handful of counts
+        assert np.abs(results[r]["hist"] - want_hist).sum() <= 1e-4 * want_hist.sum()
+        assert np.array_equal(results[r]["best"], best) or np.abs(results[r]["best"] - best).max() <= 2
+        assert np.allclose(results[r]["cur"], cur, rtol=1e-5)
+    # both ranks agree with each other exactly
+    assert np.array_equal(results[0]["hist"], results[1]["hist"])
+    assert np.array_equal(results[0]["best"], results[1]["best"])
+    assert np.array_equal(results[0]["cur"], results[1]["cur"])
+    got = np.concatenate([results[0]["logits"], results[1]["logits"]])
+    assert np.abs(got - logits).max() <= 2e-2 * np.abs(logits).max()
