@@ -1,0 +1,162 @@
+/*
+ * fq_oracle.c -- plain C (+OpenMP) restatement of the reference's CPU arithmetic.
+ * TEST INFRASTRUCTURE ONLY: the checker and the all-cores CPU baseline of bench.py.  Never linked
+ * into or called by the product (quantization/mxnet_b200).
+ *
+ * Each function follows the reference lines cited beside it (paths relative to the reference root)
+ * and mirrors oracle/fq_oracle.py, against which tests/test_oracle_c.py checks it bit for bit.
+ * Parity status: histogram / KL are pinned through the NumPy oracle to the reference's own outputs
+ * (tests/golden); the MXNet-op restatements are PARITY UNPINNED (see oracle/fq_oracle.py).
+ * Build: gcc -O2 -fopenmp -ffp-contract=off -shared -fPIC  (no -ffast-math: IEEE semantics matter).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define API __attribute__((visibility("default")))
+
+/* mshadow_op::round == roundf; mshadow_op::clip: compare/select */
+static inline float clipf(float x, float lo, float hi) { return x > hi ? hi : (x < lo ? lo : x); }
+
+/* max |x| per row: convert_conv2d.py:56,75,86,92 */
+API void fqo_absmax_rows(const float* x, int64_t rows, int64_t len, float* out) {
+#pragma omp parallel for schedule(static)
+  for (int64_t r = 0; r < rows; ++r) {
+    float m = 0.f;
+    const float* p = x + r * len;
+    for (int64_t i = 0; i < len; ++i) {
+      const float a = fabsf(p[i]);
+      if (a > m) m = a;
+    }
+    out[r] = m;
+  }
+}
+
+/* MXNet CPU mean: Kahan fp32 sum in index order, one fp32 divide (convert_conv2d.py:56 `.mean()`) */
+API float fqo_mean_kahan(const float* v, int64_t n) {
+  volatile float s = 0.f, c = 0.f;
+  for (int64_t i = 0; i < n; ++i) {
+    volatile float y = v[i] - c;
+    volatile float t = s + y;
+    c = (t - s) - y;
+    s = t;
+  }
+  return s / (float)n;
+}
+
+/* ste_func.py:41 / :39 with scalar d, s */
+API void fqo_fake_quant_scalar(const float* x, int64_t n, float d, float s, float lo, float hi, int use_clip,
+                               float* y, float* code) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    float v = x[i];
+    if (use_clip) v = clipf(v, lo, hi);
+    const float c = roundf(v / d);
+    if (code) code[i] = c;
+    y[i] = c * s;
+  }
+}
+
+/* ste_func.py:39 with a per-row scale tensor (weights): d_r = s_r + 1e-10f */
+API void fqo_fake_quant_rows(const float* x, int64_t rows, int64_t len, const float* scale, float* y, float* code) {
+#pragma omp parallel for schedule(static)
+  for (int64_t r = 0; r < rows; ++r) {
+    const float s = scale[r];
+    volatile float d = s + 1e-10f;
+    for (int64_t i = r * len; i < (r + 1) * len; ++i) {
+      const float c = roundf(x[i] / d);
+      if (code) code[i] = c;
+      y[i] = c * s;
+    }
+  }
+}
+
+/* distribution_calibrate.py:39-45: counts of the clipped non-zero values, `sc` already rounded to fp32 */
+API void fqo_hist_counts(const float* x, int64_t n, float max_, float sc, int bins, int64_t* counts) {
+  memset(counts, 0, sizeof(int64_t) * (size_t)(bins + 1));
+#pragma omp parallel
+  {
+    int64_t* local = (int64_t*)calloc((size_t)bins + 1, sizeof(int64_t));
+#pragma omp for schedule(static) nowait
+    for (int64_t i = 0; i < n; ++i) {
+      float v = x[i];
+      v = v < 0.f ? 0.f : v;          /* ndarray.clip(0, max_) */
+      v = v > max_ ? max_ : v;
+      if (v != 0.f) {
+        const int b = (int)(v * sc);
+        if (b >= 0 && b <= bins) local[b]++;
+      }
+    }
+#pragma omp critical
+    for (int b = 0; b <= bins; ++b) counts[b] += local[b];
+    free(local);
+  }
+}
+
+/* distribution_calibrate.py:138-166 for one candidate i; nep50 != 0: float32 sums, else float64 */
+static double kl_one(const float* data, int n_data, int levels, int i, int nep50, double* cand, double* q, float* ref) {
+  float last, total;
+  if (nep50) {
+    volatile float tail = 0.f, tot = 0.f;
+    for (int j = i; j < n_data; ++j) tail = tail + data[j];
+    last = data[i - 1] + tail;
+    for (int j = 0; j < i - 1; ++j) tot = tot + data[j];
+    tot = tot + last;
+    total = tot;
+  } else {
+    double tail = 0.0, tot = 0.0;
+    for (int j = i; j < n_data; ++j) tail += (double)data[j];
+    last = (float)((double)data[i - 1] + tail);
+    for (int j = 0; j < i - 1; ++j) tot += (double)data[j];
+    tot += (double)last;
+    total = (float)tot;
+  }
+  for (int k = 0; k < levels; ++k) cand[k] = 0.0;
+  for (int j = 0; j < i; ++j) cand[(int)(((double)((int64_t)j * levels)) / (double)i)] += (double)data[j];
+  double qsum = 0.0;
+  for (int j = 0; j < i; ++j) {
+    const float p = (j == i - 1 ? last : data[j]) / total;
+    ref[j] = p;
+    const double t = ((double)((int64_t)j * levels)) / (double)i;
+    const int fl = (int)t;
+    int ce = (int)ceil(t);
+    if (ce > levels - 1) ce = levels - 1;
+    double v = (cand[ce] - cand[fl]) * (t - (double)fl) + cand[fl];
+    v = v * ((p != 0.f) ? 1.0 : 0.0);
+    q[j] = v;
+    qsum += v;
+  }
+  double div = 0.0;
+  for (int j = 0; j < i; ++j) {
+    const double qn = q[j] / qsum;
+    if (qn != 0.0) {
+      const double p = (double)ref[j];
+      div += p * log(p / qn);
+    }
+  }
+  return div;
+}
+
+/* distribution_calibrate.py:117-171: divergences for i in [min_bins, bins) and the first strict arg-min */
+API int fqo_kl_calibrate(const float* data, int n_data, int levels, int min_bins, int bins, int nep50, double* div_out) {
+#pragma omp parallel
+  {
+    double* cand = (double*)malloc(sizeof(double) * (size_t)levels);
+    double* q = (double*)malloc(sizeof(double) * (size_t)bins);
+    float* ref = (float*)malloc(sizeof(float) * (size_t)bins);
+#pragma omp for schedule(dynamic, 8)
+    for (int i = min_bins; i < bins; ++i) div_out[i] = kl_one(data, n_data, levels, i, nep50, cand, q, ref);
+    free(cand);
+    free(q);
+    free(ref);
+  }
+  int best = min_bins;
+  double best_div = INFINITY;
+  for (int i = min_bins; i < bins; ++i)
+    if (div_out[i] < best_div) {
+      best_div = div_out[i];
+      best = i;
+    }
+  return best;
+}
