@@ -278,8 +278,9 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False          # the framework convolutions stay plain fp32
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
     K, W = args.steps, max(args.warmup, 1)
 
     net = build_net(dev)

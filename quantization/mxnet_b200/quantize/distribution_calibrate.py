@@ -79,9 +79,7 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
     """ Collect feature maps """
     try:
         with tqdm(total=len(loader), desc=tqdm_desc, disable=None) as pbar, torch.no_grad():
-            for X, _ in loader:
-                if ctx is not None:
-                    X = X.to(ctx, non_blocking=True)
+            for X in _prefetch(loader, ctx):
                 _ = net(X)
                 if n_batches == 0:
                     # First chunk: min/max of everything the block saw, then its histogram
@@ -144,6 +142,39 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
     fm_max_collector.device = state["minmax"][:, 1].contiguous()
     fm_max_collector.order = tuple(quantized_blocks)
     return hist_collector, fm_max_collector
+
+
+def _prefetch(loader, ctx):
+    """Yield each batch on ``ctx``, copying batch k+1 host->device on a side stream while the network runs
+    on batch k (pinned host memory makes the copy asynchronous)."""
+    if ctx is None or torch.device(ctx).type != "cuda":
+        for X, _ in loader:
+            yield X if ctx is None else X.to(ctx)
+        return
+    dev = torch.device(ctx)
+    copy_stream = torch.cuda.Stream(device=dev)
+    it = iter(loader)
+
+    def fetch():
+        try:
+            X, _ = next(it)
+        except StopIteration:
+            return None
+        if X.device == dev:
+            return X, None
+        with torch.cuda.stream(copy_stream):
+            Xd = X.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return Xd, ev
+    nxt = fetch()
+    while nxt is not None:
+        Xd, ev = nxt
+        if ev is not None:
+            torch.cuda.current_stream(dev).wait_event(ev)
+            Xd.record_stream(torch.cuda.current_stream(dev))
+        nxt = fetch()           # start the next copy before this batch's forward is queued
+        yield Xd
 
 
 def _accumulate(state, first, bins):
