@@ -88,7 +88,8 @@ FQ_API int fq_sm_count(int* out);
 FQ_API int fq_absmax_rows(const DLTensor* x, int64_t rows, const DLTensor* out, void* ws, void* stream);
 /* out2 = {min x, max x}.  nn/quantized_conv.py:68-69; distribution_calibrate.py:34-35. */
 FQ_API int fq_minmax(const DLTensor* x, const DLTensor* out2, void* ws, void* stream);
-/* out[0] = MXNet CPU mean: sequential Kahan fp32 sum / fp32(n).  convert_conv2d.py:56 `.mean()`. */
+/* out[0] = MXNet CPU mean: sequential Kahan fp32 sum / fp32(n).  convert_conv2d.py:56 `.mean()`.
+ * v may also be [rows, n] with out [rows]: one mean per row in a single launch. */
 FQ_API int fq_mean_kahan(const DLTensor* v, const DLTensor* out, void* stream);
 /* cur_max[0] = mean_n max_chw |x| in ONE launch; per_sample (NULL or [n_samples]) receives the maxima.
  * convert_conv2d.py:56; convert_dense.py:41. */

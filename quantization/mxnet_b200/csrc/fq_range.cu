@@ -95,8 +95,10 @@ __global__ void __launch_bounds__(kThreads) rows_absmax_kernel(const float* __re
   if (threadIdx.x == 0) ws->ticket = 0;
 }
 
-__global__ void mean_kahan_kernel(const float* __restrict__ v, int64_t n, float* __restrict__ out) {
+// one block per row of v[rows, n]: out[row] = Kahan mean of the row
+__global__ void mean_kahan_kernel(const float* __restrict__ v_all, int64_t n, float* __restrict__ out) {
   __shared__ float stage[1024];
+  const float* v = v_all + (int64_t)blockIdx.x * n;
   float s = 0.f, c = 0.f;
   for (int64_t base = 0; base < n; base += 1024) {
     const int m = (int)min((int64_t)1024, n - base);
@@ -106,7 +108,7 @@ __global__ void mean_kahan_kernel(const float* __restrict__ v, int64_t n, float*
       for (int i = 0; i < m; ++i) kahan_add(s, c, stage[i]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[0] = __fdiv_rn(s, (float)n);
+  if (threadIdx.x == 0) out[blockIdx.x] = __fdiv_rn(s, (float)n);
 }
 
 __global__ void scale_from_max_kernel(const float* __restrict__ max_, int bits, int is_signed, int lo_mode,
@@ -173,7 +175,11 @@ int fq_mean_kahan(const DLTensor* v_, const DLTensor* out_, void* stream) {
   FQ_TRY(view_of(out_, "fq_mean_kahan: out", false, &out));
   FQ_REQUIRE(v.is_f32() && out.is_f32(), "fq_mean_kahan: float32 only");
   FQ_REQUIRE(v.numel > 0 && out.numel >= 1, "fq_mean_kahan: empty input or output");
-  mean_kahan_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(v.as<const float>(), v.numel, out.as<float>());
+  // v: [n] -> out[0], or [rows, n] -> out[rows] (every layer's per-sample maxima in one launch)
+  const int64_t rows = (v_->ndim >= 2) ? v.numel / v_->shape[v_->ndim - 1] : 1;
+  FQ_REQUIRE(out.numel >= rows && rows <= 65535, "fq_mean_kahan: out needs one element per row (%lld rows)", (long long)rows);
+  mean_kahan_kernel<<<(unsigned)rows, kThreads, 0, (cudaStream_t)stream>>>(v.as<const float>(), v.numel / rows,
+                                                                          out.as<float>());
   FQ_LAUNCH_CHECK("mean_kahan_kernel");
   return 0;
 }

@@ -61,7 +61,8 @@ def minmax(x, out=None):
 def mean_kahan(v, out=None):
     """MXNet CPU ``mean`` of a vector."""
     v = _f32(v)
-    out = torch.empty(1, dtype=torch.float32, device=v.device) if out is None else out
+    rows = 1 if v.dim() < 2 else v.numel() // v.shape[-1]
+    out = torch.empty(rows, dtype=torch.float32, device=v.device) if out is None else out
     a, o = dl(v), dl(out)
     check_call(_lib().fq_mean_kahan(a.ptr, o.ptr, current_stream()))
     return out

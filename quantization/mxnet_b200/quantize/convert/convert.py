@@ -5,7 +5,7 @@ import torch
 from torch import nn
 
 from ... import ops
-from .convert_conv2d import gen_conv2d_converter
+from .convert_conv2d import gen_conv2d_converter, sync_pending_ranges
 from .convert_dense import gen_dense_converter
 from .convert_act import gen_act_converter, convert_relu_to_relu6
 from .convert_bn import bypass_bn
@@ -69,6 +69,7 @@ def convert_model(net, exclude=[], convert_fn=default_convert_fn, custom_fn={}):
     # Add method to update ema for `input_max` in convs (convert.py:66-78)
     def _update_ema(self, momentum=0.9):
         blocks = self.collect_quantized_blocks()
+        sync_pending_ranges(blocks)     # data parallel only: shard-local ranges -> global-batch ranges
         # if quantize input: every layer's scalar EMA in ONE launch
         state, cur, _ = _pack_states(blocks, "input_max", "current_input_max")
         if state is not None:

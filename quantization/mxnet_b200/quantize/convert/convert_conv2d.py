@@ -22,17 +22,22 @@ QuantizedArgs = namedtuple("ConvQuantizedArgs",
                            "fake_bn wino_quantize")
 
 
-def _track_range(x, m):
-    """current_input_max of this block (convert_conv2d.py:56).  With data parallelism the shard's
-    per-sample maxima are all-gathered and the Kahan mean is taken over the global batch on every rank."""
-    group = getattr(m, "_fq_dist_group", None)
-    if group is None:
-        return False
+def _per_sample_buffer(m, n):
+    buf = getattr(m, "_fq_per_sample", None)
+    if buf is None or buf.numel() != n or buf.device != m.current_input_max.device:
+        buf = torch.empty(n, dtype=torch.float32, device=m.current_input_max.device)
+        m._fq_per_sample = buf
+    return buf
+
+
+def _global_range(x, m, group):
+    """Data parallel, range needed NOW (online quantisation): the shard's per-sample maxima are
+    all-gathered and the Kahan mean is taken over the global batch on every rank."""
     from ... import dist as fqdist
-    per = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    per = _per_sample_buffer(m, x.shape[0])
     ops.input_range(x, cur_max=m.current_input_max, per_sample=per)
     ops.mean_kahan(fqdist.gather_per_sample(per, group), out=m.current_input_max)
-    return True
+    m._fq_range_pending = False
 
 
 class _InputPath(torch.autograd.Function):
@@ -41,14 +46,19 @@ class _InputPath(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, m, lo_mode):
         qa = m.quantize_args
-        if _track_range(x, m):      # data parallel: range over the global batch, then the plain quantiser
-            max_ = m.input_max.data if m.quantize_input_offline else m.current_input_max
-            ops.scale_from_max(max_, qa.in_width, qa.in_signed, lo_mode, qparams=m._fq_qparams)
+        group = getattr(m, "_fq_dist_group", None)
+        if group is not None and not m.quantize_input_offline:
+            _global_range(x, m, group)      # data parallel + online: range over the global batch first
+            ops.scale_from_max(m.current_input_max, qa.in_width, qa.in_signed, lo_mode, qparams=m._fq_qparams)
             return ops.forward_scalar(x, m._fq_qparams)
+        # single process, or offline range: one fused launch.  Under data parallelism the per-sample maxima
+        # are kept and the global mean is taken for ALL layers by one collective in update_ema().
+        per = _per_sample_buffer(m, x.shape[0]) if group is not None else None
         y, _, _ = ops.forward_online(
             x, qa.in_width, qa.in_signed, lo_mode,
             input_max=m.input_max.data if m.quantize_input_offline else None,
-            quantize=True, cur_max=m.current_input_max, qparams=m._fq_qparams)
+            quantize=True, cur_max=m.current_input_max, qparams=m._fq_qparams, per_sample=per)
+        m._fq_range_pending = group is not None
         return y
 
     @staticmethod
@@ -58,9 +68,29 @@ class _InputPath(torch.autograd.Function):
 
 def _range_only(x, m):
     """quantize_input switched off: the range is still tracked (convert_conv2d.py:55-57)."""
-    if not _track_range(x, m):
-        ops.forward_online(x, m.quantize_args.in_width, m.quantize_args.in_signed, ops.LO_ZERO, quantize=False,
-                           cur_max=m.current_input_max)
+    group = getattr(m, "_fq_dist_group", None)
+    per = _per_sample_buffer(m, x.shape[0]) if group is not None else None
+    ops.forward_online(x, m.quantize_args.in_width, m.quantize_args.in_signed, ops.LO_ZERO, quantize=False,
+                       cur_max=m.current_input_max, per_sample=per)
+    m._fq_range_pending = group is not None
+
+
+def sync_pending_ranges(blocks):
+    """Data parallel: replace every block's shard-local current_input_max by the mean over the GLOBAL batch,
+    with ONE all-gather of all layers' per-sample maxima and one batched Kahan-mean launch."""
+    from ... import dist as fqdist
+    todo = [m for m in blocks if getattr(m, "_fq_range_pending", False)]
+    if not todo:
+        return
+    group = todo[0]._fq_dist_group
+    local = torch.stack([m._fq_per_sample for m in todo])                 # [L, N/R]
+    world = torch.distributed.get_world_size(group)
+    allmax = fqdist.gather_per_sample(local.reshape(-1), group)           # [R, L, N/R]
+    allmax = allmax.reshape(world, len(todo), -1).permute(1, 0, 2).reshape(len(todo), -1).contiguous()   # [L, N]
+    means = ops.mean_kahan(allmax)
+    for i, m in enumerate(todo):
+        m.current_input_max.copy_(means[i:i + 1])
+        m._fq_range_pending = False
 
 
 class _WeightPath(torch.autograd.Function):

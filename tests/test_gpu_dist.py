@@ -66,6 +66,14 @@ def _worker(rank, port, out):
             logits = net(fqdist.shard_batch(batches[0]).to(dev))
         res["cur"] = np.array([m.current_input_max.item() for m in blocks], np.float32)
         res["logits"] = logits.cpu().numpy()
+        # --- offline inputs with range tracking: no collective in the forward, one all-gather in update_ema
+        net.quantize_input(True, online=False)
+        for m in blocks:
+            m.input_max.data.fill_(1.5)
+        with torch.no_grad():
+            net(fqdist.shard_batch(batches[1]).to(dev))
+        net.update_ema()
+        res["ema"] = np.array([m.input_max.item() for m in blocks], np.float32)
         out.put((rank, res))
         dist.destroy_process_group()
     except Exception as e:
@@ -102,7 +110,16 @@ def test_two_gpu_sharded_calibration_equals_single_gpu():
     with torch.no_grad():
         logits = net(batches[0].to(dev)).cpu().numpy()
     cur = np.array([m.current_input_max.item() for m in blocks], np.float32)
+    net.quantize_input(True, online=False)
+    for m in blocks:
+        m.input_max.data.fill_(1.5)
+    with torch.no_grad():
+        net(batches[1].to(dev))
+    net.update_ema()
+    ema = np.array([m.input_max.item() for m in blocks], np.float32)
     for r in range(WORLD):
+        assert results[r]["ema"][0] == ema[0]
+        assert np.allclose(results[r]["ema"], ema, rtol=1e-5)
         # the first converted block sees identical inputs on both paths: bit-exact everything
         assert np.array_equal(results[r]["hist"][0], want_hist[0])
         assert results[r]["max"][0] == np.float32(fmax[blocks[0]])
@@ -116,5 +133,6 @@ def test_two_gpu_sharded_calibration_equals_single_gpu():
     assert np.array_equal(results[0]["hist"], results[1]["hist"])
     assert np.array_equal(results[0]["best"], results[1]["best"])
     assert np.array_equal(results[0]["cur"], results[1]["cur"])
+    assert np.array_equal(results[0]["ema"], results[1]["ema"])
     got = np.concatenate([results[0]["logits"], results[1]["logits"]])
     assert np.abs(got - logits).max() <= 2e-2 * np.abs(logits).max()
