@@ -166,6 +166,8 @@ def main():
         params = [p for p in net.parameters() if p.requires_grad]
         opt = torch.optim.Adam(params, lr=1e-6, capturable=args.graph)
         bucket = fqdist.GradBucket(params)
+        if world > 1:
+            bucket.attach()
         loss_fn = nn.CrossEntropyLoss()
 
         def step():

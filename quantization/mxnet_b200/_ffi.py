@@ -132,6 +132,9 @@ _PyCapsule_GetPointer.restype = _c.c_void_p
 _PyCapsule_GetPointer.argtypes = [_c.py_object, _c.c_char_p]
 
 
+_small_cache = {}      # (data_ptr, shape, dtype, device index) -> _Arg of tiny persistent tensors (qparams, ranges)
+
+
 def dl(x):
     """Borrow ``x`` as a DLTensor*.  ``None`` -> NULL."""
     if x is None:
@@ -141,6 +144,12 @@ def dl(x):
             raise FQError("tensor is on %s: quantization.mxnet_b200 has no CPU path" % x.device)
         if not x.is_contiguous():
             raise FQError("tensor must be contiguous (call .contiguous() first)")
+        small = x.numel() <= 8
+        if small:
+            key = (x.data_ptr(), tuple(x.shape), x.dtype, x.device.index)
+            hit = _small_cache.get(key)
+            if hit is not None:
+                return hit
         try:
             code, bits = _DTYPES[x.dtype]
         except KeyError:
@@ -149,6 +158,13 @@ def dl(x):
         shape = (_c.c_int64 * max(nd, 1))(*x.shape)
         t = DLTensor(x.data_ptr(), DLDevice(kDLCUDA, x.device.index or 0), nd, DLDataType(code, bits, 1),
                      shape, None, 0)
+        if small:
+            # the struct only describes memory; the caller's tensor keeps that memory alive during the call
+            arg = _Arg(t, (shape,))
+            if len(_small_cache) > 4096:
+                _small_cache.clear()
+            _small_cache[key] = arg
+            return arg
         return _Arg(t, (x, shape))
     if hasattr(x, "__dlpack__") or hasattr(x, "to_dlpack_for_read"):
         cap = x.to_dlpack_for_read() if hasattr(x, "to_dlpack_for_read") else x.__dlpack__()
@@ -162,8 +178,11 @@ def ptr(a):
     return None if a is None else a.ptr
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream
+
+
 def current_stream():
-    return _c.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return _c.c_void_p(_raw_stream(torch.cuda.current_device()))
 
 
 _workspaces = {}
@@ -171,15 +190,14 @@ _workspaces = {}
 
 def workspace(device=None):
     """Zero-initialised scratch for the fused kernels: one per (device, stream)."""
-    lib = load()
-    dev = torch.cuda.current_device() if device is None else torch.device(device).index
-    stream = torch.cuda.current_stream(dev)
-    key = (dev, stream.cuda_stream)
-    ws = _workspaces.get(key)
+    dev = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    raw = _raw_stream(dev)
+    ws = _workspaces.get((dev, raw))
     if ws is None:
+        lib = load()
         nbytes = lib.fq_workspace_bytes()
         with torch.cuda.device(dev):
             ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-            check_call(lib.fq_workspace_init(_c.c_void_p(ws.data_ptr()), nbytes, _c.c_void_p(stream.cuda_stream)))
-        _workspaces[key] = ws
-    return _c.c_void_p(ws.data_ptr())
+            check_call(lib.fq_workspace_init(_c.c_void_p(ws.data_ptr()), nbytes, _c.c_void_p(raw)))
+        _workspaces[(dev, raw)] = ws = (ws, _c.c_void_p(ws.data_ptr()))
+    return ws[1]

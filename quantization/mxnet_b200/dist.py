@@ -83,7 +83,9 @@ def broadcast_parameters(net, src=0, group=None):
 
 
 class GradBucket:
-    """All gradients of a net in ONE flat fp32 buffer: a single all-reduce per QAT step."""
+    """All gradients of a net live in ONE flat fp32 buffer (each ``p.grad`` is a view into it, the way DDP's
+    gradient_as_bucket_view works), so a QAT step needs a single all-reduce and no packing copies.
+    Use ``optimizer.zero_grad(set_to_none=False)`` so that the views survive."""
 
     def __init__(self, params, group=None):
         self.params = [p for p in params if p.requires_grad]
@@ -91,31 +93,33 @@ class GradBucket:
         self.numel = sum(p.numel() for p in self.params)
         self.flat = None
 
+    def attach(self):
+        dev = self.params[0].device
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            view = self.flat[off:off + n].view(p.shape)
+            if p.grad is not None:
+                view.copy_(p.grad)
+            p.grad = view
+            off += n
+        return self
+
+    def _attached(self):
+        if self.flat is None or not self.params:
+            return False
+        p = self.params[0]
+        return p.grad is not None and p.grad.data_ptr() == self.flat.data_ptr()
+
     def all_reduce_mean(self):
         g = active_group(self.group)
         if g is None or not self.params:
             return
-        dev = self.params[0].device
-        if self.flat is None or self.flat.device != dev:
-            self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                self.flat[off:off + n].zero_()
-            else:
-                self.flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
+        if not self._attached():
+            self.attach()
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=g)
         self.flat.div_(dist.get_world_size(g))
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                p.grad = self.flat[off:off + n].reshape(p.shape).clone()
-            else:
-                p.grad.copy_(self.flat[off:off + n].reshape(p.shape))
-            off += n
 
 
 def enable_data_parallel(net, group=None):

@@ -40,6 +40,20 @@ def _global_range(x, m, group):
     m._fq_range_pending = False
 
 
+def _input_path(x, m, lo_mode):
+    """convert_conv2d.py:56-66.  Called directly when no gradient is needed, through _InputPath otherwise."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _InputPath.apply(x, m, lo_mode)
+    return _InputPath.forward(None, x, m, lo_mode)
+
+
+def _weight_path(weight, bias, gamma, beta, mean, var, rows, bits):
+    if torch.is_grad_enabled() and (weight.requires_grad or (gamma is not None and gamma.requires_grad)):
+        return _WeightPath.apply(weight, bias, gamma, beta, mean, var, rows, bits)
+    wq, bq, _ = ops.quant_weight(weight, rows, bits, gamma, beta, mean, var, bias)
+    return wq, (bq if gamma is not None else bias)
+
+
 class _InputPath(torch.autograd.Function):
     """convert_conv2d.py:56-66 in one launch; backward = identity (ste_func.py:43-44)."""
 
@@ -150,23 +164,22 @@ def _conv2d_forward(self, x):
         if qa.quantize_input:
             if self.quantize_input:
                 lo_mode = ops.LO_NEG_MAX if qa.in_signed else ops.LO_ZERO
-                x = _InputPath.apply(x, self, lo_mode)
+                x = _input_path(x, self, lo_mode)
             else:       # the range is still tracked (convert_conv2d.py:56)
                 _range_only(x.detach(), self)
         # Simulate quantization for weight (:69-97)
         if self.fixed_params != 1:
             if fold:
-                weight_q, bias = _WeightPath.apply(weight, bias, self.gamma, self.beta, self.running_mean,
-                                                   self.running_var, _weight_rows(self), qa.wt_width)
+                weight_q, bias = _weight_path(weight, bias, self.gamma, self.beta, self.running_mean,
+                                              self.running_var, _weight_rows(self), qa.wt_width)
             else:
-                weight_q, bias = _WeightPath.apply(weight, bias, None, None, None, None, _weight_rows(self),
-                                                   qa.wt_width)
+                weight_q, bias = _weight_path(weight, bias, None, None, None, None, _weight_rows(self), qa.wt_width)
         else:
             weight_q = weight
     else:
         if fold:       # fold only (:47-51 runs even when quantisation is disabled)
-            weight_q, bias = _WeightPath.apply(weight, bias, self.gamma, self.beta, self.running_mean,
-                                               self.running_var, 1, 0)
+            weight_q, bias = _weight_path(weight, bias, self.gamma, self.beta, self.running_mean,
+                                          self.running_var, 1, 0)
         else:
             weight_q = weight
 

@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from ... import ops
-from .convert_conv2d import _InputPath, _WeightPath, _range_only
+from .convert_conv2d import _input_path, _weight_path, _range_only
 
 __all__ = ['gen_dense_converter']
 
@@ -25,11 +25,11 @@ def _dense_forward(self, x):
             if x.dim() != 2:
                 raise NotImplementedError("quantised Dense expects a flattened (N, in_units) input")
             if self.quantize_input:
-                x = _InputPath.apply(x, self, ops.LO_ZERO)
+                x = _input_path(x, self, ops.LO_ZERO)
             else:
                 _range_only(x.detach(), self)
         rows = self.out_features if qa.quant_type == 'channel' else 1
-        weight_q, _ = _WeightPath.apply(weight, None, None, None, None, None, rows, qa.wt_width)
+        weight_q, _ = _weight_path(weight, None, None, None, None, None, rows, qa.wt_width)
     else:
         weight_q = weight
     return self.origin_forward(x, weight_q, bias)
