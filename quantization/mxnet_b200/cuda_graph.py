@@ -1,0 +1,43 @@
+"""CUDA-graph replay of a converted network's forward.
+
+The small-tensor configurations (CIFAR ResNet-20, MobileNetV2 at 32x32) are launch-bound: a forward is
+~100 kernels of a few microseconds each, and eager execution spends more time in Python than on the GPU.
+Every libfq_b200 entry point is capture-safe (no allocation, no host synchronisation, explicit stream,
+cooperative launches included), so the whole forward -- framework convolutions and fake-quant kernels
+alike -- can be recorded once and replayed with no host work in between.  The per-block state the
+reference exposes (``current_input_max``, ``input_max``) is updated by the replayed kernels in place.
+"""
+import torch
+
+__all__ = ["GraphedForward"]
+
+
+class GraphedForward:
+    """``g = GraphedForward(net, example_input); y = g(x)``.
+
+    ``x`` is copied into a static buffer, the captured graph is replayed and the static output is returned
+    (clone it if it must outlive the next call).  Capture happens after ``warmup`` eager iterations on a
+    side stream, so one-shot state changes (``fix_params()`` caching the quantised weights) have settled.
+    """
+
+    def __init__(self, net, example_input, warmup=3):
+        self.net = net
+        self.static_in = example_input.detach().clone()
+        self.stream = torch.cuda.Stream(device=example_input.device)
+        self.stream.wait_stream(torch.cuda.current_stream(example_input.device))
+        with torch.cuda.stream(self.stream), torch.no_grad():
+            for _ in range(max(1, warmup)):
+                net(self.static_in)
+        torch.cuda.current_stream(example_input.device).wait_stream(self.stream)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream), torch.no_grad():
+            self.static_out = net(self.static_in)
+
+    def __call__(self, x):
+        self.static_in.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+    def replay(self):
+        self.graph.replay()
+        return self.static_out

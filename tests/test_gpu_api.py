@@ -344,3 +344,43 @@ def test_qconv2d_integer_path_matches_oracle_and_tracks_float_conv(Q):
         conv._quantized = False
         with torch.no_grad():
             assert torch.allclose(conv(x), ref, atol=1e-6)
+
+
+def test_cuda_graph_replay_equals_eager_and_updates_state(Q):
+    from quantization.mxnet_b200.cuda_graph import GraphedForward
+    net, _ = build(Q, "cifar_resnet20_v1", 10)
+    net.fix_params()
+    net.quantize_input(enable=True, online=True)
+    g = torch.Generator().manual_seed(5)
+    x1 = torch.randn(32, 3, 32, 32, generator=g).cuda()
+    x2 = (torch.randn(32, 3, 32, 32, generator=g) * 2).cuda()
+    graphed = GraphedForward(net, x1)
+    blocks = net.collect_quantized_blocks()
+    for x in (x1, x2, x1):
+        got = graphed(x).clone()
+        cur_g = torch.cat([b.current_input_max for b in blocks]).clone()
+        with torch.no_grad():
+            want = net(x)
+        cur_e = torch.cat([b.current_input_max for b in blocks])
+        assert torch.equal(got, want)
+        assert torch.equal(cur_g, cur_e)                   # the replay keeps the per-block ranges current
+    net.update_ema()
+    assert all(float(b.input_max) > 0 for b in blocks)
+
+
+def test_activation_converter_and_relu6(Q):
+    """convert_act.py: ReLU -> ReLU6 and the optional activation-output quantiser (no epsilon, no STE)."""
+    relu = nn.ReLU()
+    Q.convert.convert_relu_to_relu6(relu)
+    x = torch.randn(4, 3, 5, 5, device="cuda") * 5
+    assert torch.equal(relu(x), torch.clamp(x, 0, 6))
+    act = nn.ReLU().cuda()
+    Q.convert.gen_act_converter(width=4)(act)
+    act = act.cuda()
+    y = act(x)
+    a = torch.relu(x).cpu().numpy()
+    cur = O.mean_kahan_f32(a.reshape(4, -1).max(axis=1))
+    assert F32(act.current_act_max.item()) == cur
+    scale = F32(np.float64(cur) / 15)                      # legacy promotion: numpy.float32 / int -> float64
+    want = (O.roundf((O.clip(a, 0, cur) / scale).astype(F32)) * scale).astype(F32)
+    assert np.array_equal(bits(y.cpu().numpy()), bits(want))

@@ -457,3 +457,29 @@ def test_full_size_properties(ops):
     c1 = counts.clone()
     ops.hist_nonzero(x, mx, R.BINS, counts)
     assert torch.equal(counts, 2 * c1)
+
+
+def test_beyond_2_31_elements_uses_64_bit_indexing(ops):
+    """BASELINE config 5 reaches 2^32 fp32 elements; anything indexed with 32 bits breaks past 2^31."""
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs ~20 GB of device memory")
+    n = (1 << 31) + 3 * 4096 + 8
+    x = torch.empty(n, device="cuda")
+    x.uniform_(0, 1)
+    x[-1] = 7.5                        # the maximum sits at the very last element
+    x[(1 << 31) + 5] = 0.0
+    assert float(ops.absmax_rows(x, 1)) == 7.5
+    mm = ops.minmax(x)
+    assert float(mm[1]) == 7.5 and float(mm[0]) == 0.0
+    qp = ops.scale_from_max(mm[1:2].clone(), 8, False, ops.LO_ZERO)
+    y = ops.forward_scalar(x, qp)
+    assert float(y[-1]) == float(qp[1]) * 255 and float(y[(1 << 31) + 5]) == 0.0
+    tail = slice(n - 100_000, n)
+    want, _ = O.fake_quant_scalar(host(x[tail]), *[F32(v) for v in host(qp)])
+    bits_equal(host(y[tail]), want)
+    counts = torch.zeros(R.BINS + 1, dtype=torch.int64, device="cuda")
+    ops.hist_nonzero(x, mm[1:2].clone(), R.BINS, counts)
+    del y
+    nz = sum(int((x[i:i + (1 << 28)] != 0).sum()) for i in range(0, n, 1 << 28))
+    assert int(counts.sum()) == nz
+    assert int(counts[R.BINS - 1] + counts[R.BINS]) >= 1          # the 7.5 landed in the top bin
