@@ -140,6 +140,12 @@ FQ_API int fq_ste_backward(const DLTensor* dy, const DLTensor* x, const DLTensor
 FQ_API int fq_ema_update(const DLTensor* state, const DLTensor* cur, double momentum, int scalar_cur,
                   int promotion, void* stream);
 
+/* Per-channel batch statistics of a conv output y [N, C, H, W] for the fake-BN EMA:
+ * mean[c] = sum_{n,h,w} y / (N*H*W);  var[c] = sum (y - mean[c])^2 / (N*H*W)  (two passes, as written in
+ * convert_conv2d.py:148-153).  fp32 sums in a fixed (deterministic) tree order: equal to the reference's
+ * sequential sums to a few ULP, not bit for bit.  C <= 32768. */
+FQ_API int fq_channel_stats(const DLTensor* y, const DLTensor* mean, const DLTensor* var, void* ws, void* stream);
+
 /* ---- K5 KL calibration   quantize/distribution_calibrate.py ------------- */
 /* counts[bin] += 1 for every clipped non-zero element; counts is uint64/int64 [bins+1].  :39-45 */
 FQ_API int fq_hist_nonzero(const DLTensor* x, const DLTensor* max_, int bins, int promotion,

@@ -78,6 +78,18 @@ def input_range(x, n_samples=None, cur_max=None, per_sample=None):
     return cur_max
 
 
+def channel_stats(y, mean=None, var=None):
+    """Per-channel batch mean and (two-pass, biased) variance of an [N, C, H, W] tensor for the fake-BN
+    EMA (convert_conv2d.py:148-153): 8 B/element instead of the six passes of the op-by-op formula."""
+    y = _f32(y, "y")
+    c = y.shape[1]
+    mean = torch.empty(c, dtype=torch.float32, device=y.device) if mean is None else mean
+    var = torch.empty(c, dtype=torch.float32, device=y.device) if var is None else var
+    a, m, v = dl(y), dl(mean), dl(var)
+    check_call(_lib().fq_channel_stats(a.ptr, m.ptr, v.ptr, workspace(y.device), current_stream()))
+    return mean, var
+
+
 def scale_from_max(max_, bits, signed, lo_mode, qparams=None, promotion=None):
     """{d, s, lo, hi} from a device-resident range.  convert_conv2d.py:57-64 + ste_func.py:41."""
     qparams = torch.empty(4, dtype=torch.float32, device=max_.device) if qparams is None else qparams

@@ -217,11 +217,9 @@ def _add_fake_bn_ema_hook(m):
     """convert_conv2d.py:144-154: batch statistics of the RAW convolution output for the EMA."""
     def _ema_hook(m, x):
         with torch.no_grad():
-            y = m.origin_forward(x[0], m.weight, m.bias)
-            num_samples = y.shape[0] * y.shape[2] * y.shape[3]
-            m.current_mean = y.sum(dim=(0, 2, 3)) / num_samples
-            diff_square = (y - m.current_mean.reshape(1, -1, 1, 1)) ** 2
-            m.current_var = diff_square.sum(dim=(0, 2, 3)) / num_samples
+            y = m.origin_forward(x[0], m.weight, m.bias)        # the reference's second convolution (:149)
+            # mean = y.sum(axis=(0,2,3)) / num ; var = ((y - mean) ** 2).sum(axis=(0,2,3)) / num   (:150-153)
+            m.current_mean, m.current_var = ops.channel_stats(y)
     m.register_forward_pre_hook(_ema_hook)
 
 

@@ -483,3 +483,20 @@ def test_beyond_2_31_elements_uses_64_bit_indexing(ops):
     nz = sum(int((x[i:i + (1 << 28)] != 0).sum()) for i in range(0, n, 1 << 28))
     assert int(counts.sum()) == nz
     assert int(counts[R.BINS - 1] + counts[R.BINS]) >= 1          # the 7.5 landed in the top bin
+
+
+@pytest.mark.parametrize("shape", [(8, 16, 14, 14), (128, 64, 8, 8), (4, 3, 7, 7), (32, 256, 1, 1), (2, 2048, 7, 7),
+                                   (16, 5, 13, 11), (1, 8, 32, 32)])
+def test_channel_stats_fake_bn(ops, shape):
+    y = (rng(sum(shape)).standard_normal(shape) * 2 + 0.5).astype(F32)
+    mean, var = ops.channel_stats(dev(y))
+    y64 = y.astype(np.float64)
+    want_m = y64.mean(axis=(0, 2, 3))
+    want_v = ((y64 - want_m.reshape(1, -1, 1, 1)) ** 2).mean(axis=(0, 2, 3))
+    # fp32 tree sums vs the reference's sequential fp32 sums: a few ULP of each other, both ~1e-6 from exact
+    assert np.allclose(host(mean), want_m, rtol=2e-6, atol=2e-6)
+    assert np.allclose(host(var), want_v, rtol=5e-6, atol=1e-7)
+    m2, v2 = ops.channel_stats(dev(y))            # deterministic, and the workspace is left clean
+    bits_equal(host(m2), host(mean))
+    bits_equal(host(v2), host(var))
+    bits_equal(host(ops.absmax_rows(dev(y), shape[0])), O.absmax_rows(y, shape[0]))
