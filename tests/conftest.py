@@ -1,11 +1,24 @@
 import os
 import sys
 
+# Shared GPU hosts can expose more cores than the job may use; a 16-thread OpenMP team spinning on 2 real
+# cores turns a one-second CPU reference convolution into minutes.  Keep the CPU side of the tests small.
+os.environ.setdefault("OMP_NUM_THREADS", "4")
+os.environ.setdefault("MKL_NUM_THREADS", "4")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+
+
+def pytest_sessionstart(session):
+    try:
+        import torch
+        torch.set_num_threads(4)
+    except Exception:
+        pass
 
 
 def pytest_configure(config):

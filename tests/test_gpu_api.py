@@ -72,7 +72,7 @@ def test_config1_cifar_resnet20_online_uint8_layerwise_and_logits(Q):
     rec = capture(net)
     net.fix_params()
     net.quantize_input(enable=True, online=True)          # simulate_quantization.py:346-347
-    X = torch.randn(128, 3, 32, 32, generator=torch.Generator().manual_seed(7))
+    X = torch.randn(32, 3, 32, 32, generator=torch.Generator().manual_seed(7))     # bench_configs.py runs N=128
     with torch.no_grad():
         logits = net(X.cuda()).cpu().numpy()
     blocks = net.collect_quantized_blocks()
