@@ -384,3 +384,26 @@ def test_activation_converter_and_relu6(Q):
     scale = F32(np.float64(cur) / 15)                      # legacy promotion: numpy.float32 / int -> float64
     want = (O.roundf((O.clip(a, 0, cur) / scale).astype(F32)) * scale).astype(F32)
     assert np.array_equal(bits(y.cpu().numpy()), bits(want))
+
+
+def test_export_quantized_int8_weights_and_thresholds(Q):
+    net, ref = build(Q, "cifar_resnet20_v1", 10)
+    for i, b in enumerate(net.collect_quantized_blocks()):
+        b.input_max.data.fill_(1.0 + i)
+    exp = Q.freeze.export_quantized(net)
+    ref_blocks = {m.name: m for m in ref.modules() if hasattr(m, "name")}
+    assert len(exp) == 20
+    for i, (name, e) in enumerate(exp.items()):
+        w = ref_blocks[name].weight.detach().numpy()
+        mx = np.abs(w).max()
+        q, lo, hi = O.quantize_int8_export(w, -mx, mx)
+        assert np.array_equal(e["weight_quantize"].cpu().numpy(), q)
+        assert F32(e["weight_max"].item()) == hi and F32(e["weight_min"].item()) == lo
+        assert e["max_calib_range"] == 1.0 + i and e["min_calib_range"] == 0.0
+    # freeze.quantize_params on a plain name list
+    params = {"w": torch.randn(8, 4, device="cuda"), "w_min": torch.tensor([-2.0], device="cuda"),
+              "w_max": torch.tensor([2.0], device="cuda"), "b": torch.ones(8, device="cuda")}
+    qp = Q.freeze.quantize_params(["w_quantize", "b"], params)
+    want, lo, hi = O.quantize_int8_export(params["w"].cpu().numpy(), -2.0, 2.0)
+    assert np.array_equal(qp["w_quantize"].cpu().numpy(), want) and float(qp["w_quantize_max"]) == 2.0
+    assert qp["b"] is params["b"]
