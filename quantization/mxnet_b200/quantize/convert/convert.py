@@ -1,139 +1,135 @@
-"""convert.py of the reference: walk the net, patch blocks, bolt the control methods onto ``net``."""
+"""Net-level entry points of the reference's ``quantize/convert/convert.py``.
+
+``convert_model`` visits the blocks children-first, hands each one whose EXACT type has a converter to
+that converter, and then equips ``net`` with the six control methods of the reference
+(``update_ema``, ``collect_quantized_blocks``, ``quantize_input``, ``enable_quantize``,
+``disable_quantize``, ``fix_params``; convert.py:66-121).  Here they live on one controller class and
+are bound to the net, and the EMA of every layer is a single kernel launch over packed state.
+"""
 import types
 
 import torch
 from torch import nn
 
 from ... import ops
+from .convert_act import convert_relu_to_relu6, gen_act_converter
+from .convert_bn import bypass_bn
 from .convert_conv2d import gen_conv2d_converter, sync_pending_ranges
 from .convert_dense import gen_dense_converter
-from .convert_act import gen_act_converter, convert_relu_to_relu6
-from .convert_bn import bypass_bn
 
 __all__ = ["convert_model", "convert_to_relu6", 'default_convert_fn']
 
-default_convert_fn = {
-    nn.Conv2d: gen_conv2d_converter(),
-    nn.Linear: gen_dense_converter(),
-    nn.ReLU: None,  # convert_relu_to_relu6,  # gen_act_converter(),
-    nn.BatchNorm2d: None  # bypass_bn
-}
+# Activation / BatchNorm are left alone by default, as in the reference (its alternatives are
+# convert_relu_to_relu6 / gen_act_converter() and bypass_bn).
+default_convert_fn = {nn.Conv2d: gen_conv2d_converter(), nn.Linear: gen_dense_converter(),
+                      nn.ReLU: None, nn.BatchNorm2d: None}
 
-_QBLOCK_TYPES = (nn.Linear, nn.Conv2d, nn.ReLU)
+_WEIGHTED = (nn.Linear, nn.Conv2d)
+_QUANTISABLE = _WEIGHTED + (nn.ReLU,)
 
 
-def _pack_states(blocks, attr, cur_attr):
-    """Keep every block's (1,) state and its (1,) current value in two contiguous device vectors so
-    that the EMA of ALL layers is one launch.  Re-packed lazily after .cuda()/.to()."""
-    ms = [m for m in blocks if getattr(m, attr, None) is not None]
-    if not ms:
-        return None, None, ms
-    dev = getattr(ms[0], attr).device
-    base = getattr(ms[0], attr).data
-    packed = all(getattr(m, attr).data.data_ptr() == base.data_ptr() + 4 * i and
-                 getattr(m, cur_attr).data_ptr() == getattr(ms[0], cur_attr).data_ptr() + 4 * i
-                 for i, m in enumerate(ms))
-    owner = getattr(ms[0], "_fq_arena", None)
-    if not (packed and owner is not None and owner[0].device == dev and owner[0].numel() == len(ms)):
-        state = torch.cat([getattr(m, attr).data.reshape(1).to(dev) for m in ms])
-        cur = torch.cat([getattr(m, cur_attr).reshape(1).to(dev) for m in ms])
-        for i, m in enumerate(ms):
-            getattr(m, attr).data = state[i:i + 1]
-            setattr(m, cur_attr, cur[i:i + 1])
-            m._fq_arena = (state, cur)
-        owner = (state, cur)
-    return owner[0], owner[1], ms
+def _packed(blocks, state_name, current_name):
+    """(state vector, current vector) holding every block's (1,) ``state_name`` parameter and its (1,)
+    ``current_name`` buffer contiguously, so one launch updates them all.  The per-block tensors become
+    views; the packing is redone whenever .cuda()/.to() has moved them."""
+    owners = [m for m in blocks if getattr(m, state_name, None) is not None]
+    if not owners:
+        return None
+    first = owners[0]
+    arena = getattr(first, "_fq_arena_" + state_name, None)
+    intact = arena is not None and arena[0].numel() == len(owners) and \
+        arena[0].device == getattr(first, state_name).device
+    if intact:
+        s0, c0 = arena[0].data_ptr(), arena[1].data_ptr()
+        intact = all(getattr(m, state_name).data.data_ptr() == s0 + 4 * i and
+                     getattr(m, current_name).data_ptr() == c0 + 4 * i for i, m in enumerate(owners))
+    if not intact:
+        dev = getattr(first, state_name).device
+        state = torch.cat([getattr(m, state_name).data.reshape(1).to(dev) for m in owners])
+        current = torch.cat([getattr(m, current_name).reshape(1).to(dev) for m in owners])
+        arena = (state, current)
+        for i, m in enumerate(owners):
+            getattr(m, state_name).data = state[i:i + 1]
+            setattr(m, current_name, current[i:i + 1])
+            setattr(m, "_fq_arena_" + state_name, arena)
+    return arena
+
+
+class _Controls:
+    """Bound onto the converted net by :func:`convert_model`."""
+
+    def collect_quantized_blocks(self):
+        found = []
+        self.apply(lambda m: found.append(m) if type(m) in _QUANTISABLE and hasattr(m, 'quantize_args') else None)
+        return found
+
+    def update_ema(self, momentum=0.9):
+        """state <- (1 - momentum) * current + momentum * state for input_max, act_max and the fake-BN
+        running statistics (convert.py:66-78)."""
+        blocks = self.collect_quantized_blocks()
+        sync_pending_ranges(blocks)       # data parallel only: shard-local ranges -> global-batch ranges
+        for state_name, current_name in (("input_max", "current_input_max"), ("act_max", "current_act_max")):
+            arena = _packed(blocks, state_name, current_name)
+            if arena is not None:
+                ops.ema_update(arena[0], arena[1], momentum, scalar_cur=True)
+        for m in blocks:
+            for stat, cur in (("running_mean", "current_mean"), ("running_var", "current_var")):
+                if getattr(m, stat, None) is not None and getattr(m, cur, None) is not None:
+                    ops.ema_update(getattr(m, stat).data, getattr(m, cur), momentum, scalar_cur=False)
+
+    def quantize_input(self, enable=True, online=True):
+        """Switch input (or activation) quantisation on/off and between online and offline ranges."""
+        for m in self.collect_quantized_blocks():
+            if type(m) in _WEIGHTED:
+                assert (not enable) or m.quantize_args.quantize_input
+                m.quantize_input, m.quantize_input_offline = enable, not online
+            elif type(m) == nn.ReLU:
+                assert (not enable) or m.quantize_args.quantize_act
+                m.quantize_act, m.quantize_act_offline = enable, not online
+
+    def enable_quantize(self):
+        for m in self.collect_quantized_blocks():
+            m.enable_quantize = True
+
+    def disable_quantize(self):
+        for m in self.collect_quantized_blocks():
+            m.enable_quantize = False
+
+    def fix_params(self):
+        """Ask every converted Conv2D to cache its quantised weight (and folded bias) at its next forward.
+        Dense blocks are not touched -- the reference does not fix them either (convert.py:117-121)."""
+        for m in self.collect_quantized_blocks():
+            if isinstance(m, nn.Conv2d):
+                m.fixed_params = 0
+
+
+_CONTROL_NAMES = ("update_ema", "collect_quantized_blocks", "quantize_input", "enable_quantize", "disable_quantize",
+                  "fix_params")
 
 
 def convert_model(net, exclude=[], convert_fn=default_convert_fn, custom_fn={}):
+    """Convert ``net`` in place to its simulated-quantisation version.
+
+    net        : torch.nn.Module
+    exclude    : blocks to leave untouched
+    convert_fn : {block type: converter(block) -> None}; looked up with the block's exact type
+    custom_fn  : {block instance: converter}; wins over ``convert_fn``
+    Returns None, like the reference (whose docstring promises the net).
     """
-    Convert the model to the one with simulated quantization.
-    :param net: torch.nn.Module
-        The net to convert.
-    :param exclude: list of torch.nn.Module
-        Blocks that want to exclude.
-    :param convert_fn: dict with (module type, func) key-value pairs
-        `func`: function `func(module) -> None`, applied to blocks whose EXACT type is the key.
-    :param custom_fn: dict with (module instance, func) pairs overriding `convert_fn`.
-    """
-    exclude_ids = set(id(b) for b in exclude)
+    skip = set(map(id, exclude))
 
-    # Convert network
-    def _convert(m):
-        if id(m) not in exclude_ids:
-            fn = custom_fn[m] if m in custom_fn else convert_fn.get(type(m))
-            if fn is not None:
-                fn(m)
-    net.apply(_convert)
-
-    # Add method to update ema for `input_max` in convs (convert.py:66-78)
-    def _update_ema(self, momentum=0.9):
-        blocks = self.collect_quantized_blocks()
-        sync_pending_ranges(blocks)     # data parallel only: shard-local ranges -> global-batch ranges
-        # if quantize input: every layer's scalar EMA in ONE launch
-        state, cur, _ = _pack_states(blocks, "input_max", "current_input_max")
-        if state is not None:
-            ops.ema_update(state, cur, momentum, scalar_cur=True)
-        # if quantize activation
-        state, cur, _ = _pack_states(blocks, "act_max", "current_act_max")
-        if state is not None:
-            ops.ema_update(state, cur, momentum, scalar_cur=True)
-        # if fake bn
-        for qblocks in blocks:
-            if getattr(qblocks, "running_mean", None) is not None and getattr(qblocks, "current_mean", None) is not None:
-                ops.ema_update(qblocks.running_mean.data, qblocks.current_mean, momentum, scalar_cur=False)
-            if getattr(qblocks, "running_var", None) is not None and getattr(qblocks, "current_var", None) is not None:
-                ops.ema_update(qblocks.running_var.data, qblocks.current_var, momentum, scalar_cur=False)
-    net.update_ema = types.MethodType(_update_ema, net)
-
-    # Add a method to collect all quantized convolution blocks
-    def _collect_quantized_blocks(self):
-        blocks = []
-
-        def _collect_blocks(m):
-            if type(m) in _QBLOCK_TYPES and hasattr(m, 'quantize_args'):
-                blocks.append(m)
-        net.apply(_collect_blocks)
-        return blocks
-    net.collect_quantized_blocks = types.MethodType(_collect_quantized_blocks, net)
-
-    # Add method to control the mode of input quantization as online or offline
-    def _quantize_input(self, enable=True, online=True):
-        for qblocks in self.collect_quantized_blocks():
-            if type(qblocks) in (nn.Linear, nn.Conv2d):
-                assert (not enable) or qblocks.quantize_args.quantize_input
-                qblocks.quantize_input = enable
-                qblocks.quantize_input_offline = not online
-            elif type(qblocks) == nn.ReLU:
-                assert (not enable) or qblocks.quantize_args.quantize_act
-                qblocks.quantize_act = enable
-                qblocks.quantize_act_offline = not online
-    net.quantize_input = types.MethodType(_quantize_input, net)
-
-    # Add method to control enable/disable quantization
-    def _enable_quantize(self):
-        for qblocks in self.collect_quantized_blocks():
-            qblocks.enable_quantize = True
-
-    def _disable_quantize(self):
-        for qblocks in self.collect_quantized_blocks():
-            qblocks.enable_quantize = False
-    net.enable_quantize = types.MethodType(_enable_quantize, net)
-    net.disable_quantize = types.MethodType(_disable_quantize, net)
-
-    # Add method to fixed parameters(weights and bias) -- Conv2D only, as in the reference
-    def _fix_params(self):
-        for m in net.collect_quantized_blocks():
-            if isinstance(m, nn.Conv2d):
-                m.fixed_params = 0
-    net.fix_params = types.MethodType(_fix_params, net)
+    def visit(m):
+        if id(m) in skip:
+            return
+        fn = custom_fn[m] if m in custom_fn else convert_fn.get(type(m))
+        if fn is not None:
+            fn(m)
+    net.apply(visit)
+    for name in _CONTROL_NAMES:
+        setattr(net, name, types.MethodType(getattr(_Controls, name), net))
 
 
 def convert_to_relu6(net, exclude=[]):
-    """Convert ReLUs in net to ReLU6."""
-    exclude_ids = set(id(b) for b in exclude)
-
-    def _convert_to_relu6(m):
-        if isinstance(m, nn.ReLU) and id(m) not in exclude_ids:
-            convert_relu_to_relu6(m)
-    return net.apply(_convert_to_relu6)
+    """Turn every ReLU of ``net`` (except those in ``exclude``) into a ReLU6; returns the net."""
+    skip = set(map(id, exclude))
+    return net.apply(lambda m: convert_relu_to_relu6(m) if isinstance(m, nn.ReLU) and id(m) not in skip else None)

@@ -1,4 +1,5 @@
-"""convert_bn.py of the reference: BatchNorm -> identity (used with fake-BN / merge-BN)."""
+"""``bypass_bn`` of the reference (convert_bn.py:32-36): a BatchNorm whose statistics were folded into
+the preceding convolution (fake-BN / merge-BN) becomes the identity."""
 import types
 
 from torch import nn
@@ -6,9 +7,10 @@ from torch import nn
 __all__ = ['bypass_bn']
 
 
+def _identity(self, x, *unused, **unused_kw):
+    return x
+
+
 def bypass_bn(m):
     assert isinstance(m, nn.BatchNorm2d)
-
-    def _forward(self, x, *args, **kwargs):
-        return x
-    m.forward = types.MethodType(_forward, m)
+    m.forward = types.MethodType(_identity, m)

@@ -1,2 +1,4 @@
-#-*- coding: utf-8 -*-
-from .initialize import *
+"""quantize.initialize"""
+from .initialize import qparams_init
+
+__all__ = ["qparams_init"]

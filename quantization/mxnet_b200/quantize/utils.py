@@ -1,4 +1,4 @@
-"""quantize/utils.py of the reference (collect_qparams :30-46, print_all_qparams :49-52)."""
+"""Qparam helpers of the reference's ``quantize/utils.py``."""
 from collections import OrderedDict
 
 from ..gluon_compat import collect_params
@@ -7,16 +7,11 @@ __all__ = ['collect_qparams', 'print_all_qparams']
 
 
 def collect_qparams(net):
-    """All ``*_min`` / ``*_max`` quantisation parameters, keyed by gluon-style name."""
-    ret = OrderedDict()
-    quant_params = collect_params(net, ".*[min|max]")
-    for param in quant_params:
-        if param.endswith(("_min", "_max")):
-            ret[param] = quant_params[param]
-    return ret
+    """OrderedDict of every quantisation range of ``net`` -- the parameters whose gluon-style name ends in
+    ``_min`` or ``_max`` (``<block>_input_max``, ``<block>_act_max``) -- keyed by that name."""
+    return OrderedDict((name, p) for name, p in collect_params(net).items() if name.endswith(("_min", "_max")))
 
 
 def print_all_qparams(net):
-    qparams = collect_qparams(net)
-    for param in qparams:
-        print("{}:\t\t{:+.4f}".format(param, float(qparams[param].reshape(-1)[0])))
+    for name, p in collect_qparams(net).items():
+        print("{}:\t\t{:+.4f}".format(name, float(p.reshape(-1)[0])))
