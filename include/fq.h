@@ -112,8 +112,9 @@ FQ_API int fq_forward_scalar_host(const DLTensor* x, float d, float s, float lo,
  * (convert_conv2d.py:77-79, 88-90, 93-95; convert_dense.py:56-58, 61-63). */
 FQ_API int fq_forward_rows(const DLTensor* x, int64_t rows, const DLTensor* scale, const DLTensor* y,
                     const DLTensor* codes, void* stream);
-/* Online input path in ONE cooperative launch: per-sample absmax -> Kahan mean -> scale -> quantise,
- * the second pass walking each block's slice backwards so it re-reads from L2.
+/* Online input path without a host round trip: a range launch (per-sample absmax; its last block does the
+ * Kahan mean and the scale math on the device) and the streaming quantiser, which walks the tensor backwards
+ * so that it re-reads from L2.
  * convert_conv2d.py:56-66 / convert_dense.py:41-49.  cur_max[0] and qparams[4] are written.
  * input_max != NULL selects the offline range (`input_max.asscalar()`, :58) while cur_max is still tracked;
  * y == NULL tracks the range only (quantize_input disabled, :55-57). */
@@ -121,7 +122,7 @@ FQ_API int fq_forward_online(const DLTensor* x, int64_t n_samples, int bits, int
                       int promotion, const DLTensor* input_max, const DLTensor* y, const DLTensor* codes,
                       const DLTensor* cur_max, const DLTensor* qparams, const DLTensor* per_sample,
                       void* ws, void* stream);
-/* Weight path in ONE cooperative launch: optional BN fold -> per-row absmax -> scale -> quantise.
+/* Weight path, two launches and no host round trip: optional BN fold -> per-row absmax -> scale -> quantise.
  * rows in {1 (layer), G (group), Cout (channel)}; bits <= 0 folds only (merge_bn.py:65-74).
  * gamma/beta/mean/var all NULL = no fold; bias may be NULL (treated as zeros, initialize.py:65-70).
  * convert_conv2d.py:47-51, 70-95; convert_dense.py:52-63. */

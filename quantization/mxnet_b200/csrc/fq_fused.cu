@@ -3,16 +3,17 @@
 //  fq_forward_online : per-sample absmax -> Kahan mean -> scale -> clip/quantise   (inputs)
 //      reference: quantize/convert/convert_conv2d.py:56-66, convert_dense.py:41-49, ste_func.py:41
 //      (abs, max, mean, .asscalar() sync, clip, div, round, mul = 7 passes + a host round trip there;
-//       here: one cooperative launch, 12 B/element worst case, 8 B/element when the tensor fits in L2
-//       because the second pass walks each block's slice backwards.)
+//       here: a range launch whose last block does the mean and the scale, then the streaming quantiser
+//       fed from device memory and walking the tensor backwards so that it re-reads from L2:
+//       12 B/element worst case, 8 B/element of HBM traffic when the tensor fits in L2.)
 //  fq_quant_weight   : optional BN fold -> per-row absmax -> scale -> quantise      (weights)
 //      reference: convert_conv2d.py:47-51, 70-95; convert_dense.py:52-63; merge_bn.py:65-74
 #include "fq_fused.cuh"
 
 namespace fq {
 
-enum InputMode { kRangeOnly = 0, kOnline = 1, kOfflineTrack = 2 };
-constexpr int64_t kOnlineSplitElems = 1LL << 24;     // 64 MB of fp32: half of the 126 MB L2
+enum InputMode { kRangeOnly = 0, kOfflineTrack = 2 };
+constexpr int64_t kL2ReuseElems = 24LL << 20;        // 96 MB of fp32: what may still sit in the 126 MB L2
 
 struct InputArgs {
   const float* x;
@@ -125,24 +126,16 @@ __global__ void __launch_bounds__(kThreads, 6) input_path_kernel(InputArgs a) {
       }
     }
   } else {
-    absmax_segments<MODE == kOnline>(a.x, begin, end, a.L, a.ws, red);
+    absmax_segments<true>(a.x, begin, end, a.L, a.ws, red);     // plain loads: leave the lines in L2 for the quantiser
   }
-
-  if (MODE == kOnline) {
-    grid_barrier(a.ws, [&]() { finish_rows(a.ws, a.rows, a.fin); });
-    const float d = __ldcg(a.fin.qparams + FQ_QP_D), s = __ldcg(a.fin.qparams + FQ_QP_S);
-    const float lo = __ldcg(a.fin.qparams + FQ_QP_LO), hi = __ldcg(a.fin.qparams + FQ_QP_HI);
-    quantise_slice<true>(a, begin, end, d, s, lo, hi);
-  } else {
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&a.ws->ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    finish_rows(a.ws, a.rows, a.fin);
-    if (threadIdx.x == 0) a.ws->ticket = 0;
-  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&a.ws->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  finish_rows(a.ws, a.rows, a.fin);
+  if (threadIdx.x == 0) a.ws->ticket = 0;
 }
 
 // Offline range + tracking for long rows (L >= one tile, so a tile meets at most two rows): one tile per
@@ -266,10 +259,16 @@ __device__ __forceinline__ void for_channels(const WeightArgs& a, int64_t begin,
       if (FOLD) fold_factors(a, c, g, sd);
       const auto ctx = cf(c);
       const int64_t lo = max(begin, c * a.Lc), hi = min(end, (c + 1) * a.Lc);
-      for (int64_t i = lo + lane; i < hi; i += 32) {
-        float v = __ldg(a.w + i);
-        if (FOLD) v = __fdiv_rn(__fmul_rn(v, g), sd);
-        sf(ctx, i, v);
+      // 8 independent loads in flight per lane before any of them is used: these rows are tiny and the
+      // loop is otherwise one L2 round trip per element
+      for (int64_t i0 = lo + lane; i0 < hi; i0 += 32 * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (i0 + 32 * u < hi) ? __ldg(a.w + i0 + 32 * u) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (i0 + 32 * u < hi) sf(ctx, i0 + 32 * u, FOLD ? __fdiv_rn(__fmul_rn(v[u], g), sd) : v[u]);
+        }
       }
     }
   } else {
@@ -289,7 +288,10 @@ __device__ __forceinline__ void for_channels(const WeightArgs& a, int64_t begin,
   }
 }
 
-template <bool FOLD>
+// PHASE 0: folded bias, then per-row max |W'| (or, bits <= 0, the folded weights themselves); the last block
+// to finish publishes the scales.  PHASE 1: quantise with those maxima, then restore the workspace.
+// Two plain launches: stream order is the barrier between them.
+template <bool FOLD, int PHASE>
 __global__ void __launch_bounds__(kThreads, 4) weight_path_kernel(WeightArgs a) {
   __shared__ float red[32];
   __shared__ unsigned int s_last;
@@ -297,6 +299,7 @@ __global__ void __launch_bounds__(kThreads, 4) weight_path_kernel(WeightArgs a) 
   const int64_t end = min(a.n, begin + a.per_block);
   const int64_t ch_per_row = a.cout / a.rows;
 
+  if (PHASE == 0) {
   // folded bias: b' = ((gamma * (b - mean)) / sqrtf(var + 1e-10)) + beta      convert_conv2d.py:51
   if (FOLD && a.bias_out != nullptr) {
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < a.cout; c += (int64_t)gridDim.x * blockDim.x) {
@@ -352,15 +355,23 @@ __global__ void __launch_bounds__(kThreads, 4) weight_path_kernel(WeightArgs a) 
     }
   }
 
-  grid_barrier(a.ws, [&]() {
-    if (a.scale_out != nullptr) {
+  if (a.scale_out != nullptr) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&a.ws->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
       const float qmax = (float)((1 << (a.bits - 1)) - 1);
       for (int64_t r = threadIdx.x; r < a.rows; r += blockDim.x)
         a.scale_out[r] = __fdiv_rn(__uint_as_float(__ldcg(&a.ws->rowmax[r])), qmax);
+      if (threadIdx.x == 0) a.ws->ticket = 0;
     }
-  });
+  }
+  return;
+  }   // PHASE 0
 
-  // phase 2: quantise, newest lines first
+  // PHASE 1: quantise, newest lines first
   const float qmax = (float)((1 << (a.bits - 1)) - 1);
   for_channels<FOLD>(
       a, begin, end,
@@ -406,25 +417,6 @@ static int code_kind_of(const char* who, const View& codes, int64_t n, int* kind
   else if (codes.code == kDLInt && codes.bits == 32) *kind = 5;
   else if (codes.code == kDLFloat && codes.bits == 32) *kind = 6;
   else FQ_REQUIRE(false, "%s: codes dtype (code %d, %d bits) unsupported", who, codes.code, codes.bits);
-  return 0;
-}
-
-// co-resident grid size for a cooperative kernel
-template <class K>
-static int coop_blocks(K kernel, int* out) {
-  int per_sm = 0;
-  FQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
-  FQ_REQUIRE(per_sm >= 1, "cooperative kernel does not fit on an SM");
-  if (per_sm > 8) per_sm = 8;
-  *out = per_sm * sm_count();
-  return 0;
-}
-
-template <class K, class A>
-static int launch_coop(K kernel, int grid, A& args, cudaStream_t st, const char* name) {
-  void* params[] = {(void*)&args};
-  FQ_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(kThreads), params, 0, st));
-  FQ_LAUNCH_CHECK(name);
   return 0;
 }
 
@@ -475,7 +467,7 @@ int fq_forward_online(const DLTensor* x_, int64_t n_samples, int bits, int is_si
 
   if (y.null) {   // range tracking only
     FQ_REQUIRE(codes.null, "%s: codes without y", who);
-    const int grid = slice_grid(a.n, sm_count() * 8, &a.per_block);
+    const int grid = row_grid(a.n, a.L, sm_count() * 8, &a.per_block);
     input_path_kernel<kRangeOnly><<<grid, kThreads, 0, st>>>(a);
     FQ_LAUNCH_CHECK("input_path_kernel<range>");
     return 0;
@@ -496,24 +488,19 @@ int fq_forward_online(const DLTensor* x_, int64_t n_samples, int bits, int is_si
     return 0;
   }
   if (!imax.null) {   // offline range, current range still tracked: one pass
-    const int grid = slice_grid(a.n, sm_count() * 8, &a.per_block);
+    const int grid = row_grid(a.n, a.L, sm_count() * 8, &a.per_block);
     input_path_kernel<kOfflineTrack><<<grid, kThreads, 0, st>>>(a);
     FQ_LAUNCH_CHECK("input_path_kernel<offline>");
     return 0;
   }
-  if (a.n >= kOnlineSplitElems) {
-    // Far larger than what L2 can hold between the passes: the cooperative kernel has nothing to gain, so
-    // run the range pass (which finishes with the Kahan mean and the scale on the device) and then the
-    // plain streaming quantiser; both run at copy speed and there is still no host round trip.
-    const int grid = slice_grid(a.n, sm_count() * 8, &a.per_block);
-    input_path_kernel<kRangeOnly><<<grid, kThreads, 0, st>>>(a);
-    FQ_LAUNCH_CHECK("input_path_kernel<range>");
-    return fq_forward_scalar(x_, qparams_, y_, codes_, stream);
-  }
-  int max_blocks = 0;
-  FQ_TRY(coop_blocks(input_path_kernel<kOnline>, &max_blocks) == 0);
-  const int grid = slice_grid(a.n, max_blocks, &a.per_block);
-  return launch_coop(input_path_kernel<kOnline>, grid, a, st, "input_path_kernel<online>");
+  // Online: the range pass (per-sample absmax, then the last block's Kahan mean and scale math) followed by
+  // the streaming quantiser reading its qparams from device memory -- no host round trip.  Two plain launches
+  // beat a cooperative single launch at every size (profiles/README.md): the activation is re-read from L2
+  // either way, and a cooperative launch costs more than the second launch it saves.
+  const int grid = row_grid(a.n, a.L, sm_count() * 8, &a.per_block);
+  input_path_kernel<kRangeOnly><<<grid, kThreads, 0, st>>>(a);
+  FQ_LAUNCH_CHECK("input_path_kernel<range>");
+  return launch_forward_scalar_dev(x_, a.fin.qparams, y_, codes_, a.n <= kL2ReuseElems, stream);
 }
 
 int fq_quant_weight(const DLTensor* w_, int64_t rows, int bits, const DLTensor* gamma_, const DLTensor* beta_,
@@ -578,15 +565,21 @@ int fq_quant_weight(const DLTensor* w_, int64_t rows, int bits, const DLTensor* 
   a.scale_out = scale_out.null ? nullptr : scale_out.as<float>();
   a.ws = (Workspace*)ws;
   cudaStream_t st = (cudaStream_t)stream;
-  int max_blocks = 0;
+  const int grid = row_grid(a.n, a.Lc, sm_count() * 8, &a.per_block);
   if (fold) {
-    FQ_TRY(coop_blocks(weight_path_kernel<true>, &max_blocks) == 0);
-    const int grid = slice_grid(a.n, max_blocks, &a.per_block);
-    return launch_coop(weight_path_kernel<true>, grid, a, st, "weight_path_kernel<fold>");
+    weight_path_kernel<true, 0><<<grid, kThreads, 0, st>>>(a);
+    FQ_LAUNCH_CHECK("weight_path_kernel<fold, range>");
+    if (bits > 0) {
+      weight_path_kernel<true, 1><<<grid, kThreads, 0, st>>>(a);
+      FQ_LAUNCH_CHECK("weight_path_kernel<fold, quantise>");
+    }
+    return 0;
   }
-  FQ_TRY(coop_blocks(weight_path_kernel<false>, &max_blocks) == 0);
-  const int grid = slice_grid(a.n, max_blocks, &a.per_block);
-  return launch_coop(weight_path_kernel<false>, grid, a, st, "weight_path_kernel");
+  weight_path_kernel<false, 0><<<grid, kThreads, 0, st>>>(a);
+  FQ_LAUNCH_CHECK("weight_path_kernel<range>");
+  weight_path_kernel<false, 1><<<grid, kThreads, 0, st>>>(a);
+  FQ_LAUNCH_CHECK("weight_path_kernel<quantise>");
+  return 0;
 }
 
 }  // extern "C"

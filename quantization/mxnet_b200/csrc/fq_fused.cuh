@@ -16,7 +16,8 @@ struct FinishParams {
 // Each block owns a contiguous slice of per_block elements (a multiple of 4 * kThreads * kUnroll so that
 // every slice starts 16 B aligned).  Returns the grid size.
 inline int slice_grid(int64_t n, int max_blocks, int64_t* per_block) {
-  const int64_t quantum = 4LL * kThreads * kUnroll;
+  // small tensors are latency-bound: give them more, smaller slices (one float4 per thread)
+  const int64_t quantum = (n < (1LL << 20)) ? 4LL * kThreads : 4LL * kThreads * kUnroll;
   int64_t blocks = (n + quantum - 1) / quantum;
   if (blocks < 1) blocks = 1;
   if (blocks > max_blocks) blocks = max_blocks;
@@ -24,6 +25,17 @@ inline int slice_grid(int64_t n, int max_blocks, int64_t* per_block) {
   pb = (pb + quantum - 1) / quantum * quantum;
   *per_block = pb;
   return (int)((n + pb - 1) / pb > 0 ? (n + pb - 1) / pb : 1);
+}
+
+// Slices for kernels that walk [rows, L]: short rows (< 2048 elements, taken one per warp with scalar loads, so
+// no alignment requirement) get whole rows per block and as many blocks as there are rows -- these tensors are
+// tiny and latency-bound, and every row costs a dependent chain of loads; long rows use the 16 B aligned slices.
+inline int row_grid(int64_t n, int64_t L, int max_blocks, int64_t* per_block) {
+  if (L >= 2048 || L <= 0) return slice_grid(n, max_blocks, per_block);
+  const int64_t rows = n / L;
+  const int64_t k = (rows + max_blocks - 1) / max_blocks;
+  *per_block = k * L;
+  return (int)((rows + k - 1) / k);
 }
 
 // Grid for the tile-interleaved elementwise kernels: one block per tile up to max_blocks.
@@ -48,6 +60,12 @@ inline bool check_quant_args(const char* who, int bits, int lo_mode, int promoti
   }
   return true;
 }
+
+// y = roundf(clip(x, lo, hi) / d) * s with {d, s, lo, hi} read from device memory (fq_quant.cu).  `reverse`
+// makes the first-scheduled blocks take the END of the tensor: after a forward range pass those are the
+// lines most likely still in L2.
+int launch_forward_scalar_dev(const DLTensor* x, const float* qp_dev, const DLTensor* y, const DLTensor* codes,
+                              bool reverse, void* stream);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

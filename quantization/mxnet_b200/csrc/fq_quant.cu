@@ -70,7 +70,8 @@ template <bool CLIP, class Code>
 __global__ void __launch_bounds__(kThreads, 6) forward_scalar_kernel(const float* __restrict__ x, int64_t n,
                                                                      int64_t per_block,
                                                                      const float* __restrict__ qp_dev,
-                                                                     ScalarQuant<CLIP, Code> op, int vectorised) {
+                                                                     ScalarQuant<CLIP, Code> op, int vectorised,
+                                                                     int reverse) {
   if (qp_dev != nullptr) {
     op.d = __ldg(qp_dev + FQ_QP_D);
     op.s = __ldg(qp_dev + FQ_QP_S);
@@ -81,7 +82,9 @@ __global__ void __launch_bounds__(kThreads, 6) forward_scalar_kernel(const float
   if (vectorised) {
     const int64_t nvec = n >> 2;
     const float4* p4 = reinterpret_cast<const float4*>(x);
-    for (int64_t tile = blockIdx.x; tile * (kTileElems / 4) < nvec; tile += gridDim.x) {
+    const int64_t ntiles = (nvec + kTileElems / 4 - 1) / (kTileElems / 4);
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int64_t tile = reverse ? (ntiles - 1 - t) : t;
       const int64_t v0 = tile * (kTileElems / 4) + threadIdx.x;
       if (v0 + (kUnroll - 1) * kThreads < nvec) {
         float4 v[kUnroll];
@@ -301,7 +304,8 @@ static int with_code_sink(const char* who, const View& codes, int64_t n, F f) {
 }
 
 static int forward_scalar_impl(const char* who, const DLTensor* x_, const float* qp_dev, float d, float s, float lo,
-                               float hi, bool clip, const DLTensor* y_, const DLTensor* codes_, void* stream) {
+                               float hi, bool clip, const DLTensor* y_, const DLTensor* codes_, void* stream,
+                               bool reverse = false) {
   View x, y, codes;
   FQ_TRY(view_of(x_, who, false, &x));
   FQ_TRY(view_of(y_, who, false, &y));
@@ -318,14 +322,21 @@ static int forward_scalar_impl(const char* who, const DLTensor* x_, const float*
     using Code = decltype(sink);
     if (clip) {
       ScalarQuant<true, Code> op{d, s, lo, hi, y.as<float>(), sink, QDiv()};
-      forward_scalar_kernel<true, Code><<<grid, kThreads, 0, st>>>(x.as<const float>(), n, per_block, qp_dev, op, vec);
+      forward_scalar_kernel<true, Code><<<grid, kThreads, 0, st>>>(x.as<const float>(), n, per_block, qp_dev, op, vec,
+                                                                   reverse);
     } else {
       ScalarQuant<false, Code> op{d, s, lo, hi, y.as<float>(), sink, QDiv()};
-      forward_scalar_kernel<false, Code><<<grid, kThreads, 0, st>>>(x.as<const float>(), n, per_block, qp_dev, op, vec);
+      forward_scalar_kernel<false, Code><<<grid, kThreads, 0, st>>>(x.as<const float>(), n, per_block, qp_dev, op, vec,
+                                                                    reverse);
     }
     FQ_LAUNCH_CHECK("forward_scalar_kernel");
     return 0;
   });
+}
+
+int launch_forward_scalar_dev(const DLTensor* x, const float* qp_dev, const DLTensor* y, const DLTensor* codes,
+                              bool reverse, void* stream) {
+  return forward_scalar_impl("fq_forward_online", x, qp_dev, 0, 0, 0, 0, true, y, codes, stream, reverse);
 }
 
 }  // namespace fq

@@ -204,7 +204,7 @@ static int launch_rows_absmax(const View& x, int64_t rows, Workspace* ws, const 
   const int64_t n = x.numel;
   const int64_t L = n / rows;
   int64_t per_block;
-  const int grid = slice_grid(n, sm_count() * 8, &per_block);
+  const int grid = row_grid(n, L, sm_count() * 8, &per_block);
   rows_absmax_kernel<<<grid, kThreads, 0, st>>>(x.as<const float>(), n, rows, L, per_block, ws, fin);
   FQ_LAUNCH_CHECK("rows_absmax_kernel");
   return 0;

@@ -3,7 +3,7 @@
 The small-tensor configurations (CIFAR ResNet-20, MobileNetV2 at 32x32) are launch-bound: a forward is
 ~100 kernels of a few microseconds each, and eager execution spends more time in Python than on the GPU.
 Every libfq_b200 entry point is capture-safe (no allocation, no host synchronisation, explicit stream,
-cooperative launches included), so the whole forward -- framework convolutions and fake-quant kernels
+plain launches only), so the whole forward -- framework convolutions and fake-quant kernels
 alike -- can be recorded once and replayed with no host work in between.  The per-block state the
 reference exposes (``current_input_max``, ``input_max``) is updated by the replayed kernels in place.
 """
