@@ -59,9 +59,7 @@ bool view_of(const DLTensor* t, const char* name, bool allow_null, View* out);
 struct Workspace {
   unsigned int ticket;          // "last block done" counter
   unsigned int ticket2;
-  unsigned int bar_count;       // grid barrier
-  unsigned int bar_gen;         // monotonically increasing generation (never reset)
-  unsigned int pad[28];
+  unsigned int pad[30];
   unsigned int rowmax[FQ_MAX_ROWS];   // |x| bit patterns, atomicMax target
   float minmax_part[2 * 4096];        // per-block partials of fq_minmax
 };
@@ -242,36 +240,6 @@ __device__ __forceinline__ void for_tiles(const float* __restrict__ x, int64_t n
   if (blockIdx.x == 0 && threadIdx.x < n - tail0) sf(tail0 + threadIdx.x, x[tail0 + threadIdx.x]);
 }
 
-// Grid-wide barrier for cooperative (co-resident) launches.  The last arriver runs `fn` (whole block)
-// before releasing the others.  bar_gen only ever grows, bar_count returns to 0.
-template <class FN>
-__device__ __forceinline__ void grid_barrier(Workspace* ws, FN fn) {
-  __shared__ unsigned int s_last, s_gen;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int gen = *((volatile unsigned int*)&ws->bar_gen);
-    __threadfence();
-    unsigned int t = atomicAdd(&ws->bar_count, 1u);
-    s_last = (t == gridDim.x - 1);
-    s_gen = gen;
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    fn();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      ws->bar_count = 0;
-      __threadfence();
-      atomicAdd(&ws->bar_gen, 1u);
-    }
-  } else if (threadIdx.x == 0) {
-    while (*((volatile unsigned int*)&ws->bar_gen) == s_gen) { __nanosleep(32); }
-    __threadfence();
-  }
-  __syncthreads();
-}
 #endif  // __CUDACC__
 
 }  // namespace fq

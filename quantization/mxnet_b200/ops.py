@@ -137,7 +137,8 @@ def forward_rows(x, scale, out=None, codes_dtype=None):
 
 def forward_online(x, bits=8, signed=False, lo_mode=LO_ZERO, input_max=None, quantize=True, n_samples=None,
                    out=None, cur_max=None, qparams=None, per_sample=None, codes_dtype=None, promotion=None):
-    """The whole input path of a converted block in one launch (convert_conv2d.py:56-66).
+    """The whole input path of a converted block without a host round trip (convert_conv2d.py:56-66):
+    range launch + streaming quantiser online, one fused launch when the range comes from ``input_max``.
 
     Returns (y, cur_max, qparams[, codes]); y is None when ``quantize`` is False (range tracking only).
     """
@@ -158,7 +159,7 @@ def forward_online(x, bits=8, signed=False, lo_mode=LO_ZERO, input_max=None, qua
 
 def quant_weight(w, rows, bits, gamma=None, beta=None, mean=None, var=None, bias=None, out=None, bias_out=None,
                  scale_out=None, codes_dtype=None):
-    """BN fold (optional) + per-row absmax + scale + quantise in one launch.
+    """BN fold (optional) + per-row absmax + scale + quantise: two launches, nothing read back.
 
     convert_conv2d.py:47-51, 70-95; bits <= 0 folds only (merge_bn.py:65-74).
     Returns (w_q, bias_folded or None, scales or None[, codes]).

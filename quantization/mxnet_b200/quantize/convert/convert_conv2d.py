@@ -3,7 +3,7 @@
 The patched forward keeps the reference's control flow and per-block state (``quantize_args``,
 ``fixed_params`` tri-state, ``enable_quantize``, ``quantize_input``, ``quantize_input_offline``,
 ``current_input_max``, Parameter ``input_max``; fake-BN ``gamma/beta/running_mean/running_var``),
-but each tensor is touched by ONE fused kernel launch and nothing is read back to the host:
+but each tensor goes through one or two fused kernel launches and nothing is read back to the host:
 ``current_input_max`` is a (1,) device tensor instead of a Python float.
 """
 import types
@@ -55,7 +55,7 @@ def _weight_path(weight, bias, gamma, beta, mean, var, rows, bits):
 
 
 class _InputPath(torch.autograd.Function):
-    """convert_conv2d.py:56-66 in one launch; backward = identity (ste_func.py:43-44)."""
+    """convert_conv2d.py:56-66 on the device; backward = identity (ste_func.py:43-44)."""
 
     @staticmethod
     def forward(ctx, x, m, lo_mode):
@@ -108,7 +108,7 @@ def sync_pending_ranges(blocks):
 
 
 class _WeightPath(torch.autograd.Function):
-    """convert_conv2d.py:47-51 (fake-BN fold) + :70-95 (range, scale, fake-quant) in one launch.
+    """convert_conv2d.py:47-51 (fake-BN fold) + :70-95 (range, scale, fake-quant), fused.
 
     Backward: identity through the quantiser, then the fold's chain rule in the op order MXNet's
     autograd would replay ((W * gamma) / sd ; gamma * (b - mean) / sd + beta)."""
