@@ -500,3 +500,77 @@ def test_channel_stats_fake_bn(ops, shape):
     bits_equal(host(m2), host(mean))
     bits_equal(host(v2), host(var))
     bits_equal(host(ops.absmax_rows(dev(y), shape[0])), O.absmax_rows(y, shape[0]))
+
+
+def test_randomised_shapes_against_oracle(ops):
+    """Seeded fuzzing over ragged shapes, bit widths, signedness and promotion regimes: every slice / tile /
+    short-row / long-row code path is hit with sizes that are not multiples of anything."""
+    r = rng(2024)
+    for case in range(60):
+        n_s = int(r.choice([1, 2, 3, 7, 16, 33, 128]))
+        L = int(r.choice([1, 5, 9, 31, 64, 257, 1024, 2047, 2048, 2051, 4096, 4100, 9001, 40000]))
+        bits = int(r.choice([2, 3, 4, 5, 6, 8, 12, 16]))
+        signed = bool(r.randint(2))
+        promo = ["legacy", "nep50"][r.randint(2)]
+        x = (r.standard_normal((n_s, L)) * float(r.choice([1e-3, 1.0, 40.0]))).astype(F32)
+        if not signed:
+            x = np.maximum(x, 0)
+        layer = ["conv", "dense"][r.randint(2)]
+        lo_mode = ops.LO_NEG_MAX if (signed and layer == "conv") else ops.LO_ZERO
+        # online
+        y, code, cur, qp = O.fake_quant_input(x, bits, signed, None, promo, layer)
+        gy, gcur, gqp = ops.forward_online(dev(x), bits, signed, lo_mode, promotion=promo)
+        bits_equal(host(gcur), np.array([cur], F32))
+        bits_equal(host(gy), y)
+        # offline range + tracking
+        imax = F32(abs(r.standard_normal()) + 0.1)
+        y, code, cur, qp = O.fake_quant_input(x, bits, signed, imax, promo, layer)
+        gy, gcur, gqp = ops.forward_online(dev(x), bits, signed, lo_mode, input_max=dev(np.array([imax], F32)), promotion=promo)
+        bits_equal(host(gcur), np.array([cur], F32))
+        bits_equal(host(gqp), np.array(qp, F32))
+        bits_equal(host(gy), y)
+        # weights, per-row and per-layer, treating x as [rows, L]
+        w = (x - x.mean()).astype(F32)
+        for rows in (n_s, 1):
+            s, d, _ = O.weight_scales(w, rows, max(bits, 2))
+            wy, _ = O.fake_quant_rows(w, rows, s, d)
+            gw, _, gs = ops.quant_weight(dev(w), rows, max(bits, 2))
+            bits_equal(host(gs), s)
+            bits_equal(host(gw), wy)
+            bits_equal(host(ops.forward_rows(dev(w), dev(s))), wy)
+        # histogram
+        xa = np.abs(x)
+        if xa.max() > 0:
+            want = O.histogram_counts(xa, R.BINS, xa.max(), promo)
+            counts = torch.zeros(R.BINS + 1, dtype=torch.int64, device="cuda")
+            ops.hist_nonzero(dev(xa), dev(np.array([xa.max()], F32)), R.BINS, counts, promotion=promo)
+            assert np.array_equal(host(counts)[:len(want)], want)
+
+
+def test_c_abi_rejects_bad_arguments_with_messages(ops):
+    """Error behaviour of the boundary: non-zero return + fq_last_error(), surfaced as FQError; nothing silently
+    falls back or launches on bad input."""
+    from quantization.mxnet_b200._ffi import FQError
+    x = torch.randn(8, 16, device="cuda")
+    with pytest.raises(FQError, match="contiguous"):
+        ops._ffi.dl(x.t())
+    with pytest.raises(FQError, match="float32"):
+        ops.forward_scalar_host(x.double(), 1.0, 1.0)
+    with pytest.raises(FQError, match="not divisible|divisible"):
+        ops.absmax_rows(x, 3)
+    with pytest.raises(FQError, match="rows"):
+        ops.absmax_rows(x, 0)
+    with pytest.raises(FQError, match="bits"):
+        ops.scale_from_max(torch.ones(1, device="cuda"), 1, False, ops.LO_ZERO)
+    with pytest.raises(FQError, match="qparams"):
+        ops.forward_scalar(x, torch.ones(3, device="cuda"))
+    with pytest.raises(FQError, match="counts"):
+        ops.hist_nonzero(x.abs(), torch.ones(1, device="cuda"), 2048, torch.zeros(2048, dtype=torch.int64, device="cuda"))
+    with pytest.raises(FQError, match="unsupported|codes dtype"):
+        ops.forward_scalar_host(x, 1.0, 1.0, codes_dtype=torch.float64)
+    with pytest.raises(FQError, match="given together"):
+        ops.quant_weight(torch.randn(4, 4, device="cuda"), 1, 8, gamma=torch.ones(4, device="cuda"))
+    with pytest.raises(FQError, match="divide Cout|must divide"):
+        ops.quant_weight(torch.randn(6, 4, device="cuda"), 4, 8)
+    # after all those failures the library still works and the workspace is clean
+    bits_equal(host(ops.absmax_rows(x, 8)), O.absmax_rows(host(x), 8))

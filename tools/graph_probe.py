@@ -4,7 +4,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from quantization.mxnet_b200 import ops  # noqa: E402
 
 

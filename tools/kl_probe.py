@@ -1,5 +1,5 @@
 import sys, torch, numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from quantization.mxnet_b200 import ops
 from oracle import golden_recipes as R
 h = np.stack([R.kl_hist_cases()["relu"]] * 27)

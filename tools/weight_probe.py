@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from quantization.mxnet_b200 import ops
 for shape in ((16, 1024), (96, 16, 1, 1), (144, 1, 3, 3), (320, 960, 1, 1), (64, 64, 3, 3)):
     w = torch.randn(*shape, device="cuda")
