@@ -131,6 +131,22 @@ FQ_API int fq_quant_weight(const DLTensor* w, int64_t rows, int bits, const DLTe
                     const DLTensor* bias_out, const DLTensor* scale_out, const DLTensor* codes,
                     void* ws, void* stream);
 
+/* The weight paths of MANY blocks (a whole network) in one launch per phase: launch-bound nets spend more time
+ * launching 50 tiny kernels than running them.  Outputs go to caller-owned flat float32 buffers at the given
+ * element offsets (w_off a multiple of 4; bias_off / scale_off < 0 = not wanted), so a cached job table stays
+ * valid when only the output allocation changes.  Fold-only jobs (bits <= 0) and jobs with and without BN fold
+ * can be mixed.  Results are bit-identical to calling fq_quant_weight per block. */
+typedef struct {
+  const DLTensor *w, *gamma, *beta, *mean, *var, *bias;   /* gamma..var NULL together = no fold; bias may be NULL */
+  int64_t rows;                                           /* 1 | G | Cout */
+  int32_t bits;                                           /* <= 0: fold only */
+  int32_t reserved;
+  int64_t w_off, bias_off, scale_off;
+} FqWeightJob;
+FQ_API int fq_quant_weight_multi(const FqWeightJob* jobs, int n_jobs, const DLTensor* w_out_flat,
+                                 const DLTensor* bias_out_flat, const DLTensor* scale_out_flat, void* ws,
+                                 void* stream);
+
 /* ---- K3 straight-through estimator backward ----------------------------- */
 FQ_API int fq_ste_backward(const DLTensor* dy, const DLTensor* x, const DLTensor* qparams, const DLTensor* dx,
                     int mode, void* stream);

@@ -36,6 +36,13 @@ class DLTensor(_c.Structure):
 
 
 P = _c.POINTER(DLTensor)
+
+
+class FqWeightJob(_c.Structure):
+    _fields_ = [("w", P), ("gamma", P), ("beta", P), ("mean", P), ("var", P), ("bias", P), ("rows", _c.c_int64),
+                ("bits", _c.c_int32), ("reserved", _c.c_int32), ("w_off", _c.c_int64), ("bias_off", _c.c_int64),
+                ("scale_off", _c.c_int64)]
+
 kDLCPU, kDLCUDA = 1, 2
 _DTYPES = {
     torch.float32: (2, 32), torch.float64: (2, 64),
@@ -67,6 +74,7 @@ SIGNATURES = {
     "fq_forward_online": (_c.c_int, [P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, P, P, P, P, P, P,
                                      _c.c_void_p, _c.c_void_p]),
     "fq_quant_weight": (_c.c_int, [P, _c.c_int64, _c.c_int, P, P, P, P, P, P, P, P, P, _c.c_void_p, _c.c_void_p]),
+    "fq_quant_weight_multi": (_c.c_int, [_c.POINTER(FqWeightJob), _c.c_int, P, P, P, _c.c_void_p, _c.c_void_p]),
     "fq_ste_backward": (_c.c_int, [P, P, P, P, _c.c_int, _c.c_void_p]),
     "fq_ema_update": (_c.c_int, [P, P, _c.c_double, _c.c_int, _c.c_int, _c.c_void_p]),
     "fq_hist_nonzero": (_c.c_int, [P, P, _c.c_int, _c.c_int, P, _c.c_void_p]),

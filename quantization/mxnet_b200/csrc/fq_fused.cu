@@ -232,6 +232,7 @@ struct WeightArgs {
   float* bias_out;
   float* scale_out;
   Workspace* ws;
+  unsigned int* rowmax;                   // this tensor's row-max slots inside ws->rowmax
 };
 
 struct RowQ {      // per-row quantiser: multiplier s_r and the divisor context of d_r = s_r + 1e-10
@@ -291,18 +292,21 @@ __device__ __forceinline__ void for_channels(const WeightArgs& a, int64_t begin,
 // PHASE 0: folded bias, then per-row max |W'| (or, bits <= 0, the folded weights themselves); the last block
 // to finish publishes the scales.  PHASE 1: quantise with those maxima, then restore the workspace.
 // Two plain launches: stream order is the barrier between them.
-template <bool FOLD, int PHASE>
-__global__ void __launch_bounds__(kThreads, 4) weight_path_kernel(WeightArgs a) {
+// blk / nblk: this block's index and the number of blocks working on THIS tensor.  MULTI (several tensors
+// in one launch): no tickets -- block 0 of the tensor writes the scales in phase 1 and the host clears the
+// row-max slots with a memset node afterwards.
+template <bool FOLD, int PHASE, bool MULTI>
+__device__ __forceinline__ void weight_phase(const WeightArgs& a, int blk, int nblk) {
   __shared__ float red[32];
   __shared__ unsigned int s_last;
-  const int64_t begin = (int64_t)blockIdx.x * a.per_block;
+  const int64_t begin = (int64_t)blk * a.per_block;
   const int64_t end = min(a.n, begin + a.per_block);
   const int64_t ch_per_row = a.cout / a.rows;
 
   if (PHASE == 0) {
   // folded bias: b' = ((gamma * (b - mean)) / sqrtf(var + 1e-10)) + beta      convert_conv2d.py:51
   if (FOLD && a.bias_out != nullptr) {
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < a.cout; c += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t c = (int64_t)blk * blockDim.x + threadIdx.x; c < a.cout; c += (int64_t)nblk * blockDim.x) {
       const float b = a.bias ? __ldg(a.bias + c) : 0.f;
       const float sd = __fsqrt_rn(__fadd_rn(__ldg(a.var + c), 1e-10f));
       a.bias_out[c] =
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 4) weight_path_kernel(WeightArgs a) 
           m = fmaxf(m, fabsf(v));
         }
         m = warp_max(m);
-        if (lane == 0) atomicMax(&a.ws->rowmax[c / ch_per_row], __float_as_uint(m));
+        if (lane == 0) atomicMax(&a.rowmax[c / ch_per_row], __float_as_uint(m));
       }
     } else {
       const int64_t c0 = begin / a.Lc, c1 = (end - 1) / a.Lc;
@@ -350,33 +354,40 @@ __global__ void __launch_bounds__(kThreads, 4) weight_path_kernel(WeightArgs a) 
             [&](int64_t, float4 v) { m = absmax4(m, make_float4(f1(v.x), f1(v.y), f1(v.z), f1(v.w))); },
             [&](int64_t, float v) { m = fmaxf(m, fabsf(f1(v))); });
         m = block_max(m, red);
-        if (threadIdx.x == 0) atomicMax(&a.ws->rowmax[c / ch_per_row], __float_as_uint(m));
+        if (threadIdx.x == 0) atomicMax(&a.rowmax[c / ch_per_row], __float_as_uint(m));
       }
     }
   }
 
-  if (a.scale_out != nullptr) {
+  if (!MULTI && a.scale_out != nullptr) {
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&a.ws->ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) s_last = (atomicAdd(&a.ws->ticket, 1u) == (unsigned)nblk - 1);
     __syncthreads();
     if (s_last) {
       __threadfence();
       const float qmax = (float)((1 << (a.bits - 1)) - 1);
       for (int64_t r = threadIdx.x; r < a.rows; r += blockDim.x)
-        a.scale_out[r] = __fdiv_rn(__uint_as_float(__ldcg(&a.ws->rowmax[r])), qmax);
+        a.scale_out[r] = __fdiv_rn(__uint_as_float(__ldcg(&a.rowmax[r])), qmax);
       if (threadIdx.x == 0) a.ws->ticket = 0;
     }
   }
   return;
   }   // PHASE 0
 
+  if (a.bits <= 0) return;               // fold-only job inside a mixed launch: phase 0 did everything
+  if (MULTI && blk == 0 && a.scale_out != nullptr) {
+    const float qm = (float)((1 << (a.bits - 1)) - 1);
+    for (int64_t r = threadIdx.x; r < a.rows; r += blockDim.x)
+      a.scale_out[r] = __fdiv_rn(__uint_as_float(__ldcg(&a.rowmax[r])), qm);
+  }
+
   // PHASE 1: quantise, newest lines first
   const float qmax = (float)((1 << (a.bits - 1)) - 1);
   for_channels<FOLD>(
       a, begin, end,
       [&](int64_t c) {   // {s_r, d_r}: convert_conv2d.py:76 / ste_func.py:39
-        const float s = __fdiv_rn(__uint_as_float(__ldcg(&a.ws->rowmax[c / ch_per_row])), qmax);
+        const float s = __fdiv_rn(__uint_as_float(__ldcg(&a.rowmax[c / ch_per_row])), qmax);
         RowQ rq;
         rq.s = s;
         rq.q = QDiv::make(__fadd_rn(s, 1e-10f));
@@ -396,14 +407,69 @@ __global__ void __launch_bounds__(kThreads, 4) weight_path_kernel(WeightArgs a) 
       true);
 
   // restore the workspace invariant once every block has consumed the row maxima
+  if (MULTI) return;
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&a.ws->ticket2, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) s_last = (atomicAdd(&a.ws->ticket2, 1u) == (unsigned)nblk - 1);
   __syncthreads();
   if (s_last) {
-    for (int64_t r = threadIdx.x; r < a.rows; r += blockDim.x) a.ws->rowmax[r] = 0u;
+    for (int64_t r = threadIdx.x; r < a.rows; r += blockDim.x) a.rowmax[r] = 0u;
     if (threadIdx.x == 0) a.ws->ticket2 = 0;
   }
+}
+
+template <bool FOLD, int PHASE>
+__global__ void __launch_bounds__(kThreads, 4) weight_path_kernel(WeightArgs a) {
+  weight_phase<FOLD, PHASE, false>(a, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// ---- every converted block's weights in one launch per phase ------------------------------------------
+constexpr int kWeightBatch = 30;       // jobs per launch: the table travels as a kernel parameter (< 4 KB)
+
+struct WeightJobDev {
+  const float *w, *gamma, *beta, *mean, *var, *bias;
+  float *w_out, *bias_out, *scale_out;
+  int64_t n, per_block;
+  int cout, rows, bits, first_block, rowmax_off, pad;
+};
+
+struct WeightBatch {
+  WeightJobDev job[kWeightBatch];
+  int count, total_blocks;
+  Workspace* ws;
+};
+
+template <int PHASE>
+__global__ void __launch_bounds__(kThreads, 4) weight_multi_kernel(const __grid_constant__ WeightBatch tb) {
+  int j = 0;
+  while (j + 1 < tb.count && (int)blockIdx.x >= tb.job[j + 1].first_block) ++j;
+  const WeightJobDev& q = tb.job[j];
+  WeightArgs a;
+  a.w = q.w;
+  a.w_out = q.w_out;
+  a.codes = nullptr;
+  a.code_kind = 0;
+  a.n = q.n;
+  a.cout = q.cout;
+  a.Lc = q.n / q.cout;
+  a.rows = q.rows;
+  a.per_block = q.per_block;
+  a.bits = q.bits;
+  a.gamma = q.gamma;
+  a.beta = q.beta;
+  a.mean = q.mean;
+  a.var = q.var;
+  a.bias = q.bias;
+  a.bias_out = q.bias_out;
+  a.scale_out = q.scale_out;
+  a.ws = tb.ws;
+  a.rowmax = tb.ws->rowmax + q.rowmax_off;
+  const int blk = (int)blockIdx.x - q.first_block;
+  const int nblk = ((j + 1 < tb.count) ? tb.job[j + 1].first_block : tb.total_blocks) - q.first_block;
+  if (q.gamma != nullptr)
+    weight_phase<true, PHASE, true>(a, blk, nblk);
+  else
+    weight_phase<false, PHASE, true>(a, blk, nblk);
 }
 
 static int code_kind_of(const char* who, const View& codes, int64_t n, int* kind) {
@@ -564,6 +630,7 @@ int fq_quant_weight(const DLTensor* w_, int64_t rows, int bits, const DLTensor* 
   a.bias_out = bias_out.null ? nullptr : bias_out.as<float>();
   a.scale_out = scale_out.null ? nullptr : scale_out.as<float>();
   a.ws = (Workspace*)ws;
+  a.rowmax = a.ws->rowmax;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = row_grid(a.n, a.Lc, sm_count() * 8, &a.per_block);
   if (fold) {
@@ -579,6 +646,88 @@ int fq_quant_weight(const DLTensor* w_, int64_t rows, int bits, const DLTensor* 
   FQ_LAUNCH_CHECK("weight_path_kernel<range>");
   weight_path_kernel<false, 1><<<grid, kThreads, 0, st>>>(a);
   FQ_LAUNCH_CHECK("weight_path_kernel<quantise>");
+  return 0;
+}
+
+int fq_quant_weight_multi(const FqWeightJob* jobs, int n_jobs, const DLTensor* w_out_flat_,
+                          const DLTensor* bias_out_flat_, const DLTensor* scale_out_flat_, void* ws, void* stream) {
+  const char* who = "fq_quant_weight_multi";
+  View wf, bf, sf;
+  FQ_REQUIRE(jobs != nullptr && n_jobs >= 1, "%s: no jobs", who);
+  FQ_REQUIRE(ws != nullptr, "%s: NULL workspace", who);
+  FQ_TRY(view_of(w_out_flat_, "fq_quant_weight_multi: w_out_flat", false, &wf));
+  FQ_TRY(view_of(bias_out_flat_, "fq_quant_weight_multi: bias_out_flat", true, &bf));
+  FQ_TRY(view_of(scale_out_flat_, "fq_quant_weight_multi: scale_out_flat", true, &sf));
+  FQ_REQUIRE(wf.is_f32() && aligned16(wf.data) && (bf.null || bf.is_f32()) && (sf.null || sf.is_f32()),
+             "%s: flat outputs must be float32 (w_out_flat 16-byte aligned)", who);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int budget = sm_count() * 8;
+  int done = 0;
+  while (done < n_jobs) {
+    WeightBatch tb = {};
+    tb.ws = (Workspace*)ws;
+    int blocks = 0, rowmax_used = 0, cnt = 0;
+    bool any_quant = false;
+    for (; done + cnt < n_jobs && cnt < kWeightBatch; ++cnt) {
+      const FqWeightJob& jb = jobs[done + cnt];
+      View w, gamma, beta, mean, var, bias;
+      FQ_TRY(view_of(jb.w, "fq_quant_weight_multi: w", false, &w));
+      FQ_TRY(view_of(jb.gamma, "fq_quant_weight_multi: gamma", true, &gamma));
+      FQ_TRY(view_of(jb.beta, "fq_quant_weight_multi: beta", true, &beta));
+      FQ_TRY(view_of(jb.mean, "fq_quant_weight_multi: mean", true, &mean));
+      FQ_TRY(view_of(jb.var, "fq_quant_weight_multi: var", true, &var));
+      FQ_TRY(view_of(jb.bias, "fq_quant_weight_multi: bias", true, &bias));
+      FQ_REQUIRE(w.is_f32() && w.numel > 0 && aligned16(w.data) && jb.w->ndim >= 1, "%s: job %d: bad weight tensor", who, done + cnt);
+      const int64_t cout = jb.w->shape[0];
+      const bool fold = !gamma.null;
+      FQ_REQUIRE(fold == !beta.null && fold == !mean.null && fold == !var.null, "%s: job %d: gamma, beta, mean and var must be given together", who, done + cnt);
+      if (fold)
+        FQ_REQUIRE(gamma.numel == cout && beta.numel == cout && mean.numel == cout && var.numel == cout &&
+                       (bias.null || bias.numel == cout) && jb.bias_off >= 0 && !bf.null && jb.bias_off + cout <= bf.numel,
+                   "%s: job %d: BN vectors / bias output do not match Cout=%lld", who, done + cnt, (long long)cout);
+      int64_t rows = jb.rows;
+      if (jb.bits > 0) {
+        FQ_REQUIRE(jb.bits >= 2 && jb.bits <= 24 && rows >= 1 && rows <= FQ_MAX_ROWS && cout % rows == 0,
+                   "%s: job %d: bits=%d rows=%lld Cout=%lld", who, done + cnt, jb.bits, (long long)rows, (long long)cout);
+        any_quant = true;
+      } else {
+        FQ_REQUIRE(fold, "%s: job %d: bits <= 0 (fold only) needs the BN vectors", who, done + cnt);
+        rows = 1;
+      }
+      FQ_REQUIRE(jb.w_off >= 0 && jb.w_off % 4 == 0 && jb.w_off + w.numel <= wf.numel, "%s: job %d: bad w_off", who, done + cnt);
+      FQ_REQUIRE(jb.scale_off < 0 || (!sf.null && jb.scale_off + rows <= sf.numel), "%s: job %d: bad scale_off", who, done + cnt);
+      if (rowmax_used + rows > FQ_MAX_ROWS) break;        // next launch
+      WeightJobDev& q = tb.job[cnt];
+      q.w = w.as<const float>();
+      q.gamma = fold ? gamma.as<const float>() : nullptr;
+      q.beta = fold ? beta.as<const float>() : nullptr;
+      q.mean = fold ? mean.as<const float>() : nullptr;
+      q.var = fold ? var.as<const float>() : nullptr;
+      q.bias = bias.null ? nullptr : bias.as<const float>();
+      q.w_out = wf.as<float>() + jb.w_off;
+      q.bias_out = fold ? bf.as<float>() + jb.bias_off : nullptr;
+      q.scale_out = (jb.scale_off >= 0 && jb.bits > 0) ? sf.as<float>() + jb.scale_off : nullptr;
+      q.n = w.numel;
+      q.cout = (int)cout;
+      q.rows = (int)rows;
+      q.bits = jb.bits;
+      q.first_block = blocks;
+      q.rowmax_off = rowmax_used;
+      blocks += row_grid(w.numel, w.numel / cout, budget, &q.per_block);
+      rowmax_used += (int)rows;
+    }
+    FQ_REQUIRE(cnt > 0, "%s: a single job needs more than %d row slots", who, FQ_MAX_ROWS);
+    tb.count = cnt;
+    tb.total_blocks = blocks;
+    weight_multi_kernel<0><<<blocks, kThreads, 0, st>>>(tb);
+    FQ_LAUNCH_CHECK("weight_multi_kernel<range>");
+    if (any_quant) {
+      weight_multi_kernel<1><<<blocks, kThreads, 0, st>>>(tb);
+      FQ_LAUNCH_CHECK("weight_multi_kernel<quantise>");
+      FQ_CUDA(cudaMemsetAsync(tb.ws->rowmax, 0, sizeof(unsigned int) * rowmax_used, st));
+    }
+    done += cnt;
+  }
   return 0;
 }
 

@@ -180,6 +180,74 @@ def quant_weight(w, rows, bits, gamma=None, beta=None, mean=None, var=None, bias
     return (out, bias_out, scale_out, codes) if codes_dtype is not None else (out, bias_out, scale_out)
 
 
+class WeightPlan:
+    """Cached job table for :func:`quant_weight_multi`: the weights (and BN vectors) of a network are persistent
+    tensors, so their DLTensor structs are built once; per call only the three flat output buffers change.
+
+    ``jobs``: list of dicts with keys w, rows, bits and optionally gamma, beta, mean, var, bias.
+    """
+
+    def __init__(self, jobs):
+        self.n = len(jobs)
+        self.keep = []
+        self.table = (_ffi.FqWeightJob * self.n)()
+        self.w_slices, self.bias_slices, self.scale_slices = [], [], []
+        w_off = b_off = s_off = 0
+        for i, jb in enumerate(jobs):
+            w = jb["w"]
+            fold = jb.get("gamma") is not None
+            rec = self.table[i]
+            for name in ("w", "gamma", "beta", "mean", "var", "bias"):
+                t = jb.get(name)
+                if t is None:
+                    setattr(rec, name, None)
+                else:
+                    arg = dl(_f32(t.detach(), name))
+                    self.keep.append((arg, t))
+                    setattr(rec, name, _ffi._c.pointer(arg.t))
+            bits = int(jb["bits"])
+            rows = int(jb["rows"]) if bits > 0 else 1
+            rec.rows, rec.bits = rows, bits
+            rec.w_off = w_off
+            self.w_slices.append((w_off, w.numel(), tuple(w.shape)))
+            w_off += (w.numel() + 3) // 4 * 4
+            if fold:
+                rec.bias_off = b_off
+                self.bias_slices.append((b_off, w.shape[0]))
+                b_off += w.shape[0]
+            else:
+                rec.bias_off = -1
+                self.bias_slices.append(None)
+            if bits > 0:
+                rec.scale_off = s_off
+                self.scale_slices.append((s_off, rows))
+                s_off += rows
+            else:
+                rec.scale_off = -1
+                self.scale_slices.append(None)
+        self.w_total, self.bias_total, self.scale_total = w_off, b_off, s_off
+        self.device = jobs[0]["w"].device
+        self.ptrs = tuple(jb["w"].data_ptr() for jb in jobs)
+
+    def valid_for(self, jobs):
+        return len(jobs) == self.n and all(jb["w"].data_ptr() == p for jb, p in zip(jobs, self.ptrs))
+
+
+def quant_weight_multi(plan):
+    """Run every job of ``plan`` (two launches per 30 jobs).  Returns lists (w_q, bias_folded or None, scales or
+    None), views into three freshly allocated flat buffers; results equal :func:`quant_weight` per block."""
+    dev = plan.device
+    w_flat = torch.empty(plan.w_total, dtype=torch.float32, device=dev)
+    b_flat = torch.empty(max(plan.bias_total, 1), dtype=torch.float32, device=dev)
+    s_flat = torch.empty(max(plan.scale_total, 1), dtype=torch.float32, device=dev)
+    wf, bf, sf = dl(w_flat), dl(b_flat), dl(s_flat)
+    check_call(_lib().fq_quant_weight_multi(plan.table, plan.n, wf.ptr, bf.ptr, sf.ptr, workspace(dev), current_stream()))
+    ws = [w_flat[o:o + n].view(shape) for o, n, shape in plan.w_slices]
+    bs = [None if sl is None else b_flat[sl[0]:sl[0] + sl[1]] for sl in plan.bias_slices]
+    ss = [None if sl is None else s_flat[sl[0]:sl[0] + sl[1]] for sl in plan.scale_slices]
+    return ws, bs, ss
+
+
 # ---- K3 ------------------------------------------------------------------------------------------
 def ste_backward(dy, x=None, qparams=None, mode=STE_IDENTITY):
     """ste_func.py:43-44.  Identity aliases dy (zero bytes moved); the clip mask is an extension."""

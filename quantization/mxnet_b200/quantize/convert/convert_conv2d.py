@@ -143,6 +143,107 @@ class _WeightPath(torch.autograd.Function):
         return dweight, dbias, dgamma, dbeta, None, None, None, None
 
 
+class _MultiWeightPath(torch.autograd.Function):
+    """The weight paths of every converted block in one launch per phase (ops.quant_weight_multi).
+    Inputs per job: (weight, bias, gamma, beta) with None where absent; outputs per job: w_q (+ folded bias).
+    Backward = _WeightPath.backward applied job by job."""
+
+    @staticmethod
+    def forward(ctx, plan, jobs, *tensors):
+        ws, bs, _ = ops.quant_weight_multi(plan)
+        ctx.jobs = jobs
+        ctx.tensors = tensors
+        outs = []
+        for i, jb in enumerate(jobs):
+            outs.append(ws[i])
+            if jb.get("gamma") is not None:
+                outs.append(bs[i])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        out = [None, None]
+        g = iter(grads)
+        for jb in ctx.jobs:
+            dwq = next(g)
+            if jb.get("gamma") is None:
+                out.extend([dwq, None, None, None])
+                continue
+            dbq = next(g)
+            weight, gamma, mean, var = jb["w"], jb["gamma"], jb["mean"], jb["var"]
+            bias = jb.get("bias")
+            cout = weight.shape[0]
+            sd = torch.sqrt(var + 1e-10)
+            dweight = dgamma = dbias = dbeta = None
+            if dwq is not None:
+                da = dwq.reshape(cout, -1) / sd.reshape(-1, 1)
+                dweight = (da * gamma.reshape(-1, 1)).reshape(weight.shape)
+                dgamma = (da * weight.reshape(cout, -1)).sum(dim=1)
+            if dbq is not None:
+                dn = dbq / sd
+                b = bias if bias is not None else torch.zeros_like(gamma)
+                dgamma = dn * (b - mean) if dgamma is None else dgamma + dn * (b - mean)
+                dbias = dn * gamma if bias is not None else None
+                dbeta = dbq
+            out.extend([dweight, dbias, dgamma, dbeta])
+        return tuple(out)
+
+
+def prequantize_weights(net, blocks):
+    """Net-level forward pre-hook body: run the weight path of every block that needs one in this forward as a
+    single multi-tensor launch and hand each block its result through ``_fq_pre``."""
+    jobs, owners = [], []
+    for m in blocks:
+        qa = m.quantize_args
+        if isinstance(m, nn.Conv2d):
+            if m.fixed_params == 1:
+                continue
+            fold = qa.fake_bn
+            if m.enable_quantize:
+                if qa.wino_quantize != 'none' and qa.quant_type == 'channel' and tuple(m.kernel_size) == (3, 3):
+                    continue                  # the per-block path raises the NotImplementedError
+                bits, rows = qa.wt_width, _weight_rows(m)
+            elif fold:
+                bits, rows = 0, 1
+            else:
+                continue
+            jb = {"w": m.weight, "rows": rows, "bits": bits}
+            if fold:
+                jb.update(gamma=m.gamma, beta=m.beta, mean=m.running_mean, var=m.running_var, bias=m.bias)
+        elif isinstance(m, nn.Linear):
+            if not m.enable_quantize:
+                continue
+            jb = {"w": m.weight, "rows": m.out_features if qa.quant_type == 'channel' else 1, "bits": qa.wt_width}
+        else:
+            continue
+        if not m.weight.is_cuda:
+            return
+        jobs.append(jb)
+        owners.append(m)
+    if len(jobs) < 2:
+        return                                # nothing to batch: the per-block path is just as good
+    key = tuple((id(m), jb["bits"], jb["rows"], jb.get("gamma") is not None, jb["w"].data_ptr())
+                for m, jb in zip(owners, jobs))
+    plan = getattr(net, "_fq_weight_plan", None)
+    if plan is None or plan[0] != key:
+        plan = (key, ops.WeightPlan(jobs))
+        net._fq_weight_plan = plan
+    needs_grad = torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for jb in jobs for t in (jb["w"], jb.get("gamma"), jb.get("beta"), jb.get("bias")))
+    if needs_grad:
+        flat = []
+        for jb in jobs:
+            flat.extend([jb["w"], jb.get("bias") if jb.get("gamma") is not None else None, jb.get("gamma"), jb.get("beta")])
+        outs = iter(_MultiWeightPath.apply(plan[1], jobs, *flat))
+        for m, jb in zip(owners, jobs):
+            wq = next(outs)
+            m._fq_pre = (wq, next(outs) if jb.get("gamma") is not None else None)
+    else:
+        ws, bs, _ = ops.quant_weight_multi(plan[1])
+        for i, m in enumerate(owners):
+            m._fq_pre = (ws[i], bs[i])
+
+
 def _weight_rows(m):
     qt = m.quantize_args.quant_type
     if qt == 'channel':
@@ -168,7 +269,10 @@ def _conv2d_forward(self, x):
             else:       # the range is still tracked (convert_conv2d.py:56)
                 _range_only(x.detach(), self)
         # Simulate quantization for weight (:69-97)
-        if self.fixed_params != 1:
+        pre = self.__dict__.pop("_fq_pre", None)       # set by the net-level multi-tensor launch, used once
+        if pre is not None:
+            weight_q, bias = pre[0], (pre[1] if fold else bias)
+        elif self.fixed_params != 1:
             if fold:
                 weight_q, bias = _weight_path(weight, bias, self.gamma, self.beta, self.running_mean,
                                               self.running_var, _weight_rows(self), qa.wt_width)
@@ -177,7 +281,10 @@ def _conv2d_forward(self, x):
         else:
             weight_q = weight
     else:
-        if fold:       # fold only (:47-51 runs even when quantisation is disabled)
+        pre = self.__dict__.pop("_fq_pre", None)
+        if pre is not None:
+            weight_q, bias = pre
+        elif fold:       # fold only (:47-51 runs even when quantisation is disabled)
             weight_q, bias = _weight_path(weight, bias, self.gamma, self.beta, self.running_mean,
                                           self.running_var, 1, 0)
         else:

@@ -28,9 +28,14 @@ def _dense_forward(self, x):
                 x = _input_path(x, self, ops.LO_ZERO)
             else:
                 _range_only(x.detach(), self)
-        rows = self.out_features if qa.quant_type == 'channel' else 1
-        weight_q, _ = _weight_path(weight, None, None, None, None, None, rows, qa.wt_width)
+        pre = self.__dict__.pop("_fq_pre", None)       # set by the net-level multi-tensor launch, used once
+        if pre is not None:
+            weight_q = pre[0]
+        else:
+            rows = self.out_features if qa.quant_type == 'channel' else 1
+            weight_q, _ = _weight_path(weight, None, None, None, None, None, rows, qa.wt_width)
     else:
+        self.__dict__.pop("_fq_pre", None)
         weight_q = weight
     return self.origin_forward(x, weight_q, bias)
 

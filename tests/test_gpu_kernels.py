@@ -574,3 +574,35 @@ def test_c_abi_rejects_bad_arguments_with_messages(ops):
         ops.quant_weight(torch.randn(6, 4, device="cuda"), 4, 8)
     # after all those failures the library still works and the workspace is clean
     bits_equal(host(ops.absmax_rows(x, 8)), O.absmax_rows(host(x), 8))
+
+
+def test_quant_weight_multi_equals_per_tensor(ops):
+    """One launch per phase for a whole network's weights == fq_quant_weight block by block, bit for bit."""
+    r = rng(77)
+    shapes = [(32, 3, 3, 3), (32, 1, 3, 3), (64, 32, 1, 1), (10, 64), (256, 256, 3, 3), (16, 16, 1, 1), (96, 1, 3, 3)] * 10
+    jobs = []
+    for i, shp in enumerate(shapes):          # 70 jobs: more than one launch's worth, mixed kinds
+        w = dev((r.standard_normal(shp) * 0.1).astype(F32))
+        kind = i % 4
+        jb = {"w": w, "rows": shp[0] if kind in (0, 2) else 1, "bits": [8, 4, 2, 0][kind]}
+        if kind in (2, 3) and len(shp) == 4:
+            c = shp[0]
+            jb.update(gamma=dev((1 + 0.2 * r.standard_normal(c)).astype(F32)), beta=dev((0.1 * r.standard_normal(c)).astype(F32)),
+                      mean=dev((0.1 * r.standard_normal(c)).astype(F32)), var=dev(np.abs(1 + 0.3 * r.standard_normal(c)).astype(F32)),
+                      bias=dev((0.05 * r.standard_normal(c)).astype(F32)) if i % 8 < 4 else None)
+        elif kind == 3:
+            jb["bits"] = 8
+        jobs.append(jb)
+    plan = ops.WeightPlan(jobs)
+    for _ in range(2):                        # twice: the workspace must come back clean
+        ws, bs, ss = ops.quant_weight_multi(plan)
+        for i, jb in enumerate(jobs):
+            fold = jb.get("gamma") is not None
+            w1, b1, s1 = ops.quant_weight(jb["w"], jb["rows"], jb["bits"], jb.get("gamma"), jb.get("beta"), jb.get("mean"),
+                                          jb.get("var"), jb.get("bias"))
+            assert torch.equal(ws[i], w1), i
+            if fold:
+                assert torch.equal(bs[i], b1), i
+            if jb["bits"] > 0:
+                assert torch.equal(ss[i], s1), i
+    bits_equal(host(ops.absmax_rows(jobs[0]["w"], 1)), O.absmax_rows(host(jobs[0]["w"]), 1))
