@@ -108,7 +108,8 @@ _CONTROL_NAMES = ("update_ema", "collect_quantized_blocks", "quantize_input", "e
 
 
 def _before_net_forward(net, args):
-    prequantize_weights(net, net.collect_quantized_blocks())
+    if getattr(net, "batch_weight_paths", True):           # set to False to force the per-block launches
+        prequantize_weights(net, net.collect_quantized_blocks())
 
 
 def _after_net_forward(net, args, output):

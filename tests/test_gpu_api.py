@@ -407,3 +407,25 @@ def test_export_quantized_int8_weights_and_thresholds(Q):
     want, lo, hi = O.quantize_int8_export(params["w"].cpu().numpy(), -2.0, 2.0)
     assert np.array_equal(qp["w_quantize"].cpu().numpy(), want) and float(qp["w_quantize_max"]) == 2.0
     assert qp["b"] is params["b"]
+
+
+def test_multi_tensor_weight_path_gradients_equal_per_block_path(Q):
+    """QAT through convert_model with fake-BN: the batched weight launch and its chain rule must give the same
+    forward and the same gradients (weight, gamma, beta, bias) as the per-block autograd Functions."""
+    torch.backends.cudnn.deterministic = True
+    results = []
+    for batched in (True, False):
+        net, _ = build(Q, "cifar_resnet20_v1", 10, weight_width=4, quant_type="channel", fake_bn=True)
+        net.batch_weight_paths = batched
+        net.train()
+        x = torch.randn(8, 3, 32, 32, generator=torch.Generator().manual_seed(9)).cuda()
+        out = net(x)
+        out.square().mean().backward()
+        grads = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+        results.append((out.detach().clone(), grads))
+    torch.backends.cudnn.deterministic = False
+    (o1, g1), (o2, g2) = results
+    assert torch.equal(o1, o2)
+    assert set(g1) == set(g2) and any(k.endswith("gamma") for k in g1) and any(k.endswith("beta") for k in g1)
+    for k in g1:
+        torch.testing.assert_close(g1[k], g2[k], rtol=1e-5, atol=1e-8, msg=k)
