@@ -109,11 +109,11 @@ _CONTROL_NAMES = ("update_ema", "collect_quantized_blocks", "quantize_input", "e
 
 def _before_net_forward(net, args):
     if getattr(net, "batch_weight_paths", True):           # set to False to force the per-block launches
-        prequantize_weights(net, net.collect_quantized_blocks())
+        prequantize_weights(net, net._fq_hook_blocks)
 
 
 def _after_net_forward(net, args, output):
-    for m in net.collect_quantized_blocks():      # a block the forward did not reach must not keep a stale result
+    for m in net._fq_hook_blocks:                 # a block the forward did not reach must not keep a stale result
         m.__dict__.pop("_fq_pre", None)
 
 
@@ -141,6 +141,7 @@ def convert_model(net, exclude=[], convert_fn=default_convert_fn, custom_fn={}):
     # multi-tensor launch at the start of every net-level forward instead of ~50 tiny launches spread over it.
     # Weights do not depend on activations, so the results are the same; a block called on its own still
     # takes its per-block path.
+    net._fq_hook_blocks = net.collect_quantized_blocks()   # blocks converted later simply keep their per-block path
     if not getattr(net, "_fq_weight_hooks", False):
         net.register_forward_pre_hook(_before_net_forward)
         net.register_forward_hook(_after_net_forward)
