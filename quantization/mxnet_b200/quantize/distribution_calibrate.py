@@ -51,7 +51,6 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
         state["counts"] = torch.zeros(n_blk, bins + 1, dtype=torch.int64, device=dev)
         state["hist"] = torch.zeros(n_blk, bins + 1, dtype=torch.float32, device=dev)
         state["minmax"] = torch.zeros(n_blk, 2, dtype=torch.float32, device=dev)
-        state["seen_last"] = torch.zeros(1, dtype=torch.int32, device=dev)
         state["seen_hist"] = []
 
     """ Add hooks to quantized blocks """
@@ -108,7 +107,6 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
                 if state:
                     fqdist.sync_counts(state["counts"], group)
                     # hist_collector[m] = last_hist + hist.astype(float32), all blocks in one launch
-                    state["seen_last"].zero_()
                     _accumulate(state, n_batches == 0, bins)
                 n_batches += 1
                 pbar.update(1)
