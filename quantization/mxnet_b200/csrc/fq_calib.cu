@@ -210,6 +210,159 @@ __global__ void __launch_bounds__(kKlThreads) kl_candidate_kernel(const float* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// KL search, 32 candidates per block: the sequential sums become LANE-PARALLEL chains.
+// ---------------------------------------------------------------------------------------------
+// In the block-per-candidate kernel above, 40 % of all warp instructions are issued for a single active
+// lane (the three left-to-right sums).  Here a block owns 32 consecutive candidates i0 .. i0+31, lane c of
+// every warp works for candidate i0+c, and the chains of all 32 run in one warp at once: every chain step is
+// one full-width instruction instead of 32 nearly empty ones.  Q (pass 1) and the divergence terms (pass 2)
+// are produced by all eight warps in 32-bin chunks into a double-buffered shared-memory ring
+// [bin][candidate] and consumed by warp 0; each value is computed with exactly the operations of the
+// reference and added in exactly its order, so the results are bit-identical to kl_candidate_kernel.
+constexpr int kKlGroup = 32;
+constexpr int kKlGroupThreads = 256;
+
+template <bool LEGACY>
+__global__ void __launch_bounds__(kKlGroupThreads) kl_group_kernel(const float* __restrict__ hist_all, int n_data,
+                                                                   int levels, int min_bins, int bins,
+                                                                   double* __restrict__ div_all) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const float* __restrict__ hist = hist_all + (int64_t)blockIdx.y * n_data;
+  double* div = div_all + (int64_t)blockIdx.y * bins;
+  double* cand = reinterpret_cast<double*>(smem_raw);                  // [levels][32]
+  double* ring = cand + (size_t)levels * kKlGroup;                     // [2][32 bins][32 candidates]
+  float* H = reinterpret_cast<float*>(ring + 2 * 32 * kKlGroup);       // [n_data]
+  __shared__ double s_tail[kKlGroup], s_prefix[kKlGroup], s_qsum[kKlGroup];
+  __shared__ float s_last[kKlGroup], s_total[kKlGroup];
+  const int tid = threadIdx.x, c = tid & 31, w = tid >> 5;
+  const int i_lo = min_bins + (int)blockIdx.x * kKlGroup;
+  const int i_hi = min(i_lo + kKlGroup - 1, bins - 1);                 // largest candidate of the block
+  const bool valid = i_lo + c < bins;
+  const int i = valid ? i_lo + c : i_hi;                               // spare lanes shadow the last candidate
+
+  for (int j = tid; j < n_data; j += kKlGroupThreads) H[j] = hist[j];
+  __syncthreads();
+
+  // sum(data[i:]) on warp 0 and the first i-1 terms of sum(ref_distribution) on warp 1, lane = candidate;
+  // float32 accumulators under NEP 50, float64 under legacy promotion (distribution_calibrate.py:143-145)
+  if (w == 0) {
+    if (LEGACY) {
+      double acc = 0.0;
+      for (int j = i_lo; j < n_data; ++j) {
+        const double h = (double)H[j];
+        if (j >= i) acc = __dadd_rn(acc, h);
+      }
+      s_tail[c] = acc;
+    } else {
+      float acc = 0.f;
+      for (int j = i_lo; j < n_data; ++j) {
+        const float h = H[j];
+        if (j >= i) acc = __fadd_rn(acc, h);
+      }
+      s_tail[c] = (double)acc;
+    }
+  } else if (w == 1) {
+    if (LEGACY) {
+      double acc = 0.0;
+      for (int j = 0; j < i_hi - 1; ++j) {
+        const double h = (double)H[j];
+        if (j < i - 1) acc = __dadd_rn(acc, h);
+      }
+      s_prefix[c] = acc;
+    } else {
+      float acc = 0.f;
+      for (int j = 0; j < i_hi - 1; ++j) {
+        const float h = H[j];
+        if (j < i - 1) acc = __fadd_rn(acc, h);
+      }
+      s_prefix[c] = (double)acc;
+    }
+  }
+  // level buckets of every candidate: cand[k][c] = sum of hist[j] with floor(j*levels/i_c) == k (:149-152)
+  for (int p = tid; p < levels * kKlGroup; p += kKlGroupThreads) {
+    const int cc = p & 31, k = p >> 5;
+    const int ii = min(i_lo + cc, bins - 1);
+    const int j0 = (int)(((long long)k * ii + levels - 1) / levels);
+    const int j1 = (int)(((long long)(k + 1) * ii + levels - 1) / levels);
+    double acc = 0.0;
+    for (int j = j0; j < j1 && j < ii; ++j) acc = __dadd_rn(acc, (double)H[j]);
+    cand[p] = acc;
+  }
+  __syncthreads();
+  if (w == 0) {
+    if (LEGACY) {
+      const float last = (float)__dadd_rn((double)H[i - 1], s_tail[c]);
+      s_last[c] = last;
+      s_total[c] = (float)__dadd_rn(s_prefix[c], (double)last);
+    } else {
+      const float last = __fadd_rn(H[i - 1], (float)s_tail[c]);
+      s_last[c] = last;
+      s_total[c] = __fadd_rn((float)s_prefix[c], last);
+    }
+  }
+  __syncthreads();
+  const float total = s_total[c], last = s_last[c];
+  const double di = (double)i;
+
+  // Q_j of candidate i (:154-159), exactly as in kl_candidate_kernel
+  auto q_of = [&](int j, float& p) -> double {
+    p = __fdiv_rn(j == i - 1 ? last : H[j], total);
+    const double t = __ddiv_rn((double)((long long)j * levels), di);
+    const int fl = (int)t;
+    int ce = (int)ceil(t);
+    ce = ce > levels - 1 ? levels - 1 : ce;
+    const double cf = cand[fl * kKlGroup + c], cc2 = cand[ce * kKlGroup + c];
+    double q = __dadd_rn(__dmul_rn(__dsub_rn(cc2, cf), __dsub_rn(t, (double)fl)), cf);
+    return __dmul_rn(q, (p != 0.f) ? 1.0 : 0.0);
+  };
+
+  const int n_chunks = (i_hi + 31) / 32;          // bins 0 .. i_hi-1
+  for (int pass = 0; pass < 2; ++pass) {
+    const double qsum = pass ? s_qsum[c] : 0.0;
+    double acc = 0.0;                              // warp 0: the running left-to-right sum of candidate i
+    for (int ch = 0; ch <= n_chunks; ++ch) {
+      if (ch < n_chunks) {                         // produce chunk ch
+        double* buf = ring + (size_t)(ch & 1) * 32 * kKlGroup;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int jj = w + 8 * r, j = ch * 32 + jj;
+          double v = 0.0;
+          if (j < i) {
+            float p;
+            const double q = q_of(j, p);
+            if (pass == 0) {
+              v = q;
+            } else {                               // entries with Q == 0 are dropped (:164-165)
+              const double qn = __ddiv_rn(q, qsum);
+              if (qn != 0.0) {
+                const double pd = (double)p;
+                v = __dmul_rn(pd, log(__ddiv_rn(pd, qn)));
+              }
+            }
+          }
+          buf[jj * kKlGroup + c] = v;
+        }
+      }
+      if (w == 0 && ch > 0) {                      // consume chunk ch-1 (written before the last barrier)
+        const double* buf = ring + (size_t)((ch - 1) & 1) * 32 * kKlGroup;
+        const int jbase = (ch - 1) * 32;
+#pragma unroll 8
+        for (int jj = 0; jj < 32; ++jj) {
+          const double v = buf[jj * kKlGroup + c];
+          if (jbase + jj < i) acc = __dadd_rn(acc, v);
+        }
+      }
+      __syncthreads();
+    }
+    if (w == 0) {
+      if (pass == 0) s_qsum[c] = acc;
+      else if (valid) div[i] = acc;
+    }
+    __syncthreads();
+  }
+}
+
 // first strict minimum, NaN never wins (:167-169)
 __global__ void kl_argmin_kernel(const double* __restrict__ div_all, int min_bins, int bins, int* __restrict__ best) {
   __shared__ double sv[kThreads];
@@ -383,7 +536,14 @@ int fq_kl_search(const DLTensor* hist_, int levels, int min_bins, int bins, int 
   if (layers == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int ncand = bins - min_bins;
-  if (ncand > 0) {
+  const size_t group_smem = sizeof(double) * ((size_t)levels * kKlGroup + 2 * 32 * kKlGroup) + sizeof(float) * (n_data + 4);
+  if (ncand > 0 && group_smem <= 200 * 1024) {
+    auto kern = (promotion == FQ_PROMOTION_LEGACY) ? kl_group_kernel<true> : kl_group_kernel<false>;
+    FQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem));
+    kern<<<dim3((ncand + kKlGroup - 1) / kKlGroup, layers), kKlGroupThreads, group_smem, st>>>(
+        hist.as<const float>(), n_data, levels, min_bins, bins, dv.as<double>());
+    FQ_LAUNCH_CHECK("kl_group_kernel");
+  } else if (ncand > 0) {        // very many levels: one block per candidate
     const size_t smem = sizeof(double) * (levels + bins);
     auto kern = (promotion == FQ_PROMOTION_LEGACY) ? kl_candidate_kernel<true> : kl_candidate_kernel<false>;
     FQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
