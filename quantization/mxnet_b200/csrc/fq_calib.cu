@@ -220,8 +220,28 @@ __global__ void __launch_bounds__(kKlThreads) kl_candidate_kernel(const float* _
 // are produced by all eight warps in 32-bin chunks into a double-buffered shared-memory ring
 // [bin][candidate] and consumed by warp 0; each value is computed with exactly the operations of the
 // reference and added in exactly its order, so the results are bit-identical to kl_candidate_kernel.
+// Correctly rounded a / b with a reciprocal that is computed once: y = RN(1/b), q0 = RN(a*y),
+// r = a - b*q0 (exact in one FMA), q = RN(q0 + r*y).  With a correctly rounded y and the faithful q0 this is
+// Markstein's correction step and yields RN(a/b) (checked against exact rational arithmetic in
+// tests/test_fast_quotient_math.py, all-ones divisors included); three FMA-class instructions instead of the
+// ~35 of an IEEE double division whose divisor never changes (the candidate size i, the sum of Q).
+struct DDiv {
+  double b, y;
+  __device__ __forceinline__ static DDiv make(double b) {
+    DDiv d;
+    d.b = b;
+    d.y = __drcp_rn(b);
+    return d;
+  }
+  __device__ __forceinline__ double div(double a) const {
+    const double q0 = __dmul_rn(a, y);
+    const double r = __fma_rn(-b, q0, a);
+    return __fma_rn(r, y, q0);
+  }
+};
+
 constexpr int kKlGroup = 32;
-constexpr int kKlGroupThreads = 256;
+constexpr int kKlGroupThreads = 512;      // 16 warps: two resident blocks give 32 warps per SM
 
 template <bool LEGACY>
 __global__ void __launch_bounds__(kKlGroupThreads) kl_group_kernel(const float* __restrict__ hist_all, int n_data,
@@ -303,12 +323,12 @@ __global__ void __launch_bounds__(kKlGroupThreads) kl_group_kernel(const float* 
   }
   __syncthreads();
   const float total = s_total[c], last = s_last[c];
-  const double di = (double)i;
+  const DDiv by_i = DDiv::make((double)i);
 
-  // Q_j of candidate i (:154-159), exactly as in kl_candidate_kernel
+  // Q_j of candidate i (:154-159), the same values as in kl_candidate_kernel
   auto q_of = [&](int j, float& p) -> double {
     p = __fdiv_rn(j == i - 1 ? last : H[j], total);
-    const double t = __ddiv_rn((double)((long long)j * levels), di);
+    const double t = by_i.div((double)((long long)j * levels));
     const int fl = (int)t;
     int ce = (int)ceil(t);
     ce = ce > levels - 1 ? levels - 1 : ce;
@@ -319,14 +339,14 @@ __global__ void __launch_bounds__(kKlGroupThreads) kl_group_kernel(const float* 
 
   const int n_chunks = (i_hi + 31) / 32;          // bins 0 .. i_hi-1
   for (int pass = 0; pass < 2; ++pass) {
-    const double qsum = pass ? s_qsum[c] : 0.0;
+    const DDiv by_qsum = DDiv::make(pass ? s_qsum[c] : 1.0);
     double acc = 0.0;                              // warp 0: the running left-to-right sum of candidate i
     for (int ch = 0; ch <= n_chunks; ++ch) {
       if (ch < n_chunks) {                         // produce chunk ch
         double* buf = ring + (size_t)(ch & 1) * 32 * kKlGroup;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int jj = w + 8 * r, j = ch * 32 + jj;
+        for (int r = 0; r < 32 / (kKlGroupThreads / 32); ++r) {
+          const int jj = w + (kKlGroupThreads / 32) * r, j = ch * 32 + jj;
           double v = 0.0;
           if (j < i) {
             float p;
@@ -334,7 +354,7 @@ __global__ void __launch_bounds__(kKlGroupThreads) kl_group_kernel(const float* 
             if (pass == 0) {
               v = q;
             } else {                               // entries with Q == 0 are dropped (:164-165)
-              const double qn = __ddiv_rn(q, qsum);
+              const double qn = by_qsum.div(q);
               if (qn != 0.0) {
                 const double pd = (double)p;
                 v = __dmul_rn(pd, log(__ddiv_rn(pd, qn)));

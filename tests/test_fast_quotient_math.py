@@ -54,3 +54,33 @@ def test_fast_path_is_taken_almost_always_on_ordinary_data():
     want = O.roundf((O.clip(v, lo, hi) / d).astype(F32))
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert fast.mean() > 0.9995
+
+
+def test_markstein_correction_gives_the_correctly_rounded_double_quotient():
+    """csrc/fq_calib.cu DDiv: y = RN(1/b), q0 = RN(a*y), r = fma(-b, q0, a), q = fma(r, y, q0) must equal a / b.
+    FMA is emulated with exact rational arithmetic (float(Fraction) rounds to nearest even)."""
+    import random
+    import struct
+    from fractions import Fraction as Fr
+
+    def fma(x, y, z):
+        return float(Fr(x) * Fr(y) + Fr(z))
+
+    def ddiv(a, b):
+        y = 1.0 / b
+        q0 = a * y
+        return fma(fma(-b, q0, a), y, q0)
+    rnd = random.Random(3)
+    for levels in (256, 128, 16, 255):                    # t = j * levels / i
+        for i in list(range(2, 120)) + rnd.sample(range(120, 2048), 60):
+            for j in rnd.sample(range(i), min(i, 25)):
+                assert ddiv(float(j * levels), float(i)) == float(j * levels) / float(i)
+    for _ in range(40000):                                # Q_j / sum(Q)
+        b = rnd.uniform(1, 2) * 2.0 ** rnd.randint(-5, 40)
+        a = b * rnd.random() * 2.0 ** -rnd.randint(0, 30)
+        assert ddiv(a, b) == a / b
+    for e in range(-2, 3):                                # divisors whose significand is all ones
+        b = struct.unpack("d", struct.pack("Q", (0x3ff + e) << 52 | 0xfffffffffffff))[0]
+        for _ in range(1500):
+            a = rnd.uniform(0, 4) * b
+            assert ddiv(a, b) == a / b

@@ -606,3 +606,12 @@ def test_quant_weight_multi_equals_per_tensor(ops):
             if jb["bits"] > 0:
                 assert torch.equal(ss[i], s1), i
     bits_equal(host(ops.absmax_rows(jobs[0]["w"], 1)), O.absmax_rows(host(jobs[0]["w"]), 1))
+
+
+def test_kl_search_many_levels_takes_the_block_per_candidate_kernel(ops):
+    """levels = 1024 does not fit the 32-candidate kernel's shared memory: the by-the-book kernel runs."""
+    h = R.kl_hist_cases()["lognormal"]
+    best, div = ops.kl_search(dev(h), 1024, 1024, R.BINS, promotion="nep50")
+    want = O.kl_divergences(h, 1024, 1024, R.BINS, "nep50")
+    assert int(best[0]) == O.kl_calibrate(h, 1024, 1024, R.BINS, "nep50")
+    assert np.isclose(host(div)[0][1024:], want[1024:], rtol=1e-11, atol=1e-13, equal_nan=True).all()
