@@ -281,7 +281,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.allow_tf32 = False          # the framework convolutions stay plain fp32
     torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = not args.no_e2e      # autotune the framework forward of the e2e leg only
     K, W = args.steps, max(args.warmup, 1)
 
     net = build_net(dev)

@@ -71,8 +71,16 @@ def lst(path, out):
         f.write("%-100s %6s %12s %7s %10s\n" % ("kernel", "n", "total_us", "share", "avg_us"))
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("%-100s %6d %12.1f %7.3f %10.1f\n" % (k[:100], v[0], v[1] / 1e3, v[1] / tot, v[1] / v[0] / 1e3))
-        mine = sum(v[1] for k, v in agg.items() if "fq::" in k or k.startswith("fq") or "hist_" in k or "kl_" in k)
-        f.write("\nshare of libfq_b200 kernels: %.3f\n" % (mine / tot))
+        is_mine = lambda k: "fq::" in k or k.startswith("fq") or "hist_" in k or "kl_" in k
+        mine = sum(v[1] for k, v in agg.items() if is_mine(k))
+        f.write("\nshare of libfq_b200 kernels in the whole process: %.3f\n" % (mine / tot))
+        f.write("\n# libfq_b200 kernels only.  bench.py's TIMED region launches nothing else (the torch/cuDNN kernels above\n"
+                "# belong to the untimed set-up that produces the layer inputs), so these are the shares to compare with\n"
+                "# the CUDA-event breakdown in the bench JSON.\n")
+        f.write("%-100s %6s %12s %7s %10s\n" % ("kernel", "n", "total_us", "share", "avg_us"))
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            if is_mine(k):
+                f.write("%-100s %6d %12.1f %7.3f %10.1f\n" % (k[:100], v[0], v[1] / 1e3, v[1] / mine, v[1] / v[0] / 1e3))
 
 
 if __name__ == "__main__":
