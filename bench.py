@@ -41,8 +41,8 @@ def workload_config(n_gpus, extra=None):
         "batch_per_gpu": BATCH, "bins": BINS, "levels": LEVELS, "layers": N_LAYERS,
         "elements_per_step_per_gpu": ELEMS_PER_IMAGE * BATCH,
         "l2": "inputs (2.56 GB per step) exceed the 126 MB L2; no flush needed",
-        "parallelism": "batch sharded over %d GPU(s); NCCL max-all-reduce of first-batch ranges, sum-all-reduce "
-                       "of the int64 counts once per step" % n_gpus,
+        "parallelism": "batch sharded over %d GPU(s); NCCL max-all-reduce of first-batch ranges, one sum-all-reduce "
+                       "of the int64 counts per 32 steps (float32 adds replayed per step in batch order)" % n_gpus,
     }
     if extra:
         cfg.update(extra)
@@ -268,6 +268,7 @@ def capture_layer_inputs(net, X):
 def run_b200(args):
     import torch
     import torch.distributed as dist
+    from quantization.mxnet_b200 import dist as fqdist
     from quantization.mxnet_b200 import ops
     from quantization.mxnet_b200.quantize.distribution_calibrate import collect_feature_maps, kl_calibrate_all
 
@@ -293,12 +294,17 @@ def run_b200(args):
     n_elems = sum(a.numel() for a in acts)
     assert len(acts) == N_LAYERS and n_elems == ELEMS_PER_IMAGE * BATCH, (len(acts), n_elems)
 
-    counts = torch.zeros(N_LAYERS, BINS + 1, dtype=torch.int64, device=dev)
     hist = torch.zeros(N_LAYERS, BINS + 1, dtype=torch.float32, device=dev)
+    launches = [0]
+
+    def fold(c, first):
+        ops.hist_accumulate(c.reshape(-1), hist.view(-1), first)
+        launches[0] += 1
+    # integer counts of up to 32 batches share ONE sum-all-reduce; the float32 adds are replayed in batch order
+    ring = fqdist.CountsRing(N_LAYERS, BINS + 1, dev, accumulate=fold, slots=32)
     minmax = torch.zeros(N_LAYERS, 2, dtype=torch.float32, device=dev)
     div = torch.empty(N_LAYERS, BINS, dtype=torch.float64, device=dev)
     thresholds = torch.empty(N_LAYERS, dtype=torch.float32, device=dev)
-    launches = [0]
 
     def step(first, ev=None):
         if first:
@@ -310,15 +316,14 @@ def run_b200(args):
                 minmax[:, 1].copy_(mx)
         if ev is not None:
             ev[0].record()
-        ops.hist_nonzero_multi(acts, minmax, 2, 1, BINS, counts, promotion="nep50")     # 27 layers, one launch
+        ops.hist_nonzero_multi(acts, minmax, 2, 1, BINS, ring.slot(), promotion="nep50")     # 27 layers, one launch
         if ev is not None:
             ev[1].record()
-        if world > 1:
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-        ops.hist_accumulate(counts.view(-1), hist.view(-1), first)
-        launches[0] += 2
+        launches[0] += 1
+        ring.commit()
 
     def kl_close():
+        ring.flush()
         best, _ = ops.kl_search(hist[:, :BINS], LEVELS, LEVELS, BINS, promotion="nep50", divergence=div)
         ops.kl_threshold(best, minmax[:, 1].contiguous(), BINS, out=thresholds)
         launches[0] += 3

@@ -173,7 +173,9 @@ FQ_API int fq_hist_nonzero(const DLTensor* x, const DLTensor* max_, int bins, in
  * counts: (u)int64 [n_tensors, bins+1]. */
 FQ_API int fq_hist_nonzero_multi(const DLTensor* const* xs, int n_tensors, const DLTensor* maxes, int max_stride,
                                  int max_offset, int bins, int promotion, const DLTensor* counts, void* stream);
-/* hist = (first ? 0 : hist) + float32(counts); counts <- 0; seen_last[0] |= counts[bins] != 0.  :47,103-104 */
+/* hist = (first ? 0 : hist) + float32(counts); counts <- 0; seen_last[0] |= counts[bins] != 0.  :47,103-104
+ * hist: float32 [n]; counts: (u)int64 [steps, n] (steps >= 1) -- the batches are folded in order, one float32
+ * add per batch as the reference does, so a data-parallel run may all-reduce the counts of many batches at once. */
 FQ_API int fq_hist_accumulate_f32(const DLTensor* counts, const DLTensor* hist, int first,
                            const DLTensor* seen_last, void* stream);
 /* best[l] = first strict arg-min of the KL divergence over i in [min_bins, bins).  :117-171

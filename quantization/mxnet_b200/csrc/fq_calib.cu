@@ -23,34 +23,56 @@ __global__ void ema_kernel(float* __restrict__ state, const float* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // histogram of the clipped non-zero values
 // ---------------------------------------------------------------------------------------------
-// One slice of one tensor into the block-private histogram `sh`, then one atomic per non-empty bin.
-__device__ __forceinline__ void hist_slice(const float* __restrict__ x, int64_t begin, int64_t end, float max_,
-                                           int bins, int promotion, unsigned long long* __restrict__ counts,
-                                           unsigned int* sh, bool vectorised, int64_t n, int64_t stride0,
-                                           int64_t stride) {
-  for (int b = threadIdx.x; b <= bins; b += blockDim.x) sh[b] = 0u;
-  // scales = bins / (max_ + 1e-5)      distribution_calibrate.py:41
-  const float sc = (promotion == FQ_PROMOTION_LEGACY) ? (float)((double)bins / ((double)max_ + 1e-5))
-                                                      : __fdiv_rn((float)bins, __fadd_rn(max_, 1e-5f));
-  __syncthreads();
-  auto one = [&](float v) {
-    v = fminf(fmaxf(v, 0.f), max_);                         // ndarray.clip(0, max_); NaN -> 0 -> ignored
-    // zeros are ignored (:40); 0 < v <= max_ keeps trunc(v * sc) inside [0, bins] (clamped anyway)
-    if (v != 0.f) atomicAdd(&sh[min((unsigned int)__float2int_rz(__fmul_rn(v, sc)), (unsigned int)bins)], 1u);
-  };
-  if (vectorised) {
-    for_range<false, false>(
-        x, begin, end,
-        [&](int64_t, float4 v) {
-          one(v.x);
-          one(v.y);
-          one(v.z);
-          one(v.w);
-        },
-        [&](int64_t, float v) { one(v); });
-  } else {
-    for (int64_t i = stride0; i < n; i += stride) one(x[i]);
+// Block-private histogram `sh` (bins + 1 counters + one trash counter per warp), then one global atomic per
+// non-empty bin.
+//
+// Per element: `setp v > 0` (NaN and -0.0 fail: zeros are dropped, :40), `min(v, max_)` (the upper half of
+// ndarray.clip(0, max_), :39), `mul`, `cvt.rzi.u32`, a memory-safety clamp to `bins`, an address LEA, a SELECT
+// that sends dropped elements to the warp's trash counter, and one unconditional `red.shared.add.u32` (ptxas:
+// ATOMS.POPC.INC, lanes with the same address are merged) -- 8 instructions of straight-line code.  The C++ form
+// (`if (v != 0) atomicAdd`) compiled to a divergent branch with its BSSY/BSYNC pair and a rematerialised shared
+// base per element (14.7 instructions per element, issue slots 70 % busy); a predicated `red` is turned into
+// the same branch by ptxas.
+// 0 < v <= max_ keeps trunc(v * sc) inside [0, bins]: fl(bins / (max_ + 1e-5)) * max_ <= bins (1 + 2^-23).
+struct HistBins {
+  float max_, sc;
+  unsigned int bins, base, trash;
+  __device__ __forceinline__ void init(unsigned int* sh, float max_in, int bins_in, int promotion) {
+    max_ = max_in;
+    bins = (unsigned int)bins_in;
+    // scales = bins / (max_ + 1e-5)      distribution_calibrate.py:41
+    sc = (promotion == FQ_PROMOTION_LEGACY) ? (float)((double)bins_in / ((double)max_in + 1e-5))
+                                            : __fdiv_rn((float)bins_in, __fadd_rn(max_in, 1e-5f));
+    base = (unsigned int)__cvta_generic_to_shared(sh);
+    trash = base + (bins + 1u + (threadIdx.x >> 5)) * 4u;
   }
+  __device__ __forceinline__ void add(float v) const {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .f32 t;\n\t.reg .u32 q;\n\t"
+        "setp.gt.f32 p, %0, 0f00000000;\n\t"
+        "min.f32 t, %0, %1;\n\t"
+        "mul.rn.f32 t, t, %2;\n\t"
+        "cvt.rzi.u32.f32 q, t;\n\t"
+        "min.u32 q, q, %3;\n\t"
+        "shl.b32 q, q, 2;\n\t"
+        "add.u32 q, q, %4;\n\t"
+        "selp.u32 q, q, %5, p;\n\t"
+        "red.shared.add.u32 [q], 1;\n\t}" ::"f"(v), "f"(max_), "f"(sc), "r"(bins), "r"(base), "r"(trash)
+        : "memory");
+  }
+  __device__ __forceinline__ void add4(float4 v) const {
+    add(v.x);
+    add(v.y);
+    add(v.z);
+    add(v.w);
+  }
+};
+
+__device__ __forceinline__ void hist_zero(unsigned int* sh, int bins) {
+  for (int b = threadIdx.x; b < bins + 1 + 32; b += blockDim.x) sh[b] = 0u;
+  __syncthreads();
+}
+__device__ __forceinline__ void hist_flush(const unsigned int* sh, int bins, unsigned long long* __restrict__ counts) {
   __syncthreads();
   for (int b = threadIdx.x; b <= bins; b += blockDim.x) {
     const unsigned int c = sh[b];
@@ -58,45 +80,94 @@ __device__ __forceinline__ void hist_slice(const float* __restrict__ x, int64_t 
   }
 }
 
-__global__ void __launch_bounds__(kThreads) hist_kernel(const float* __restrict__ x, int64_t n, int64_t per_block,
-                                                        const float* __restrict__ max_dev, int bins, int promotion,
-                                                        unsigned long long* __restrict__ counts, int vectorised) {
-  extern __shared__ unsigned int sh[];     // bins + 1 private counters
-  const int64_t begin = (int64_t)blockIdx.x * per_block;
-  hist_slice(x, begin, min(n, begin + per_block), __ldg(max_dev), bins, promotion, counts, sh, vectorised != 0, n,
-             (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+// Launch shape (tools/hist_probe.py on the 27 layer inputs of config 2, 2.56 GB): 256 threads, 3 blocks per SM,
+// up to 80 registers -- ptxas then keeps 16 independent 16 B loads in flight per thread (the 4-deep tile loop
+// unrolled 4x): 360 us = 7.1 TB/s.  More, smaller blocks (8 per SM at 32 registers: 416 us; 6 per SM: 381 us;
+// 4 per SM: 402 us) or fewer (2 per SM: 426-440 us; one 512/1024-thread block: 414-443 us) are all slower.
+constexpr int kHistThreads = 256;
+constexpr int kHistBlocksPerSM = 3;
+constexpr int kHistTileVec = kHistThreads * kUnroll;        // float4 per tile
+
+// Block j of the nblk blocks of a 16 B aligned tensor: tiles of kHistTileVec float4 go round-robin over the
+// tensor's blocks, so the resident blocks stream one contiguous window of it.
+__device__ __forceinline__ void hist_stream(const float* __restrict__ x, int64_t n, int j, int nblk, const HistBins& hb) {
+  const float4* p4 = reinterpret_cast<const float4*>(x);
+  const int64_t nvec = n >> 2;
+  int64_t v0 = (int64_t)j * kHistTileVec + threadIdx.x;
+  const int64_t step = (int64_t)nblk * kHistTileVec;
+  for (; v0 + (int64_t)(kUnroll - 1) * kHistThreads < nvec; v0 += step) {
+    float4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream(p4 + v0 + u * kHistThreads);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) hb.add4(v[u]);
+  }
+  // the tensor's last, partial tile: only the block whose turn it is still has v0 < nvec
+#pragma unroll 1
+  for (int u = 0; u < kUnroll; ++u) {
+    const int64_t vi = v0 + (int64_t)u * kHistThreads;
+    if (vi < nvec) hb.add4(ld_stream(p4 + vi));
+  }
+  if (j == nblk - 1 && threadIdx.x < (n & 3)) hb.add(x[(nvec << 2) + threadIdx.x]);
 }
 
-// Multi-tensor variant: block -> (tensor, slice) through a table passed by value.
+// Multi-tensor launch: block -> (tensor, block within the tensor) through a table passed by value.
 struct HistBatch {
   const float* x[FQ_MAX_BATCH];
   int64_t n[FQ_MAX_BATCH];
-  int64_t per_block[FQ_MAX_BATCH];
   int first_block[FQ_MAX_BATCH + 1];
   int count;
 };
 
-__global__ void __launch_bounds__(kThreads) hist_multi_kernel(const __grid_constant__ HistBatch tb,
-                                                              const float* __restrict__ maxes, int max_stride,
-                                                              int max_offset, int bins, int promotion,
-                                                              unsigned long long* __restrict__ counts) {
-  extern __shared__ unsigned int sh[];
+__global__ void __launch_bounds__(kHistThreads, kHistBlocksPerSM)
+    hist_multi_kernel(const __grid_constant__ HistBatch tb, const float* __restrict__ maxes, int max_stride,
+                      int max_offset, int bins, int promotion, unsigned long long* __restrict__ counts) {
+  extern __shared__ unsigned int sh[];     // bins + 1 private counters, 32 trash counters
   int t = 0;
   while (t + 1 < tb.count && (int)blockIdx.x >= tb.first_block[t + 1]) ++t;
-  const int64_t begin = (int64_t)((int)blockIdx.x - tb.first_block[t]) * tb.per_block[t];
-  hist_slice(tb.x[t], begin, min(tb.n[t], begin + tb.per_block[t]), __ldg(maxes + (int64_t)t * max_stride + max_offset),
-             bins, promotion, counts + (int64_t)t * (bins + 1), sh, true, 0, 0, 0);
+  const float max_ = __ldg(maxes + (int64_t)t * max_stride + max_offset);
+  HistBins hb;
+  hb.init(sh, max_, bins, promotion);
+  hist_zero(sh, bins);
+  // the reference asserts max_ > 0 (:36); with max_ <= 0 everything would clip to <= 0 and be dropped
+  if (max_ > 0.f)
+    hist_stream(tb.x[t], tb.n[t], (int)blockIdx.x - tb.first_block[t], tb.first_block[t + 1] - tb.first_block[t], hb);
+  hist_flush(sh, bins, counts + (int64_t)t * (bins + 1));
 }
 
+// Any alignment: grid-stride scalar loads (views at odd offsets; never the hot path).
+__global__ void __launch_bounds__(kThreads) hist_unaligned_kernel(const float* __restrict__ x, int64_t n,
+                                                                  const float* __restrict__ max_dev, int bins,
+                                                                  int promotion, unsigned long long* __restrict__ counts) {
+  extern __shared__ unsigned int sh[];
+  const float max_ = __ldg(max_dev);
+  HistBins hb;
+  hb.init(sh, max_, bins, promotion);
+  hist_zero(sh, bins);
+  if (max_ > 0.f)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      hb.add(x[i]);
+  hist_flush(sh, bins, counts);
+}
+
+// counts holds `steps` consecutive batches ([steps, nb]); they are folded in batch order, so that a data-parallel
+// run may all-reduce the integer counts of many batches at once and still replay the reference's per-batch
+// float32 accumulation exactly.
 __global__ void hist_accumulate_kernel(unsigned long long* __restrict__ counts, float* __restrict__ hist, int nb,
-                                       int first, int* __restrict__ seen_last) {
+                                       int steps, int first, int* __restrict__ seen_last) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
-  const unsigned long long c = counts[b];
-  counts[b] = 0ull;
-  const float f = __ull2float_rn(c);                         // hist.astype("float32")  (:47)
-  hist[b] = first ? f : __fadd_rn(hist[b], f);               // last_hist + hist        (:103-104)
-  if (b == nb - 1 && seen_last != nullptr && c != 0ull) seen_last[0] = 1;
+  float h = first ? 0.f : hist[b];
+  bool any = false;
+  for (int s = 0; s < steps; ++s) {
+    const unsigned long long c = counts[(int64_t)s * nb + b];
+    counts[(int64_t)s * nb + b] = 0ull;
+    const float f = __ull2float_rn(c);                         // hist.astype("float32")  (:47)
+    h = (first && s == 0) ? f : __fadd_rn(h, f);               // last_hist + hist        (:103-104)
+    any |= (c != 0ull);
+  }
+  hist[b] = h;
+  if (b == nb - 1 && seen_last != nullptr && any) seen_last[0] = 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -441,6 +512,25 @@ int fq_ema_update(const DLTensor* state_, const DLTensor* cur_, double momentum,
   return 0;
 }
 
+// Blocks of one launch shared out over its tensors in proportion to their sizes (at least one each; never more
+// than the tensor has tiles).  Fills tb.first_block, returns the grid size.
+static int hist_share_blocks(HistBatch* tb, int budget) {
+  int64_t total = 0;
+  for (int i = 0; i < tb->count; ++i) total += tb->n[i];
+  int blocks = 0;
+  for (int i = 0; i < tb->count; ++i) {
+    tb->first_block[i] = blocks;
+    if (tb->n[i] == 0) continue;
+    int64_t share = (int64_t)((double)budget * (double)tb->n[i] / (double)total);
+    const int64_t tiles = (tb->n[i] + 4LL * kHistTileVec - 1) / (4LL * kHistTileVec);
+    if (share > tiles) share = tiles;
+    if (share < 1) share = 1;
+    blocks += (int)share;
+  }
+  tb->first_block[tb->count] = blocks;
+  return blocks;
+}
+
 int fq_hist_nonzero(const DLTensor* x_, const DLTensor* max__, int bins, int promotion, const DLTensor* counts_,
                     void* stream) {
   View x, mx, counts;
@@ -453,19 +543,23 @@ int fq_hist_nonzero(const DLTensor* x_, const DLTensor* max__, int bins, int pro
              "fq_hist_nonzero: counts must be (u)int64 [bins+1]");
   FQ_REQUIRE(promotion == FQ_PROMOTION_LEGACY || promotion == FQ_PROMOTION_NEP50, "fq_hist_nonzero: bad promotion");
   if (x.numel == 0) return 0;
-  const int vec = aligned16(x.data);
-  int64_t per_block = 0;
-  int grid;
-  if (vec) {
-    grid = slice_grid(x.numel, sm_count() * 8, &per_block);
+  const size_t smem = sizeof(unsigned int) * (bins + 1 + 32);
+  if (aligned16(x.data)) {
+    HistBatch tb = {};
+    tb.x[0] = x.as<const float>();
+    tb.n[0] = x.numel;
+    tb.count = 1;
+    const int blocks = hist_share_blocks(&tb, sm_count() * kHistBlocksPerSM);
+    hist_multi_kernel<<<blocks, kHistThreads, smem, (cudaStream_t)stream>>>(
+        tb, mx.as<const float>(), 1, 0, bins, promotion, counts.as<unsigned long long>());
+    FQ_LAUNCH_CHECK("hist_multi_kernel");
   } else {
     const int64_t b = (x.numel + kThreads - 1) / kThreads;
-    grid = (int)(b > sm_count() * 8 ? sm_count() * 8 : b);
+    const int grid = (int)(b > sm_count() * 8 ? sm_count() * 8 : b);
+    hist_unaligned_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
+        x.as<const float>(), x.numel, mx.as<const float>(), bins, promotion, counts.as<unsigned long long>());
+    FQ_LAUNCH_CHECK("hist_unaligned_kernel");
   }
-  hist_kernel<<<grid, kThreads, sizeof(unsigned int) * (bins + 1), (cudaStream_t)stream>>>(
-      x.as<const float>(), x.numel, per_block, mx.as<const float>(), bins, promotion,
-      counts.as<unsigned long long>(), vec);
-  FQ_LAUNCH_CHECK("hist_kernel");
   return 0;
 }
 
@@ -484,34 +578,21 @@ int fq_hist_nonzero_multi(const DLTensor* const* xs, int n_tensors, const DLTens
                  counts.numel == (int64_t)n_tensors * (bins + 1),
              "%s: counts must be (u)int64 [n_tensors, bins+1]", who);
   FQ_REQUIRE(promotion == FQ_PROMOTION_LEGACY || promotion == FQ_PROMOTION_NEP50, "%s: bad promotion", who);
-  const int budget = sm_count() * 8;
+  const int budget = sm_count() * kHistBlocksPerSM;
   for (int base = 0; base < n_tensors; base += FQ_MAX_BATCH) {
     const int cnt = (n_tensors - base < FQ_MAX_BATCH) ? n_tensors - base : FQ_MAX_BATCH;
     HistBatch tb = {};
-    int64_t total = 0;
     for (int i = 0; i < cnt; ++i) {
       View x;
       FQ_TRY(view_of(xs[base + i], "fq_hist_nonzero_multi: x", false, &x));
       FQ_REQUIRE(x.is_f32() && aligned16(x.data), "%s: tensor %d must be float32 and 16-byte aligned", who, base + i);
       tb.x[i] = x.as<const float>();
       tb.n[i] = x.numel;
-      total += x.numel;
     }
-    int blocks = 0;
-    for (int i = 0; i < cnt; ++i) {
-      tb.first_block[i] = blocks;
-      if (tb.n[i] == 0) {
-        tb.per_block[i] = 0;
-        continue;
-      }
-      int share = (int)((double)budget * (double)tb.n[i] / (double)(total > 0 ? total : 1));
-      if (share < 1) share = 1;
-      blocks += slice_grid(tb.n[i], share, &tb.per_block[i]);
-    }
-    tb.first_block[cnt] = blocks;
     tb.count = cnt;
+    const int blocks = hist_share_blocks(&tb, budget);
     if (blocks == 0) continue;
-    hist_multi_kernel<<<blocks, kThreads, sizeof(unsigned int) * (bins + 1), (cudaStream_t)stream>>>(
+    hist_multi_kernel<<<blocks, kHistThreads, sizeof(unsigned int) * (bins + 1 + 32), (cudaStream_t)stream>>>(
         tb, mx.as<const float>() + (int64_t)base * max_stride, max_stride, max_offset, bins, promotion,
         counts.as<unsigned long long>() + (int64_t)base * (bins + 1));
     FQ_LAUNCH_CHECK("hist_multi_kernel");
@@ -526,11 +607,14 @@ int fq_hist_accumulate_f32(const DLTensor* counts_, const DLTensor* hist_, int f
   FQ_TRY(view_of(hist_, "fq_hist_accumulate_f32: hist", false, &hist));
   FQ_TRY(view_of(seen_last_, "fq_hist_accumulate_f32: seen_last", true, &seen));
   FQ_REQUIRE((counts.code == kDLInt || counts.code == kDLUInt) && counts.bits == 64, "fq_hist_accumulate_f32: counts must be (u)int64");
-  FQ_REQUIRE(hist.is_f32() && hist.numel == counts.numel && hist.numel > 0, "fq_hist_accumulate_f32: hist must be float32 like counts");
+  FQ_REQUIRE(hist.is_f32() && hist.numel > 0 && counts.numel >= hist.numel && counts.numel % hist.numel == 0 &&
+                 hist.numel <= INT32_MAX && counts.numel / hist.numel <= INT32_MAX,
+             "fq_hist_accumulate_f32: hist must be float32 [n] and counts [steps, n]");
   FQ_REQUIRE(seen.null || (seen.code == kDLInt && seen.bits == 32 && seen.numel >= 1), "fq_hist_accumulate_f32: seen_last must be int32");
-  const int nb = (int)counts.numel;
+  const int nb = (int)hist.numel;
   hist_accumulate_kernel<<<(nb + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      counts.as<unsigned long long>(), hist.as<float>(), nb, first, seen.null ? nullptr : seen.as<int>());
+      counts.as<unsigned long long>(), hist.as<float>(), nb, (int)(counts.numel / hist.numel), first,
+      seen.null ? nullptr : seen.as<int>());
   FQ_LAUNCH_CHECK("hist_accumulate_kernel");
   return 0;
 }

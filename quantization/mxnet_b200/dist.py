@@ -3,7 +3,7 @@ weights replicated.  Every statistic on this path is a max, an integ
 per-sample maxima, so the collectives below make an N-GPU run reproduce the single-GPU result:
 
   first-batch maxima (KL)      all_reduce(MAX)   [L]          exact
-  per-batch histogram counts   all_reduce(SUM)   [L, bins+1]  exact (int64)
+  per-batch histogram counts   all_reduce(SUM)   [S, L, bins+1]  exact (int64); S batches per collective
   per-sample input maxima      all_gather        [N]          exact; the Kahan mean then runs on every rank
   QAT gradients                all_reduce(SUM)/R one flat fp32 bucket
 
@@ -13,7 +13,7 @@ All messages are tiny (<= 442 KB) except the gradient bucket; they go through to
 import torch
 import torch.distributed as dist
 
-__all__ = ["active_group", "shard_batch", "sync_first_batch_minmax", "sync_counts", "gather_per_sample",
+__all__ = ["active_group", "shard_batch", "sync_first_batch_minmax", "sync_counts", "CountsRing", "gather_per_sample",
            "GradBucket", "broadcast_parameters", "enable_data_parallel", "disable_data_parallel"]
 
 
@@ -60,6 +60,51 @@ def sync_counts(counts, group=None):
     if g is not None:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=g)
     return counts
+
+
+class CountsRing:
+    """Per-batch integer counts of up to ``slots`` batches, all-reduced TOGETHER.
+
+    The reference adds ``float32(counts)`` of one batch after the other (distribution_calibrate.py:47,103-104),
+    so the counts of a global batch must be summed over the ranks before they are folded -- but nothing needs
+    them before the KL search.  Keeping every batch's counts in its own slot and replaying the float32 adds in
+    batch order after ONE collective per ``slots`` batches gives the same bits as an all-reduce per batch, without
+    a latency-bound collective in every step (and one fold launch per ``slots`` batches instead of one per batch).
+
+    ``accumulate(counts_2d [S, n], first)`` is the fold (ops.hist_accumulate on the GPU); ``on_reduced(counts_3d)``
+    sees the global counts before they are folded (deferred 2049th-bin check).
+    """
+
+    def __init__(self, n_layers, n_bins, device, accumulate, group=None, slots=32, on_reduced=None):
+        self.group = active_group(group)
+        self.slots = max(1, int(slots))
+        self.ring = torch.zeros(self.slots, n_layers, n_bins, dtype=torch.int64, device=device)
+        self.used = 0
+        self.flushed = 0
+        self.accumulate = accumulate
+        self.on_reduced = on_reduced
+
+    def slot(self):
+        """[n_layers, n_bins] zeroed counters for the batch being collected."""
+        return self.ring[self.used]
+
+    def commit(self):
+        """The current slot holds a complete batch."""
+        self.used += 1
+        if self.used == self.slots:
+            self.flush()
+
+    def flush(self):
+        if self.used == 0:
+            return
+        part = self.ring[:self.used]
+        if self.group is not None:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
+        if self.on_reduced is not None:
+            self.on_reduced(part)
+        self.accumulate(part.view(self.used, -1), self.flushed == 0)     # zeroes the slots again
+        self.flushed += self.used
+        self.used = 0
 
 
 def gather_per_sample(per_sample, group=None):

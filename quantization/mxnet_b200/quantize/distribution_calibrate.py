@@ -5,8 +5,9 @@ single-threaded NumPy passes and searches the threshold in a pure-Python O(bins^
 forward hook launches one histogram kernel on the activation where it lives (4 B/element, read
 once), per-batch counts of ALL layers are folded into the float32 histograms by one launch, and the
 KL search runs one CUDA block per candidate threshold.  With ``torch.distributed`` initialised the
-batch is sharded across ranks: first-batch maxima are max-all-reduced and the integer counts
-sum-all-reduced once per batch, so every rank ends with bit-identical histograms.
+batch is sharded across ranks: first-batch maxima are max-all-reduced and the integer counts of up to
+``ring_slots`` batches are sum-all-reduced together and then folded in batch order, so every rank ends with
+the bit-identical histograms of a single-GPU run over the global batches.
 
 Reference behaviours kept: the first batch's max is frozen for all later batches (:97-101); zeros
 are ignored (:40); float32 accumulation in batch order (:47,:103-104); the 2049th bin when
@@ -29,7 +30,7 @@ class _Collector(dict):
     order = ()
 
 
-def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", group=None):
+def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", group=None, ring_slots=32):
     """
     Collect feature maps and record discrete histograms.
     :param net: converted torch.nn.Module
@@ -37,6 +38,8 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
         Number of bins to generate discrete histograms.
     :param loader: iterable of (X, y) batches
     :param ctx: torch.device (or None: keep X where it is)
+    :param group, ring_slots: data-parallel runs only -- process group, and how many batches share one
+        sum-all-reduce of the integer counts (results do not depend on it)
     :return: (hist_collector, fm_max_collector) keyed by block, values numpy float32 histogram /
         numpy.float32 max, as in the reference.
     """
@@ -48,10 +51,14 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
     state = {}      # allocated on the first hooked tensor's device
 
     def _alloc(dev):
-        state["counts"] = torch.zeros(n_blk, bins + 1, dtype=torch.int64, device=dev)
         state["hist"] = torch.zeros(n_blk, bins + 1, dtype=torch.float32, device=dev)
         state["minmax"] = torch.zeros(n_blk, 2, dtype=torch.float32, device=dev)
         state["seen_hist"] = []
+        # per-block flag "this batch produced a 2049th bin" (deferred length check), taken from the GLOBAL counts
+        state["ring"] = fqdist.CountsRing(
+            n_blk, bins + 1, dev, group=group, slots=ring_slots,
+            accumulate=lambda c, first: ops.hist_accumulate(c.reshape(-1), state["hist"].view(-1), first, None),
+            on_reduced=lambda c: state["seen_hist"].append((c[:, :, bins] != 0).to(torch.int32)))
 
     """ Add hooks to quantized blocks """
     hooks = []
@@ -71,7 +78,7 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
         elif x.data_ptr() % 16 == 0 and i not in pending:
             pending[i] = x          # histogrammed together with the other layers after the forward
         else:
-            ops.hist_nonzero(x, state["minmax"][i, 1:2], bins, state["counts"][i])
+            ops.hist_nonzero(x, state["minmax"][i, 1:2], bins, state["ring"].slot()[i])
     for blk in quantized_blocks:
         hooks.append(blk.register_forward_hook(_collect))
 
@@ -92,24 +99,26 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
                     fqdist.sync_first_batch_minmax(state["minmax"], group)
                     for i, xs in first_batch.items():
                         for x in xs:
-                            ops.hist_nonzero(x, state["minmax"][i, 1:2], bins, state["counts"][i])
+                            ops.hist_nonzero(x, state["minmax"][i, 1:2], bins, state["ring"].slot()[i])
                     first_batch.clear()
                 if pending:
                     # every layer of the batch in ONE launch, blocks shared out by tensor size
                     order = sorted(pending)
                     if order == list(range(n_blk)):
                         ops.hist_nonzero_multi([pending[i] for i in order], state["minmax"], 2, 1, bins,
-                                               state["counts"])
+                                               state["ring"].slot())
                     else:
                         for i in order:
-                            ops.hist_nonzero(pending[i], state["minmax"][i, 1:2], bins, state["counts"][i])
+                            ops.hist_nonzero(pending[i], state["minmax"][i, 1:2], bins, state["ring"].slot()[i])
                     pending.clear()
                 if state:
-                    fqdist.sync_counts(state["counts"], group)
-                    # hist_collector[m] = last_hist + hist.astype(float32), all blocks in one launch
-                    _accumulate(state, n_batches == 0, bins)
+                    # hist_collector[m] = last_hist + hist.astype(float32), all blocks in one launch; with
+                    # ranks, one sum-all-reduce per `ring_slots` batches and the adds replayed in batch order
+                    state["ring"].commit()
                 n_batches += 1
                 pbar.update(1)
+            if state:
+                state["ring"].flush()
     finally:
         """ Delete hooks """
         for h in hooks:
@@ -122,7 +131,7 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
     # one device->host transfer for everything, then the reference's deferred checks
     hist = state["hist"].cpu().numpy()
     minmax = state["minmax"].cpu().numpy()
-    seen = torch.stack(state["seen_hist"]).cpu().numpy() if state["seen_hist"] else np.zeros((0, n_blk), np.int32)
+    seen = torch.cat(state["seen_hist"]).cpu().numpy() if state["seen_hist"] else np.zeros((0, n_blk), np.int32)
     for i, m in enumerate(quantized_blocks):
         if i not in called:
             continue
@@ -173,15 +182,6 @@ def _prefetch(loader, ctx):
             Xd.record_stream(torch.cuda.current_stream(dev))
         nxt = fetch()           # start the next copy before this batch's forward is queued
         yield Xd
-
-
-def _accumulate(state, first, bins):
-    counts, hist = state["counts"], state["hist"]
-    n_blk = counts.shape[0]
-    # per-block flag "this batch produced a 2049th bin" (deferred length check)
-    state["seen_hist"].append((counts[:, bins] != 0).to(torch.int32))
-    ops.hist_accumulate(counts.view(-1), hist.view(-1), first, None)
-    assert n_blk == hist.shape[0]
 
 
 def kl_calibrate(data, levels, min_bins, bins):

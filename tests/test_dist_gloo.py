@@ -114,3 +114,58 @@ def test_single_process_helpers_are_no_ops():
     c = torch.ones(2, 5, dtype=torch.int64)
     assert fqdist.sync_counts(c) is c
     assert torch.equal(fqdist.gather_per_sample(x[:, 0]), x[:, 0])
+
+
+def _ring_worker(rank, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    from quantization.mxnet_b200 import dist as fqdist
+    try:
+        r = np.random.RandomState(11)
+        n_layers, nb, n_batches = 3, 17, 7
+        # counts large enough that float32(count) rounds: the order of the float32 adds matters
+        per_rank = r.randint(0, 1 << 26, size=(WORLD, n_batches, n_layers, nb)).astype(np.int64)
+        want = np.zeros((n_layers, nb), np.float32)
+        for b in range(n_batches):
+            f = per_rank[:, b].sum(axis=0).astype(np.float32)
+            want = f if b == 0 else want + f
+        for slots in (1, 3, 32):
+            hist = torch.zeros(n_layers * nb)
+            seen = []
+
+            def fold(c, first, hist=hist):
+                # what fq_hist_accumulate_f32 does: one float32 add per batch, in order; counts <- 0
+                for s in range(c.shape[0]):
+                    f = c[s].to(torch.float32)
+                    hist.copy_(f if (first and s == 0) else hist + f)
+                c.zero_()
+            ring = fqdist.CountsRing(n_layers, nb, "cpu", accumulate=fold, slots=slots,
+                                     on_reduced=lambda c: seen.append(c.clone()))
+            for b in range(n_batches):
+                ring.slot().add_(torch.from_numpy(per_rank[rank, b]))
+                ring.commit()
+            ring.flush()
+            assert ring.used == 0 and ring.flushed == n_batches and int(ring.ring.abs().sum()) == 0
+            assert np.array_equal(hist.numpy().reshape(n_layers, nb), want), slots
+            assert np.array_equal(torch.cat(seen).numpy(), per_rank.sum(axis=0))
+        out.put((rank, "ok"))
+    except Exception as e:
+        import traceback
+        out.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_counts_ring_replays_the_per_batch_float32_adds():
+    """One all-reduce per `slots` batches must give the bits of one all-reduce per batch."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ring_worker, args=(r, port, out)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results

@@ -361,6 +361,37 @@ def test_histogram_multi_tensor_equals_single(ops):
     assert int(got.sum()) == sum(int((x != 0).sum()) for x in xs)
 
 
+def test_hist_accumulate_many_batches_in_one_launch_replays_the_adds_in_order(ops):
+    """counts [steps, n]: one float32 add per batch in batch order (distribution_calibrate.py:47,103-104),
+    the same bits as one launch per batch (what a deferred all-reduce of many batches relies on)."""
+    r = np.random.RandomState(3)
+    steps, n = 9, 3 * 2049
+    c = r.randint(0, 1 << 27, size=(steps, n)).astype(np.int64)       # float32(count) rounds
+    c[:, -1] = 0
+    want = np.zeros(n, F32)
+    for s in range(steps):
+        want = c[s].astype(F32) if s == 0 else want + c[s].astype(F32)
+    for first in (True, False):
+        counts = dev(c)
+        hist = torch.full((n,), 5.0, device="cuda")
+        seen = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ops.hist_accumulate(counts.view(-1), hist, first, seen)
+        w = want
+        if not first:
+            w = np.full(n, 5.0, F32)
+            for s in range(steps):
+                w = w + c[s].astype(F32)
+        bits_equal(host(hist), w)
+        assert int(counts.abs().sum()) == 0 and int(seen[0]) == 0
+    counts = dev(c)
+    counts[4, -1] = 7
+    seen = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.hist_accumulate(counts.view(-1), torch.zeros(n, device="cuda"), True, seen)
+    assert int(seen[0]) == 1
+    with pytest.raises(Exception):
+        ops.hist_accumulate(torch.zeros(n + 1, dtype=torch.int64, device="cuda"), torch.zeros(n, device="cuda"), True)
+
+
 _KL = [(n, l) for n, ls in R.KL_LEVELS.items() for l in ls]
 
 
