@@ -152,8 +152,10 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
 
 
 def _prefetch(loader, ctx):
-    """Yield each batch on ``ctx``, copying batch k+1 host->device on a side stream while the network runs
-    on batch k (pinned host memory makes the copy asynchronous)."""
+    """Yield each batch on ``ctx``: batch k+1 is copied host->device on a side stream while the network runs on
+    batch k (pinned host memory makes the copy asynchronous).  Two persistent device buffers are used in turn;
+    before one is overwritten the host waits for the step that read it, which also keeps the host at most two
+    steps ahead of the GPU -- no allocation per batch, no unbounded queue of copies."""
     if ctx is None or torch.device(ctx).type != "cuda":
         for X, _ in loader:
             yield X if ctx is None else X.to(ctx)
@@ -161,27 +163,39 @@ def _prefetch(loader, ctx):
     dev = torch.device(ctx)
     copy_stream = torch.cuda.Stream(device=dev)
     it = iter(loader)
+    bufs, consumed = [None, None], [None, None]
+    fetched = 0
 
     def fetch():
+        nonlocal fetched
         try:
             X, _ = next(it)
         except StopIteration:
             return None
         if X.device == dev:
-            return X, None
+            return X, None, None
+        slot = fetched % 2
+        fetched += 1
+        if consumed[slot] is not None:
+            consumed[slot].synchronize()        # the step that read this buffer two batches ago has finished
+        if bufs[slot] is None or bufs[slot].shape != X.shape or bufs[slot].dtype != X.dtype:
+            bufs[slot] = torch.empty(X.shape, dtype=X.dtype, device=dev)
+            copy_stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(copy_stream):
-            Xd = X.to(dev, non_blocking=True)
+            bufs[slot].copy_(X, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return Xd, ev
+        return bufs[slot], ev, slot
     nxt = fetch()
     while nxt is not None:
-        Xd, ev = nxt
+        Xd, ev, slot = nxt
         if ev is not None:
             torch.cuda.current_stream(dev).wait_event(ev)
-            Xd.record_stream(torch.cuda.current_stream(dev))
         nxt = fetch()           # start the next copy before this batch's forward is queued
         yield Xd
+        if slot is not None:    # the consumer has queued everything that reads Xd
+            consumed[slot] = torch.cuda.Event()
+            consumed[slot].record(torch.cuda.current_stream(dev))
 
 
 def kl_calibrate(data, levels, min_bins, bins):
