@@ -214,6 +214,14 @@ def main():
         line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
+        if "graph_ms_per_step" in extra:
+            # a live CUDA graph that captured NCCL work keeps the communicator busy: destroy_process_group() never
+            # returns (seen on 2 GPUs).  Drop the graph, line the ranks up and leave without the teardown.
+            graph.reset()
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
