@@ -75,6 +75,24 @@ def timed(step, K, W, world):
     return float(t) / K
 
 
+_GRAPHS = []
+
+
+def capture(step, warm=3):
+    """Record `step` as a CUDA graph after `warm` eager iterations on a side stream -> (graph, static result)."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(warm):
+            step()
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        out = step()
+    _GRAPHS.append(graph)
+    return graph, out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, required=True, choices=sorted(CONFIGS))
@@ -116,21 +134,17 @@ def main():
         step()                                                  # caches the quantised weights (fixed_params -> 1)
         t_q = timed(step, args.steps, args.warmup, world)
         if args.graph and world == 1:
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                for _ in range(3):
-                    step()
-            torch.cuda.current_stream().wait_stream(s)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=s):
-                out = step()
+            graph, out = capture(step)
             ref = step()
             graph.replay()
             torch.cuda.synchronize()
             extra["graph_output_equals_eager"] = bool(torch.equal(out, ref))
             extra["graph_ms_per_step"] = timed(graph.replay, args.steps, args.warmup, world)
             extra["graph_images_per_sec"] = batch / (extra["graph_ms_per_step"] * 1e-3)
+        net.disable_quantize()
+        if args.graph and world == 1:
+            graph_f, _ = capture(step)
+            extra["graph_framework_only_ms_per_step"] = timed(graph_f.replay, args.steps, args.warmup, world)
         net.disable_quantize()
         t_f = timed(step, args.steps, args.warmup, world)
     elif cfg["kind"] == "ema_calib":
@@ -184,15 +198,7 @@ def main():
             # layers' launches replay back to back with no Python in between.  With ranks, the NCCL all-gather of
             # the per-sample maxima and the all-reduce of the gradient bucket are captured with the rest.
             try:
-                s = torch.cuda.Stream()
-                s.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(s):
-                    for _ in range(3):
-                        step()
-                torch.cuda.current_stream().wait_stream(s)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=s):
-                    loss_g = step()
+                graph, loss_g = capture(step)
                 graph.replay()
                 torch.cuda.synchronize()
                 extra["graph_loss_finite"] = bool(torch.isfinite(loss_g).item())
@@ -204,6 +210,9 @@ def main():
                 extra["graph_error"] = str(e)[:300]
         net.disable_quantize()
         t_f = timed(step, args.steps, args.warmup, world)
+        if "graph_ms_per_step" in extra:
+            graph_f, _ = capture(step)
+            extra["graph_framework_only_ms_per_step"] = timed(graph_f.replay, args.steps, args.warmup, world)
 
     if rank == 0:
         line = {"config": args.config, "workload": cfg["name"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -217,7 +226,8 @@ def main():
         if "graph_ms_per_step" in extra:
             # a live CUDA graph that captured NCCL work keeps the communicator busy: destroy_process_group() never
             # returns (seen on 2 GPUs).  Drop the graph, line the ranks up and leave without the teardown.
-            graph.reset()
+            for g_ in _GRAPHS:
+                g_.reset()
             torch.cuda.synchronize()
             dist.barrier()
             sys.stdout.flush()

@@ -68,6 +68,25 @@ constexpr int kThreads = 256;
 constexpr int kUnroll = 4;            // independent 16 B loads in flight per thread
 
 #ifdef __CUDACC__
+// Launch `kernel` as a programmatic dependent of the previous kernel in `st` (see pdl_wait below).
+template <class... KArgs, class... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
+#ifdef __CUDACC__
 // ---------------------------------------------------------------------------
 // device side
 // ---------------------------------------------------------------------------
@@ -88,6 +107,14 @@ __device__ __forceinline__ void st_stream(float4* p, float4 v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
+
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_dependent() below may start while the
+// kernel before it in the stream is still running.  It must call pdl_wait() before touching anything that
+// kernel writes (and before writing anything that kernel reads); everything above the wait -- index math, loads
+// of data the earlier kernel only reads -- overlaps with the earlier kernel's tail.  The earlier kernel calls
+// pdl_launch_dependents() as its first instruction.  Both are no-ops under a plain launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // mshadow_op::round == roundf (half away from zero); rintf + tie fix-up, branch free.
 __device__ __forceinline__ float round_half_away(float q) {

@@ -81,6 +81,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads, 6) input_path_kernel(InputArgs a) {
   __shared__ float red[32];
   __shared__ unsigned int s_last;
+  if (MODE == kRangeOnly) pdl_launch_dependents();       // the quantiser behind us may start loading x (fq_common.cuh)
   const int64_t begin = (int64_t)blockIdx.x * a.per_block;
   const int64_t end = min(a.n, begin + a.per_block);
 

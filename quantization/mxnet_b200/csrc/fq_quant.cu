@@ -72,17 +72,24 @@ __global__ void __launch_bounds__(kThreads, 6) forward_scalar_kernel(const float
                                                                      const float* __restrict__ qp_dev,
                                                                      ScalarQuant<CLIP, Code> op, int vectorised,
                                                                      int reverse) {
-  if (qp_dev != nullptr) {
-    op.d = __ldg(qp_dev + FQ_QP_D);
-    op.s = __ldg(qp_dev + FQ_QP_S);
-    op.lo = __ldg(qp_dev + FQ_QP_LO);
-    op.hi = __ldg(qp_dev + FQ_QP_HI);
-  }
-  op.prepare();
+  // As a programmatic dependent of the range kernel (fq_forward_online) this kernel starts while that kernel's
+  // last block is still computing the qparams: the first tile of x -- which the range kernel only reads -- is
+  // loaded before the wait.  L1 may hold this layer's qparams from the previous step: read them past it (.cg).
+  auto read_qparams = [&]() {
+    pdl_wait();
+    if (qp_dev != nullptr) {
+      op.d = __ldcg(qp_dev + FQ_QP_D);
+      op.s = __ldcg(qp_dev + FQ_QP_S);
+      op.lo = __ldcg(qp_dev + FQ_QP_LO);
+      op.hi = __ldcg(qp_dev + FQ_QP_HI);
+    }
+    op.prepare();
+  };
   if (vectorised) {
     const int64_t nvec = n >> 2;
     const float4* p4 = reinterpret_cast<const float4*>(x);
     const int64_t ntiles = (nvec + kTileElems / 4 - 1) / (kTileElems / 4);
+    bool have_qp = false;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int64_t tile = reverse ? (ntiles - 1 - t) : t;
       const int64_t v0 = tile * (kTileElems / 4) + threadIdx.x;
@@ -90,18 +97,28 @@ __global__ void __launch_bounds__(kThreads, 6) forward_scalar_kernel(const float
         float4 v[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream(p4 + v0 + u * kThreads);
+        if (!have_qp) {
+          read_qparams();
+          have_qp = true;
+        }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) op.vec(4 * (v0 + u * kThreads), v[u]);
       } else {
+        if (!have_qp) {
+          read_qparams();
+          have_qp = true;
+        }
         for (int u = 0; u < kUnroll; ++u) {
           const int64_t j = v0 + u * kThreads;
           if (j < nvec) op.vec(4 * j, ld_stream(p4 + j));
         }
       }
     }
+    if (!have_qp) read_qparams();
     const int64_t tail0 = nvec << 2;
     if (blockIdx.x == 0 && threadIdx.x < n - tail0) op.sca(tail0 + threadIdx.x, x[tail0 + threadIdx.x]);
   } else {   // some pointer is not 16 B aligned: plain scalar grid-stride loop
+    read_qparams();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
       op.sca(i, x[i]);
   }
@@ -305,7 +322,7 @@ static int with_code_sink(const char* who, const View& codes, int64_t n, F f) {
 
 static int forward_scalar_impl(const char* who, const DLTensor* x_, const float* qp_dev, float d, float s, float lo,
                                float hi, bool clip, const DLTensor* y_, const DLTensor* codes_, void* stream,
-                               bool reverse = false) {
+                               bool reverse = false, bool dependent = false) {
   View x, y, codes;
   FQ_TRY(view_of(x_, who, false, &x));
   FQ_TRY(view_of(y_, who, false, &y));
@@ -320,7 +337,11 @@ static int forward_scalar_impl(const char* who, const DLTensor* x_, const float*
   cudaStream_t st = (cudaStream_t)stream;
   return with_code_sink(who, codes, n, [&](auto sink) -> int {
     using Code = decltype(sink);
-    if (clip) {
+    if (clip && dependent) {
+      ScalarQuant<true, Code> op{d, s, lo, hi, y.as<float>(), sink, QDiv()};
+      FQ_CUDA(launch_dependent(forward_scalar_kernel<true, Code>, dim3(grid), dim3(kThreads), 0, st, x.as<const float>(), n,
+                               per_block, qp_dev, op, (int)vec, (int)reverse));
+    } else if (clip) {
       ScalarQuant<true, Code> op{d, s, lo, hi, y.as<float>(), sink, QDiv()};
       forward_scalar_kernel<true, Code><<<grid, kThreads, 0, st>>>(x.as<const float>(), n, per_block, qp_dev, op, vec,
                                                                    reverse);
@@ -336,7 +357,8 @@ static int forward_scalar_impl(const char* who, const DLTensor* x_, const float*
 
 int launch_forward_scalar_dev(const DLTensor* x, const float* qp_dev, const DLTensor* y, const DLTensor* codes,
                               bool reverse, void* stream) {
-  return forward_scalar_impl("fq_forward_online", x, qp_dev, 0, 0, 0, 0, true, y, codes, stream, reverse);
+  // launched right behind the range kernel that produces qp_dev: programmatic dependent launch
+  return forward_scalar_impl("fq_forward_online", x, qp_dev, 0, 0, 0, 0, true, y, codes, stream, reverse, true);
 }
 
 }  // namespace fq

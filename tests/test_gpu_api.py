@@ -221,6 +221,29 @@ def test_config2_like_kl_calibration_flow(Q):
         Q.ops.set_promotion("legacy")
 
 
+def test_collect_feature_maps_loader_forms_and_ring_sizes_agree(Q):
+    """Pinned / pageable host batches (double-buffered prefetch), device-resident batches, a ragged last batch
+    and every ring size must give the same histograms bit for bit."""
+    net, _ = build(Q, "cifar_resnet20_v1", 10, quant_type="channel")
+    net.disable_quantize()
+    g = torch.Generator().manual_seed(3)
+    sizes = [8, 8, 8, 8, 8, 5]
+    batches = [torch.randn(n, 3, 32, 32, generator=g) * (1.0 + 0.2 * i) for i, n in enumerate(sizes)]
+    dev = torch.device("cuda")
+    ref_h, ref_m = Q.dc.collect_feature_maps(net, 2048, [(b.cuda(), None) for b in batches], dev, ring_slots=1)
+    blocks = net.collect_quantized_blocks()
+    forms = {"pinned": [(b.pin_memory(), None) for b in batches], "pageable": [(b, None) for b in batches]}
+    for name, loader in forms.items():
+        for slots in (1, 4, 32):
+            h, m = Q.dc.collect_feature_maps(net, 2048, loader, dev, ring_slots=slots)
+            for b in blocks:
+                assert np.array_equal(bits(h[b]), bits(ref_h[b])), (name, slots, b.name)
+                assert m[b] == ref_m[b]
+    # device-side state of the collectors feeds kl_calibrate_all without an upload
+    best = Q.dc.kl_calibrate_all(ref_h, 256, 256, 2048)
+    assert best.shape == (len(blocks),)
+
+
 def test_collect_feature_maps_rejects_negative_activations(Q):
     net, _ = build(Q, "cifar_resnet20_v1", 10)
     net.disable_quantize()

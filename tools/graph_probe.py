@@ -1,5 +1,6 @@
-"""Per-op time of the online input path under CUDA-graph replay (launch-bound regime): the fused cooperative
-kernel vs. the two plain launches (range + quantiser) it can be split into."""
+"""Per-op time of the online input path under CUDA-graph replay (launch-bound regime): fq_forward_online (range
+kernel + quantiser launched as its programmatic dependent) vs. the same two kernels as two plain launches, the
+quantiser alone, and the weight path."""
 import sys
 
 import torch
