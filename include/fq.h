@@ -131,6 +131,19 @@ FQ_API int fq_quant_weight(const DLTensor* w, int64_t rows, int bits, const DLTe
                     const DLTensor* bias_out, const DLTensor* scale_out, const DLTensor* codes,
                     void* ws, void* stream);
 
+/* Winograd-domain per-channel weight fake-quantisation (wino_quantize = "F23" | "F43" | "F63";
+ * convert_conv2d.py:71-83, wino_matrix.py:28-60):
+ *   U = G w G^T per 3x3 kernel;  M_o = max |U[o]|;  s_o = M_o / (2^(bits-1)-1);
+ *   Uq = roundf(U / (s_o + 1e-10f)) * s_o;  w_out = GI Uq GTI.
+ * w, w_out: float32 [Cout, Cin, 3, 3]; G [a, 3], GI = pinv(G) [3, a], GTI = pinv(G^T) [a, 3], float32, a in {4, 6, 8}
+ * (the caller computes the pseudo-inverses, as the reference does with numpy); scale_out: optional [Cout].
+ * Every dot product runs over its contraction index in ascending order as acc = a0*b0, acc = fma(ak, bk, acc). */
+FQ_API int fq_quant_weight_wino(const DLTensor* w, const DLTensor* G, const DLTensor* GI, const DLTensor* GTI, int bits,
+                                const DLTensor* w_out, const DLTensor* scale_out, void* ws, void* stream);
+/* Its straight-through backward: dw = G^T ((GI^T (dwq GTI^T)) G), the four products autograd replays. */
+FQ_API int fq_wino_backward(const DLTensor* dwq, const DLTensor* G, const DLTensor* GI, const DLTensor* GTI,
+                            const DLTensor* dw, void* stream);
+
 /* The weight paths of MANY blocks (a whole network) in one launch per phase: launch-bound nets spend more time
  * launching 50 tiny kernels than running them.  Outputs go to caller-owned flat float32 buffers at the given
  * element offsets (w_off a multiple of 4; bias_off / scale_off < 0 = not wanted), so a cached job table stays

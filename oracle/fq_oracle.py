@@ -208,6 +208,86 @@ def fake_quant_weight(w, bits=8, quant_type="layer", groups=1):
 
 
 # ---------------------------------------------------------------------------
+# Winograd-domain weight quantisation   convert_conv2d.py:71-83 ; wino_matrix.py:28-60
+# ---------------------------------------------------------------------------
+_WINO_G = {
+    "F23": [[1, 0, 0], [1 / 2, 1 / 2, 1 / 2], [1 / 2, -1 / 2, 1 / 2], [0, 0, 1]],
+    "F43": [[1 / 4, 0, 0], [-1 / 6, -1 / 6, -1 / 6], [-1 / 6, 1 / 6, -1 / 6], [1 / 24, 1 / 12, 1 / 6],
+            [1 / 24, -1 / 12, 1 / 6], [0, 0, 1]],
+    "F63": [[1, 0, 0], [-2 / 9, -2 / 9, -2 / 9], [-2 / 9, 2 / 9, -2 / 9], [1 / 90, 1 / 45, 2 / 45],
+            [1 / 90, -1 / 45, 2 / 45], [32 / 45, 16 / 45, 8 / 45], [32 / 45, -16 / 45, 8 / 45], [0, 0, 1]],
+}
+
+
+def winograd_matrices(name):
+    """G as ``nd.array`` makes it (float32), and the float32 pseudo-inverses of G and G.T that the reference
+    computes with ``np.linalg.pinv(G.asnumpy())`` on every forward (convert_conv2d.py:80-82)."""
+    G = np.array(_WINO_G[name], dtype=F32)
+    GI = np.linalg.pinv(G).astype(F32)
+    GTI = np.linalg.pinv(np.ascontiguousarray(G.T)).astype(F32)
+    return G, GI, GTI
+
+
+def _fma32(a, b, c):
+    """float32 fused multiply-add.  The product of two float32 is exact in x87 extended precision (64-bit
+    significand); the sum is rounded once there and once more to float32 -- a double rounding that differs from a
+    true FMA with probability ~2^-39 per operation, far below what the tests can hit."""
+    LD = np.longdouble
+    assert np.finfo(LD).nmant >= 63, "needs x87 extended precision"
+    return (np.asarray(a, F32).astype(LD) * np.asarray(b, F32).astype(LD) + np.asarray(c, F32).astype(LD)).astype(F32)
+
+
+def _dot_chain(pairs):
+    """sum_k a_k * b_k in ascending k as ``acc = a0*b0; acc = fma(a_k, b_k, acc)``.
+
+    PARITY UNPINNED: MXNet's ``nd.dot`` is a BLAS sgemm (contraction length 3 / 4 / 6 / 8 here) whose summation
+    order and FMA use are not defined by MXNet; this chain is the contract the CUDA kernel is held to."""
+    (a0, b0), rest = pairs[0], pairs[1:]
+    acc = (np.asarray(a0, F32) * np.asarray(b0, F32)).astype(F32)
+    for a, b in rest:
+        acc = _fma32(a, b, acc)
+    return acc
+
+
+def wino_transform(w, G):
+    """U = (G w) G^T per 3x3 kernel (:72-73); w: [..., 3, 3] -> [..., a, a]."""
+    w = np.asarray(w, dtype=F32)
+    a = G.shape[0]
+    # (G w)[p][c] = sum_r G[p][r] w[r][c]
+    T = _dot_chain([(G[:, r].reshape(a, 1), w[..., r, :][..., None, :]) for r in range(3)])          # [..., a, 3]
+    # U[p][q] = sum_c (G w)[p][c] G[q][c]
+    return _dot_chain([(T[..., :, c][..., :, None], G[:, c].reshape(1, a)) for c in range(3)])       # [..., a, a]
+
+
+def fake_quant_weight_wino(w, name, bits=8):
+    """convert_conv2d.py:71-83 for quant_type='channel' and a 3x3 kernel -> (w_q, scales [Cout], U, Uq)."""
+    w = np.asarray(w, dtype=F32)
+    assert w.ndim == 4 and w.shape[2:] == (3, 3)
+    G, GI, GTI = winograd_matrices(name)
+    a = G.shape[0]
+    U = wino_transform(w, G)                                    # [Cout, Cin, a, a]
+    s, d, _ = weight_scales(U, w.shape[0], bits)
+    Uq, _ = fake_quant_rows(U, w.shape[0], s, d)
+    # (G+ Uq)[r][q] = sum_p GI[r][p] Uq[p][q]
+    V = _dot_chain([(GI[:, p].reshape(3, 1), Uq[..., p, :][..., None, :]) for p in range(a)])        # [..., 3, a]
+    # w_q[r][c] = sum_q (G+ Uq)[r][q] GTI[q][c]
+    wq = _dot_chain([(V[..., :, q][..., :, None], GTI[q, :].reshape(1, 3)) for q in range(a)])       # [..., 3, 3]
+    return wq, s, U, Uq
+
+
+def wino_backward(dwq, name):
+    """Straight-through backward of the above in the order autograd replays it:
+    dX = dw_q GTI^T ; dUq = GI^T dX ; dT = dU G ; dw = G^T dT."""
+    dwq = np.asarray(dwq, dtype=F32)
+    G, GI, GTI = winograd_matrices(name)
+    a = G.shape[0]
+    dX = _dot_chain([(dwq[..., :, c][..., :, None], GTI[:, c].reshape(1, a)) for c in range(3)])     # [..., 3, a]
+    dU = _dot_chain([(GI[r, :].reshape(a, 1), dX[..., r, :][..., None, :]) for r in range(3)])       # [..., a, a]
+    dT = _dot_chain([(dU[..., :, q][..., :, None], G[q, :].reshape(1, 3)) for q in range(a)])        # [..., a, 3]
+    return _dot_chain([(G[p, :].reshape(3, 1), dT[..., p, :][..., None, :]) for p in range(a)])      # [..., 3, 3]
+
+
+# ---------------------------------------------------------------------------
 # BN fold   convert_conv2d.py:47-51 ; merge_bn.py:65-74
 # ---------------------------------------------------------------------------
 def fold_bn(w, bias, gamma, beta, mean, var):

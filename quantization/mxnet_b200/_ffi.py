@@ -75,6 +75,8 @@ SIGNATURES = {
                                      _c.c_void_p, _c.c_void_p]),
     "fq_quant_weight": (_c.c_int, [P, _c.c_int64, _c.c_int, P, P, P, P, P, P, P, P, P, _c.c_void_p, _c.c_void_p]),
     "fq_quant_weight_multi": (_c.c_int, [_c.POINTER(FqWeightJob), _c.c_int, P, P, P, _c.c_void_p, _c.c_void_p]),
+    "fq_quant_weight_wino": (_c.c_int, [P, P, P, P, _c.c_int, P, P, _c.c_void_p, _c.c_void_p]),
+    "fq_wino_backward": (_c.c_int, [P, P, P, P, P, _c.c_void_p]),
     "fq_ste_backward": (_c.c_int, [P, P, P, P, _c.c_int, _c.c_void_p]),
     "fq_ema_update": (_c.c_int, [P, P, _c.c_double, _c.c_int, _c.c_int, _c.c_void_p]),
     "fq_hist_nonzero": (_c.c_int, [P, P, _c.c_int, _c.c_int, P, _c.c_void_p]),

@@ -180,6 +180,28 @@ def quant_weight(w, rows, bits, gamma=None, beta=None, mean=None, var=None, bias
     return (out, bias_out, scale_out, codes) if codes_dtype is not None else (out, bias_out, scale_out)
 
 
+def quant_weight_wino(w, G, GI, GTI, bits, out=None, scale_out=None):
+    """Winograd-domain per-channel weight fake-quant: U = G w G^T, per-Cout absmax, quantise, back through the
+    pseudo-inverses (convert_conv2d.py:71-83).  Returns (w_q, scales [Cout])."""
+    w = _f32(w, "w")
+    out = torch.empty_like(w) if out is None else out
+    if scale_out is None:
+        scale_out = torch.empty(w.shape[0], dtype=torch.float32, device=w.device)
+    a, g, gi, gti, o, so = dl(w), dl(G), dl(GI), dl(GTI), dl(out), dl(scale_out)
+    check_call(_lib().fq_quant_weight_wino(a.ptr, g.ptr, gi.ptr, gti.ptr, bits, o.ptr, so.ptr, workspace(w.device),
+                                           current_stream()))
+    return out, scale_out
+
+
+def wino_backward(dwq, G, GI, GTI, out=None):
+    """Straight-through backward of :func:`quant_weight_wino`: dw = G^T (GI^T dwq GTI^T) G."""
+    dwq = _f32(dwq, "dwq")
+    out = torch.empty_like(dwq) if out is None else out
+    a, g, gi, gti, o = dl(dwq), dl(G), dl(GI), dl(GTI), dl(out)
+    check_call(_lib().fq_wino_backward(a.ptr, g.ptr, gi.ptr, gti.ptr, o.ptr, current_stream()))
+    return out
+
+
 class WeightPlan:
     """Cached job table for :func:`quant_weight_multi`: the weights (and BN vectors) of a network are persistent
     tensors, so their DLTensor structs are built once; per call only the three flat output buffers change.

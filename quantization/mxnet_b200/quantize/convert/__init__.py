@@ -1,5 +1,5 @@
 """quantize.convert: converter factories, the net-level driver and the fake-quant primitive."""
-from . import convert_act, convert_bn, convert_conv2d, convert_dense, ste_func
+from . import convert_act, convert_bn, convert_conv2d, convert_dense, ste_func, wino_matrix
 from .convert import convert_model, convert_to_relu6, default_convert_fn
 from .convert_act import convert_relu_to_relu6, gen_act_converter
 from .convert_bn import bypass_bn

@@ -13,6 +13,7 @@ import torch
 from torch import nn
 
 from ... import ops
+from .wino_matrix import winograd_matrices
 
 __all__ = ['gen_conv2d_converter']
 
@@ -52,6 +53,44 @@ def _weight_path(weight, bias, gamma, beta, mean, var, rows, bits):
         return _WeightPath.apply(weight, bias, gamma, beta, mean, var, rows, bits)
     wq, bq, _ = ops.quant_weight(weight, rows, bits, gamma, beta, mean, var, bias)
     return wq, (bq if gamma is not None else bias)
+
+
+def _is_wino(m):
+    """convert_conv2d.py:71,80: per-channel quantisation of a 3x3 kernel in the Winograd domain."""
+    qa = m.quantize_args
+    return qa.wino_quantize != 'none' and qa.quant_type == 'channel' and tuple(m.kernel_size) == (3, 3)
+
+
+def _wino_mats(m):
+    """(G, pinv(G), pinv(G.T)) on the weight's device; the pseudo-inverses are the float32 ones NumPy computes on
+    the host, as in the reference (:80-82), and are cached per block."""
+    dev = m.weight.device
+    mats = m.__dict__.get("_fq_wino")
+    if mats is None or mats[0].device != dev:
+        mats = tuple(torch.from_numpy(a).to(dev) for a in winograd_matrices(m.quantize_args.wino_quantize))
+        m._fq_wino = mats
+    return mats
+
+
+class _WinoPath(torch.autograd.Function):
+    """convert_conv2d.py:71-83: G w G^T -> per-channel fake-quant -> G+ . (G^T)+ ; the quantiser is straight
+    through, the four matrix products get their exact adjoints."""
+
+    @staticmethod
+    def forward(ctx, weight, G, GI, GTI, bits):
+        ctx.mats = (G, GI, GTI)
+        return ops.quant_weight_wino(weight, G, GI, GTI, bits)[0]
+
+    @staticmethod
+    def backward(ctx, dwq):
+        return ops.wino_backward(dwq.contiguous(), *ctx.mats), None, None, None, None
+
+
+def _wino_path(weight, m):
+    G, GI, GTI = _wino_mats(m)
+    if torch.is_grad_enabled() and weight.requires_grad:
+        return _WinoPath.apply(weight, G, GI, GTI, m.quantize_args.wt_width)
+    return ops.quant_weight_wino(weight, G, GI, GTI, m.quantize_args.wt_width)[0]
 
 
 class _InputPath(torch.autograd.Function):
@@ -200,8 +239,8 @@ def prequantize_weights(net, blocks):
                 continue
             fold = qa.fake_bn
             if m.enable_quantize:
-                if qa.wino_quantize != 'none' and qa.quant_type == 'channel' and tuple(m.kernel_size) == (3, 3):
-                    continue                  # the per-block path raises the NotImplementedError
+                if _is_wino(m):
+                    continue                  # Winograd-domain blocks take their own per-block path
                 bits, rows = qa.wt_width, _weight_rows(m)
             elif fold:
                 bits, rows = 0, 1
@@ -257,9 +296,6 @@ def _conv2d_forward(self, x):
     qa = self.quantize_args
     weight, bias = self.weight, self.bias
     fold = self.fixed_params != 1 and qa.fake_bn
-    if qa.wino_quantize != 'none' and qa.quant_type == 'channel' and tuple(self.kernel_size) == (3, 3):
-        raise NotImplementedError("Winograd-domain weight quantisation is outside the B200 hot path (SURVEY 8f)")
-
     if self.enable_quantize:
         # Quantize input (convert_conv2d.py:55-66)
         if qa.quantize_input:
@@ -272,6 +308,11 @@ def _conv2d_forward(self, x):
         pre = self.__dict__.pop("_fq_pre", None)       # set by the net-level multi-tensor launch, used once
         if pre is not None:
             weight_q, bias = pre[0], (pre[1] if fold else bias)
+        elif self.fixed_params != 1 and _is_wino(self):
+            if fold:        # :47-51 first, then the Winograd-domain quantiser on the folded weight
+                weight, bias = _weight_path(weight, bias, self.gamma, self.beta, self.running_mean,
+                                            self.running_var, 1, 0)
+            weight_q = _wino_path(weight, self)
         elif self.fixed_params != 1:
             if fold:
                 weight_q, bias = _weight_path(weight, bias, self.gamma, self.beta, self.running_mean,

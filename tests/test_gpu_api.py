@@ -452,3 +452,56 @@ def test_multi_tensor_weight_path_gradients_equal_per_block_path(Q):
     assert set(g1) == set(g2) and any(k.endswith("gamma") for k in g1) and any(k.endswith("beta") for k in g1)
     for k in g1:
         torch.testing.assert_close(g1[k], g2[k], rtol=1e-5, atol=1e-8, msg=k)
+
+
+@pytest.mark.parametrize("fake_bn", [False, True])
+def test_winograd_domain_weight_quantisation_through_the_converter(Q, fake_bn):
+    """gen_conv2d_converter(quant_type='channel', wino_quantize='F43'): 3x3 kernels are quantised in the Winograd
+    domain (convert_conv2d.py:71-83), 1x1 kernels per channel as usual; gradients reach the weights."""
+    torch.manual_seed(5)
+    net = nn.Sequential(nn.Conv2d(3, 8, 3, padding=1), nn.ReLU(), nn.Conv2d(8, 8, 1), nn.ReLU(),
+                        nn.Conv2d(8, 4, 3, padding=1, groups=2)).cuda()
+    conv = Q.convert.gen_conv2d_converter(quant_type="channel", wino_quantize="F43", quantize_input=False,
+                                          fake_bn=fake_bn)
+    Q.convert.convert_model(net, convert_fn={nn.Conv2d: conv, nn.ReLU: None})
+    if fake_bn:
+        g = torch.Generator().manual_seed(1)
+        for m in net:
+            if isinstance(m, nn.Conv2d):
+                m.gamma.data.copy_(1 + 0.1 * torch.randn(m.out_channels, generator=g))
+                m.beta.data.copy_(0.1 * torch.randn(m.out_channels, generator=g))
+                m.running_mean.data.copy_(0.1 * torch.randn(m.out_channels, generator=g))
+                m.running_var.data.copy_(1 + 0.2 * torch.rand(m.out_channels, generator=g))
+    seen = {}
+    for i, m in enumerate(net):
+        if isinstance(m, nn.Conv2d):
+            orig = m.origin_forward
+            m.origin_forward = (lambda x, w, b, _i=i, _o=orig: (seen.__setitem__(_i, (w.detach().cpu().numpy(),
+                                None if b is None else b.detach().cpu().numpy())), _o(x, w, b))[1])
+    x = torch.randn(2, 3, 8, 8, device="cuda")
+    y = net(x)
+    for i, m in enumerate(net):
+        if not isinstance(m, nn.Conv2d):
+            continue
+        w = m.weight.detach().cpu().numpy()
+        b = None if m.bias is None else m.bias.detach().cpu().numpy()
+        if fake_bn:
+            w, b = O.fold_bn(w, b, m.gamma.detach().cpu().numpy(), m.beta.detach().cpu().numpy(),
+                             m.running_mean.detach().cpu().numpy(), m.running_var.detach().cpu().numpy())
+        if tuple(m.kernel_size) == (3, 3):
+            want = O.fake_quant_weight_wino(w, "F43", 8)[0]
+        else:
+            want = O.fake_quant_weight(w, 8, "channel")[0]
+        assert np.array_equal(bits(seen[i][0]), bits(want)), i
+        if fake_bn:
+            assert np.array_equal(bits(seen[i][1]), bits(b)), i
+    y.sum().backward()
+    for m in net:
+        if isinstance(m, nn.Conv2d):
+            assert m.weight.grad is not None and torch.isfinite(m.weight.grad).all() and float(m.weight.grad.abs().sum()) > 0
+    # fix_params caches the Winograd-quantised weights like any others (:101-105)
+    net.fix_params()
+    with torch.no_grad():
+        y2 = net(x)
+        y3 = net(x)
+    assert torch.equal(y2, y3) and all(m.fixed_params == 1 for m in net if isinstance(m, nn.Conv2d))

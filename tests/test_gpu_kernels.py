@@ -646,3 +646,45 @@ def test_kl_search_many_levels_takes_the_block_per_candidate_kernel(ops):
     want = O.kl_divergences(h, 1024, 1024, R.BINS, "nep50")
     assert int(best[0]) == O.kl_calibrate(h, 1024, 1024, R.BINS, "nep50")
     assert np.isclose(host(div)[0][1024:], want[1024:], rtol=1e-11, atol=1e-13, equal_nan=True).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# Winograd-domain weight quantisation (convert_conv2d.py:71-83)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["F23", "F43", "F63"])
+@pytest.mark.parametrize("shape,bits", [((16, 16, 3, 3), 8), ((7, 5, 3, 3), 8), ((64, 1, 3, 3), 4), ((40, 33, 3, 3), 2),
+                                        ((256, 128, 3, 3), 8)])
+def test_wino_weight_quant_matches_oracle(ops, name, shape, bits):
+    w = (rng(shape[0] * 13 + shape[1]).standard_normal(shape) * 0.1).astype(F32)
+    w[0, 0] = 0                                # an all-zero kernel
+    G, GI, GTI = O.winograd_matrices(name)
+    want, want_s, _, _ = O.fake_quant_weight_wino(w, name, bits)
+    got, got_s = ops.quant_weight_wino(dev(w), dev(G), dev(GI), dev(GTI), bits)
+    bits_equal(host(got_s), want_s)
+    bits_equal(host(got), want)
+    # the workspace is restored: a second call gives the same answer
+    got2, _ = ops.quant_weight_wino(dev(w), dev(G), dev(GI), dev(GTI), bits)
+    bits_equal(host(got2), want)
+    # and the plain weight path still works on the same workspace
+    wq, _, sc = ops.quant_weight(dev(w), shape[0], bits)
+    y, _, s = O.fake_quant_weight(w, bits, "channel")
+    bits_equal(host(wq), y)
+
+
+def test_wino_all_zero_weight_and_errors(ops):
+    G, GI, GTI = (dev(m) for m in O.winograd_matrices("F43"))
+    z = torch.zeros(4, 3, 3, 3, device="cuda")
+    out, s = ops.quant_weight_wino(z, G, GI, GTI, 8)
+    assert float(out.abs().max()) == 0.0 and float(s.abs().max()) == 0.0
+    with pytest.raises(Exception, match="Cout, Cin, 3, 3"):
+        ops.quant_weight_wino(torch.zeros(4, 3, 5, 5, device="cuda"), G, GI, GTI, 8)
+    with pytest.raises(Exception, match="GI must be"):
+        ops.quant_weight_wino(z, G, GTI, GI, 8)
+
+
+@pytest.mark.parametrize("name", ["F23", "F43", "F63"])
+def test_wino_backward_matches_oracle(ops, name):
+    g = rng(17).standard_normal((33, 9, 3, 3)).astype(F32)
+    G, GI, GTI = O.winograd_matrices(name)
+    got = ops.wino_backward(dev(g), dev(G), dev(GI), dev(GTI))
+    bits_equal(host(got), O.wino_backward(g, name))
