@@ -36,6 +36,14 @@ mm = torch.stack([ops.minmax(t) for t in (x, xl, x)])
 ops.hist_nonzero(x, mm[0, 1:2].clone(), 2048, counts[0])
 ops.hist_nonzero_multi([x, xl, x], mm, 2, 1, 2048, counts)
 hist = torch.zeros(3, 2049, device="cuda"); ops.hist_accumulate(counts.view(-1), hist.view(-1), True)
+ops.hist_nonzero(xl.view(-1)[1:], mm[1, 1:2].clone(), 2048, counts[1])                 # unaligned view: scalar kernel
+ring = torch.ones(4, 3, 2049, dtype=torch.int64, device="cuda")
+ops.hist_accumulate(ring.view(-1), hist.view(-1), False)                                # four batches in one launch
+from quantization.mxnet_b200.quantize.convert import wino_matrix as wm  # noqa: E402   Winograd-domain weights
+for name in ("F23", "F43", "F63"):
+    G, GI, GTI = (dev(m) for m in wm.winograd_matrices(name))
+    ops.quant_weight_wino(w, G, GI, GTI, 8); ops.quant_weight_wino(wd, G, GI, GTI, 4)
+    ops.wino_backward(w, G, GI, GTI)
 h = dev(np.floor(1e4 * np.exp(-np.arange(2048) / 300.0)).astype(np.float32))
 best, div = ops.kl_search(torch.stack([h, h]), 256, 1900, 2048, promotion="nep50")     # 148 candidates x 2 layers
 best2, _ = ops.kl_search(h, 1024, 2000, 2048, promotion="legacy")                      # block-per-candidate kernel
