@@ -4,7 +4,10 @@
     python bench_sweep.py [--max-log2 30] [--reps 20] [--out profiles/sweep.json]
 
 Every kernel is timed with CUDA events on torch's current stream after warm-up; between timed
-iterations a 512 MiB buffer is rewritten to flush the 126 MB L2 (unless --no-flush).  GB/s is
+iterations a 512 MiB buffer is rewritten to flush the 126 MB L2 (unless --no-flush) and a second 512 MiB
+buffer is then read, so that the ~100 MB of DIRTY lines the rewrite leaves in L2 are written back before the
+clock starts instead of inside the timed kernel (which would add up to 100 MB of write traffic to a kernel
+that moves 4 MB ... 16 GB: +37 % at 2^26 elements for a 4 B/element kernel).  GB/s is
 ALGORITHMIC bytes / time: 4 B/elem range, 8 B/elem forward, 12 B/elem online,
 4 B/elem histogram, 12 B/elem masked STE backward.
 """
@@ -35,7 +38,8 @@ def timeit(fn, reps, flush):
     ts = []
     for _ in range(reps):
         if flush is not None:
-            flush.add_(1)
+            flush[0].add_(1)          # rewrite 512 MiB: nothing of the tensor under test survives in L2
+            flush[1].max()            # read 512 MiB: the dirty lines of the rewrite are evicted (written back) now
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()
@@ -58,7 +62,8 @@ def main():
     args = ap.parse_args()
     torch.cuda.set_device(0)
     peak, peak_kind = peak_gbs()
-    flush = None if args.no_flush else torch.zeros(128 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    flush = None if args.no_flush else (torch.zeros(128 * 1024 * 1024, dtype=torch.float32, device="cuda"),
+                                        torch.zeros(128 * 1024 * 1024, dtype=torch.float32, device="cuda"))
     rows_out = []
     want = set(k for k in args.kernels.split(",") if k)
     for lg in range(args.min_log2, args.max_log2 + 1, args.step):

@@ -66,47 +66,63 @@ struct ScalarQuant {
 // One tile of 4 * kThreads * kUnroll elements per block, no loop: like a plain copy kernel the grid
 // is as large as the tensor, registers stay low enough for 6+ resident blocks per SM and every
 // thread has kUnroll 16 B loads in flight before it touches the data.
-template <bool CLIP, class Code>
-__global__ void __launch_bounds__(kThreads, 6) forward_scalar_kernel(const float* __restrict__ x, int64_t n,
+// PDL = true: launched as a programmatic dependent of the range kernel (fq_forward_online on small, latency-bound
+// tensors).  The kernel then starts while the range kernel's last block is still computing the qparams: the first
+// tile of x -- which the range kernel only reads -- is loaded before the wait.  One thread per block waits and
+// reads the qparams past L1 (.cg; L1 may still hold this layer's values of the previous step) and shares them
+// through shared memory: every warp of every block asking one L2 slice for the same 16 bytes costs microseconds
+// even at a few hundred blocks (and halves the throughput at 2^30 elements), so large tensors keep the plain
+// launch with L1-cached qparams.
+template <bool CLIP, class Code, bool PDL = false>
+__global__ void __launch_bounds__(kThreads, PDL ? 4 : 6) forward_scalar_kernel(const float* __restrict__ x, int64_t n,
                                                                      int64_t per_block,
                                                                      const float* __restrict__ qp_dev,
                                                                      ScalarQuant<CLIP, Code> op, int vectorised,
                                                                      int reverse) {
-  // As a programmatic dependent of the range kernel (fq_forward_online) this kernel starts while that kernel's
-  // last block is still computing the qparams: the first tile of x -- which the range kernel only reads -- is
-  // loaded before the wait.  L1 may hold this layer's qparams from the previous step: read them past it (.cg).
-  auto read_qparams = [&]() {
-    pdl_wait();
-    if (qp_dev != nullptr) {
-      op.d = __ldcg(qp_dev + FQ_QP_D);
-      op.s = __ldcg(qp_dev + FQ_QP_S);
-      op.lo = __ldcg(qp_dev + FQ_QP_LO);
-      op.hi = __ldcg(qp_dev + FQ_QP_HI);
+  __shared__ float s_qp[PDL ? 4 : 1];
+  auto wait_for_qparams = [&]() {
+    if (threadIdx.x == 0) {
+      pdl_wait();
+      s_qp[0] = __ldcg(qp_dev + FQ_QP_D);
+      s_qp[1] = __ldcg(qp_dev + FQ_QP_S);
+      s_qp[2] = __ldcg(qp_dev + FQ_QP_LO);
+      s_qp[PDL ? 3 : 0] = __ldcg(qp_dev + FQ_QP_HI);
     }
+    __syncthreads();
+    op.d = s_qp[0];
+    op.s = s_qp[1];
+    op.lo = s_qp[2];
+    op.hi = s_qp[PDL ? 3 : 0];
     op.prepare();
   };
+  if constexpr (!PDL) {
+    if (qp_dev != nullptr) {
+      op.d = __ldg(qp_dev + FQ_QP_D);
+      op.s = __ldg(qp_dev + FQ_QP_S);
+      op.lo = __ldg(qp_dev + FQ_QP_LO);
+      op.hi = __ldg(qp_dev + FQ_QP_HI);
+    }
+    op.prepare();
+  }
   if (vectorised) {
     const int64_t nvec = n >> 2;
     const float4* p4 = reinterpret_cast<const float4*>(x);
     const int64_t ntiles = (nvec + kTileElems / 4 - 1) / (kTileElems / 4);
-    bool have_qp = false;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int64_t tile = reverse ? (ntiles - 1 - t) : t;
       const int64_t v0 = tile * (kTileElems / 4) + threadIdx.x;
-      if (v0 + (kUnroll - 1) * kThreads < nvec) {
+      if ((tile + 1) * (kTileElems / 4) <= nvec) {        // block-uniform: the barrier below needs that
         float4 v[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream(p4 + v0 + u * kThreads);
-        if (!have_qp) {
-          read_qparams();
-          have_qp = true;
+        if constexpr (PDL) {
+          if (t == blockIdx.x) wait_for_qparams();       // first tile: its loads are already in flight
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) op.vec(4 * (v0 + u * kThreads), v[u]);
       } else {
-        if (!have_qp) {
-          read_qparams();
-          have_qp = true;
+        if constexpr (PDL) {
+          if (t == blockIdx.x) wait_for_qparams();
         }
         for (int u = 0; u < kUnroll; ++u) {
           const int64_t j = v0 + u * kThreads;
@@ -114,11 +130,13 @@ __global__ void __launch_bounds__(kThreads, 6) forward_scalar_kernel(const float
         }
       }
     }
-    if (!have_qp) read_qparams();
+    if constexpr (PDL) {
+      if ((int64_t)blockIdx.x >= ntiles) wait_for_qparams();     // a block with nothing but the scalar tail
+    }
     const int64_t tail0 = nvec << 2;
     if (blockIdx.x == 0 && threadIdx.x < n - tail0) op.sca(tail0 + threadIdx.x, x[tail0 + threadIdx.x]);
   } else {   // some pointer is not 16 B aligned: plain scalar grid-stride loop
-    read_qparams();
+    if constexpr (PDL) wait_for_qparams();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
       op.sca(i, x[i]);
   }
@@ -339,8 +357,8 @@ static int forward_scalar_impl(const char* who, const DLTensor* x_, const float*
     using Code = decltype(sink);
     if (clip && dependent) {
       ScalarQuant<true, Code> op{d, s, lo, hi, y.as<float>(), sink, QDiv()};
-      FQ_CUDA(launch_dependent(forward_scalar_kernel<true, Code>, dim3(grid), dim3(kThreads), 0, st, x.as<const float>(), n,
-                               per_block, qp_dev, op, (int)vec, (int)reverse));
+      FQ_CUDA(launch_dependent(forward_scalar_kernel<true, Code, true>, dim3(grid), dim3(kThreads), 0, st,
+                               x.as<const float>(), n, per_block, qp_dev, op, (int)vec, (int)reverse));
     } else if (clip) {
       ScalarQuant<true, Code> op{d, s, lo, hi, y.as<float>(), sink, QDiv()};
       forward_scalar_kernel<true, Code><<<grid, kThreads, 0, st>>>(x.as<const float>(), n, per_block, qp_dev, op, vec,
@@ -357,8 +375,12 @@ static int forward_scalar_impl(const char* who, const DLTensor* x_, const float*
 
 int launch_forward_scalar_dev(const DLTensor* x, const float* qp_dev, const DLTensor* y, const DLTensor* codes,
                               bool reverse, void* stream) {
-  // launched right behind the range kernel that produces qp_dev: programmatic dependent launch
-  return forward_scalar_impl("fq_forward_online", x, qp_dev, 0, 0, 0, 0, true, y, codes, stream, reverse, true);
+  // launched right behind the range kernel that produces qp_dev: as its programmatic dependent when the tensor
+  // is small enough to be latency-bound (<= 1024 tiles)
+  int64_t n = 1;
+  for (int i = 0; x != nullptr && i < x->ndim; ++i) n *= x->shape[i];
+  return forward_scalar_impl("fq_forward_online", x, qp_dev, 0, 0, 0, 0, true, y, codes, stream, reverse,
+                             n <= 1024 * kTileElems);
 }
 
 }  // namespace fq
