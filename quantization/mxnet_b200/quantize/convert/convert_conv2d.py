@@ -128,21 +128,46 @@ def _range_only(x, m):
     m._fq_range_pending = group is not None
 
 
+def _as_rows(tensors):
+    """[len(tensors), n] view over the tensors when they are consecutive rows of one allocation, else None."""
+    t0 = tensors[0]
+    n = t0.numel()
+    base = t0.untyped_storage().data_ptr()
+    for i, t in enumerate(tensors):
+        if (t.numel() != n or t.dtype != t0.dtype or not t.is_contiguous() or t.untyped_storage().data_ptr() != base
+                or t.storage_offset() != t0.storage_offset() + i * n):
+            return None
+    return torch.empty(0, dtype=t0.dtype, device=t0.device).set_(t0.untyped_storage(), t0.storage_offset(),
+                                                                  (len(tensors), n), (n, 1))
+
+
 def sync_pending_ranges(blocks):
     """Data parallel: replace every block's shard-local current_input_max by the mean over the GLOBAL batch,
-    with ONE all-gather of all layers' per-sample maxima and one batched Kahan-mean launch."""
+    with ONE all-gather of all layers' per-sample maxima and one batched Kahan-mean launch.  The per-sample
+    buffers of all blocks are rows of one arena (packed on first use) and the means land directly in the packed
+    ``current_input_max`` vector update_ema() works on, so a step costs the collective, one transpose and one
+    launch -- not a copy per layer."""
     from ... import dist as fqdist
     todo = [m for m in blocks if getattr(m, "_fq_range_pending", False)]
     if not todo:
         return
     group = todo[0]._fq_dist_group
-    local = torch.stack([m._fq_per_sample for m in todo])                 # [L, N/R]
+    local = _as_rows([m._fq_per_sample for m in todo])                    # [L, N/R]
+    if local is None:
+        local = torch.stack([m._fq_per_sample for m in todo])
+        for i, m in enumerate(todo):
+            m._fq_per_sample = local[i]          # the range kernels write into the arena from now on
     world = torch.distributed.get_world_size(group)
     allmax = fqdist.gather_per_sample(local.reshape(-1), group)           # [R, L, N/R]
     allmax = allmax.reshape(world, len(todo), -1).permute(1, 0, 2).reshape(len(todo), -1).contiguous()   # [L, N]
-    means = ops.mean_kahan(allmax)
-    for i, m in enumerate(todo):
-        m.current_input_max.copy_(means[i:i + 1])
+    cur = _as_rows([m.current_input_max for m in todo])                   # packed by update_ema (convert._packed)
+    if cur is not None:
+        ops.mean_kahan(allmax, out=cur.view(-1))
+    else:
+        means = ops.mean_kahan(allmax)
+        for i, m in enumerate(todo):
+            m.current_input_max.copy_(means[i:i + 1])
+    for m in todo:
         m._fq_range_pending = False
 
 
