@@ -179,7 +179,7 @@ def main():
             fqdist.enable_data_parallel(net)
         params = [p for p in net.parameters() if p.requires_grad]
         opt = torch.optim.Adam(params, lr=1e-6, capturable=args.graph)
-        bucket = fqdist.GradBucket(params)
+        bucket = fqdist.GradBucket(params, net=net if world > 1 else None)   # input ranges ride with the gradients
         if world > 1:
             bucket.attach()
         loss_fn = nn.CrossEntropyLoss()

@@ -130,17 +130,27 @@ def broadcast_parameters(net, src=0, group=None):
 class GradBucket:
     """All gradients of a net live in ONE flat fp32 buffer (each ``p.grad`` is a view into it, the way DDP's
     gradient_as_bucket_view works), so a QAT step needs a single all-reduce and no packing copies.
-    Use ``optimizer.zero_grad(set_to_none=False)`` so that the views survive."""
+    Use ``optimizer.zero_grad(set_to_none=False)`` so that the views survive.
 
-    def __init__(self, params, group=None):
+    ``net=`` (a converted net under :func:`enable_data_parallel`): the per-sample input maxima of the step ride in
+    the tail of the same buffer -- every rank fills its own [L, N/R] slice of an otherwise zero [R, L, N/R] block,
+    so the sum-all-reduce IS the all-gather (x + 0 is exact) -- and ``net.update_ema()`` calls made earlier in the
+    step are completed right after the collective.  The step then has one rendezvous between the ranks instead
+    of two (the second one, in the middle of the step, costs about 0.5 ms of rank skew per step on 2-4 GPUs)."""
+
+    def __init__(self, params, group=None, net=None):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.numel = sum(p.numel() for p in self.params)
         self.flat = None
+        self.net = net
+        self._deferred_ema = []
+        if net is not None:
+            net._fq_grad_bucket = self
 
-    def attach(self):
+    def attach(self, tail_numel=0):
         dev = self.params[0].device
-        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.flat = torch.zeros(self.numel + tail_numel, dtype=torch.float32, device=dev)
         off = 0
         for p in self.params:
             n = p.numel()
@@ -157,14 +167,44 @@ class GradBucket:
         p = self.params[0]
         return p.grad is not None and p.grad.data_ptr() == self.flat.data_ptr()
 
+    # ---- input ranges riding along -----------------------------------------------------------------------------
+    def _pending(self):
+        if self.net is None:
+            return []
+        from .quantize.convert.convert_conv2d import pending_range_blocks
+        return pending_range_blocks(self.net.collect_quantized_blocks())
+
+    def takes_over_ema(self):
+        """True when update_ema() should wait for all_reduce_mean(): training step, ranges still shard-local."""
+        return (self.net is not None and torch.is_grad_enabled() and active_group(self.group) is not None
+                and bool(self._pending()))
+
+    def defer_ema(self, momentum):
+        self._deferred_ema.append(momentum)
+
     def all_reduce_mean(self):
         g = active_group(self.group)
         if g is None or not self.params:
             return
-        if not self._attached():
-            self.attach()
+        world, rank = dist.get_world_size(g), dist.get_rank(g)
+        todo = self._pending()
+        n = todo[0]._fq_per_sample.numel() if todo else 0
+        tail_numel = world * len(todo) * n
+        if not self._attached() or self.flat.numel() != self.numel + tail_numel:
+            self.attach(tail_numel)
+        tail = self.flat[self.numel:].view(world, len(todo), n) if todo else None
+        if todo:
+            from .quantize.convert.convert_conv2d import local_range_arena
+            local_range_arena(todo, into=tail[rank])
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=g)
-        self.flat.div_(dist.get_world_size(g))
+        self.flat[:self.numel].div_(world)
+        if todo:
+            from .quantize.convert.convert_conv2d import finish_global_ranges
+            finish_global_ranges(todo, tail)
+            tail.zero_()          # the other ranks' slices must be zero again; ours is rewritten by the next forward
+        deferred, self._deferred_ema = self._deferred_ema, []
+        for momentum in deferred:
+            self.net.update_ema(momentum)
 
 
 def enable_data_parallel(net, group=None):

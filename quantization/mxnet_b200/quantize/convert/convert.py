@@ -67,6 +67,12 @@ class _Controls:
         """state <- (1 - momentum) * current + momentum * state for input_max, act_max and the fake-BN
         running statistics (convert.py:66-78)."""
         blocks = self.collect_quantized_blocks()
+        bucket = getattr(self, "_fq_grad_bucket", None)
+        if bucket is not None and bucket.takes_over_ema():
+            # data-parallel training step: the ranges travel with the gradient all-reduce and the EMA is applied
+            # right after it (nothing reads input_max before the next forward)
+            bucket.defer_ema(momentum)
+            return
         sync_pending_ranges(blocks)       # data parallel only: shard-local ranges -> global-batch ranges
         for state_name, current_name in (("input_max", "current_input_max"), ("act_max", "current_act_max")):
             arena = _packed(blocks, state_name, current_name)

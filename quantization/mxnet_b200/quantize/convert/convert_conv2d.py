@@ -141,26 +141,35 @@ def _as_rows(tensors):
                                                                   (len(tensors), n), (n, 1))
 
 
-def sync_pending_ranges(blocks):
-    """Data parallel: replace every block's shard-local current_input_max by the mean over the GLOBAL batch,
-    with ONE all-gather of all layers' per-sample maxima and one batched Kahan-mean launch.  The per-sample
-    buffers of all blocks are rows of one arena (packed on first use) and the means land directly in the packed
-    ``current_input_max`` vector update_ema() works on, so a step costs the collective, one transpose and one
-    launch -- not a copy per layer."""
-    from ... import dist as fqdist
-    todo = [m for m in blocks if getattr(m, "_fq_range_pending", False)]
-    if not todo:
-        return
-    group = todo[0]._fq_dist_group
-    local = _as_rows([m._fq_per_sample for m in todo])                    # [L, N/R]
-    if local is None:
-        local = torch.stack([m._fq_per_sample for m in todo])
+def pending_range_blocks(blocks):
+    """Blocks whose current_input_max still holds the mean over this rank's shard only."""
+    return [m for m in blocks if getattr(m, "_fq_range_pending", False)]
+
+
+def local_range_arena(todo, into=None):
+    """[L, N/R] per-sample maxima of the pending blocks as ONE tensor.  The blocks' buffers are rows of an arena
+    (packed on first use, or moved into ``into`` when the caller owns the exchange buffer), so later steps
+    need no packing kernel: the range kernels write straight into it."""
+    rows = _as_rows([m._fq_per_sample for m in todo])
+    if into is not None:
+        if rows is None or rows.data_ptr() != into.data_ptr():
+            for i, m in enumerate(todo):
+                into[i].copy_(m._fq_per_sample)
+                m._fq_per_sample = into[i]
+        return into
+    if rows is None:
+        rows = torch.stack([m._fq_per_sample for m in todo])
         for i, m in enumerate(todo):
-            m._fq_per_sample = local[i]          # the range kernels write into the arena from now on
-    world = torch.distributed.get_world_size(group)
-    allmax = fqdist.gather_per_sample(local.reshape(-1), group)           # [R, L, N/R]
-    allmax = allmax.reshape(world, len(todo), -1).permute(1, 0, 2).reshape(len(todo), -1).contiguous()   # [L, N]
-    cur = _as_rows([m.current_input_max for m in todo])                   # packed by update_ema (convert._packed)
+            m._fq_per_sample = rows[i]
+    return rows
+
+
+def finish_global_ranges(todo, allmax):
+    """allmax: [R, L, N/R] per-sample maxima of every rank -> Kahan mean over the global batch in sample order,
+    written to every block's current_input_max (one launch when update_ema() has packed them)."""
+    world = allmax.shape[0]
+    allmax = allmax.permute(1, 0, 2).reshape(len(todo), -1).contiguous()   # [L, N]
+    cur = _as_rows([m.current_input_max for m in todo])
     if cur is not None:
         ops.mean_kahan(allmax, out=cur.view(-1))
     else:
@@ -169,6 +178,23 @@ def sync_pending_ranges(blocks):
             m.current_input_max.copy_(means[i:i + 1])
     for m in todo:
         m._fq_range_pending = False
+    return world
+
+
+def sync_pending_ranges(blocks):
+    """Data parallel: replace every block's shard-local current_input_max by the mean over the GLOBAL batch,
+    with ONE all-gather of all layers' per-sample maxima and one batched Kahan-mean launch -- not a collective
+    or a copy per layer.  (A dist.GradBucket built with ``net=`` goes further and lets the maxima ride in the tail
+    of the gradient all-reduce.)"""
+    from ... import dist as fqdist
+    todo = pending_range_blocks(blocks)
+    if not todo:
+        return
+    group = todo[0]._fq_dist_group
+    local = local_range_arena(todo)                                       # [L, N/R]
+    world = torch.distributed.get_world_size(group)
+    allmax = fqdist.gather_per_sample(local.reshape(-1), group)           # [R, L, N/R]
+    finish_global_ranges(todo, allmax.reshape(world, len(todo), -1))
 
 
 class _WeightPath(torch.autograd.Function):

@@ -169,3 +169,103 @@ def test_two_rank_counts_ring_replays_the_per_batch_float32_adds():
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, "ok"), (1, "ok")], results
+
+
+def _bucket_worker(rank, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    from quantization.mxnet_b200 import dist as fqdist
+    from quantization.mxnet_b200 import ops
+    try:
+        # the Kahan-mean launch is CUDA only: stand in for it with the oracle (this test is about the exchange)
+        def mean_kahan(v, out=None):
+            res = torch.tensor([O.mean_kahan_f32(row.numpy()) for row in v.reshape(-1, v.shape[-1])])
+            if out is None:
+                return res
+            out.copy_(res)
+            return out
+        ops.mean_kahan = mean_kahan
+
+        class Block:
+            pass
+
+        class Net(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.lin = torch.nn.Linear(4, 3)
+                self.blocks = [Block() for _ in range(3)]
+                self.ema_calls = []
+                for b in self.blocks:
+                    b.current_input_max = torch.zeros(1)
+                    b._fq_range_pending = False
+
+            def collect_quantized_blocks(self):
+                return self.blocks
+
+            def update_ema(self, momentum=0.9):
+                # what convert._Controls.update_ema does first
+                bucket = getattr(self, "_fq_grad_bucket", None)
+                if bucket is not None and bucket.takes_over_ema():
+                    bucket.defer_ema(momentum)
+                    return
+                assert not any(b._fq_range_pending for b in self.blocks)
+                self.ema_calls.append((momentum, [float(b.current_input_max) for b in self.blocks]))
+
+        torch.manual_seed(0)
+        net = Net()
+        fqdist.broadcast_parameters(net)
+        bucket = fqdist.GradBucket(net.parameters(), net=net)
+        r = np.random.RandomState(4)
+        for step in range(3):
+            per = np.abs(r.standard_normal((WORLD, 3, 4))).astype(np.float32)       # [rank, block, sample]
+            for i, b in enumerate(net.blocks):
+                mine = torch.from_numpy(per[rank, i].copy())
+                if getattr(b, "_fq_per_sample", None) is None:
+                    b._fq_per_sample = mine
+                else:
+                    b._fq_per_sample.copy_(mine)              # the range kernel writes in place
+                b._fq_range_pending = True
+            x = torch.arange(8, dtype=torch.float32).reshape(2, 4) + rank + step
+            for p in net.parameters():
+                if p.grad is not None:
+                    p.grad.zero_()
+            net.lin(x).sum().backward()
+            local = torch.cat([p.grad.reshape(-1).clone() for p in net.parameters()])
+            net.update_ema(0.9)                               # before the collective: must be deferred
+            assert len(net.ema_calls) == step
+            bucket.all_reduce_mean()
+            gathered = [torch.zeros_like(local) for _ in range(WORLD)]
+            dist.all_gather(gathered, local)
+            assert torch.equal(torch.cat([p.grad.reshape(-1) for p in net.parameters()]), (gathered[0] + gathered[1]) / WORLD)
+            want = [float(O.mean_kahan_f32(np.concatenate([per[0, i], per[1, i]]))) for i in range(3)]
+            assert [float(b.current_input_max) for b in net.blocks] == want, step
+            assert len(net.ema_calls) == step + 1 and net.ema_calls[-1] == (0.9, want)
+            assert not any(b._fq_range_pending for b in net.blocks)
+            assert float(bucket.flat[bucket.numel:].abs().sum()) == 0.0          # tail is zero again
+            # the blocks' buffers now live in this rank's slice of the tail
+            assert all(b._fq_per_sample.data_ptr() == bucket.flat[bucket.numel:].view(WORLD, 3, 4)[rank, i].data_ptr()
+                       for i, b in enumerate(net.blocks))
+        # without grad (evaluation) nothing is deferred
+        with torch.no_grad():
+            net.update_ema(0.5)
+        assert net.ema_calls[-1][0] == 0.5
+        out.put((rank, "ok"))
+    except Exception as e:
+        import traceback
+        out.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_input_ranges_ride_in_the_gradient_all_reduce():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, port, out)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results

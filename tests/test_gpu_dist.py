@@ -74,6 +74,23 @@ def _worker(rank, port, out):
             net(fqdist.shard_batch(batches[1]).to(dev))
         net.update_ema()
         res["ema"] = np.array([m.input_max.item() for m in blocks], np.float32)
+        # --- the same step as a training step: update_ema() is deferred and the per-sample maxima ride in the tail
+        #     of the gradient all-reduce (dist.GradBucket(net=...)): one collective, same input_max
+        for m in blocks:
+            m.input_max.data.fill_(1.5)
+        params = [p for p in net.parameters() if p.requires_grad]
+        bucket = fqdist.GradBucket(params, net=net)
+        for step in range(2):           # the second step runs with the blocks' buffers inside the bucket's tail
+            if step == 1:
+                for m in blocks:
+                    m.input_max.data.fill_(1.5)
+            y = net(fqdist.shard_batch(batches[1]).to(dev))
+            net.update_ema()
+            assert bucket._deferred_ema == [0.9]
+            y.sum().backward()
+            bucket.all_reduce_mean()
+            res["ema_bucket%d" % step] = np.array([m.input_max.item() for m in blocks], np.float32)
+        res["grad0"] = params[0].grad.detach().cpu().numpy().copy()
         out.put((rank, res))
         dist.destroy_process_group()
     except Exception as e:
@@ -134,5 +151,11 @@ def test_two_gpu_sharded_calibration_equals_single_gpu():
     assert np.array_equal(results[0]["best"], results[1]["best"])
     assert np.array_equal(results[0]["cur"], results[1]["cur"])
     assert np.array_equal(results[0]["ema"], results[1]["ema"])
+    for r in range(WORLD):
+        for step in range(2):
+            assert results[r]["ema_bucket%d" % step][0] == results[r]["ema"][0]
+            assert np.allclose(results[r]["ema_bucket%d" % step], results[r]["ema"], rtol=1e-6)
+    assert np.array_equal(results[0]["ema_bucket1"], results[1]["ema_bucket1"])
+    assert np.array_equal(results[0]["grad0"], results[1]["grad0"]) and np.abs(results[0]["grad0"]).sum() > 0
     got = np.concatenate([results[0]["logits"], results[1]["logits"]])
     assert np.abs(got - logits).max() <= 2e-2 * np.abs(logits).max()
