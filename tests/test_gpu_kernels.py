@@ -361,6 +361,39 @@ def test_histogram_multi_tensor_equals_single(ops):
     assert int(got.sum()) == sum(int((x != 0).sum()) for x in xs)
 
 
+@pytest.mark.parametrize("bins", [1, 7, 100, 2048, 4096, 8192])
+def test_histogram_other_bin_counts_ragged_and_unaligned(ops, bins):
+    r = rng(bins)
+    for n, off in ((1, 0), (3, 0), (4099, 0), (70_001, 1), (300_000, 3), (1_234_567, 0)):
+        x = np.maximum(r.standard_normal(n + off) * 3, 0).astype(F32)
+        x[::7] = 0
+        t = dev(x)[off:]                       # off != 0: not 16 B aligned -> scalar kernel
+        for promo in ("legacy", "nep50"):
+            mx = F32(x[off:].max() * 0.8) if n > 3 else F32(max(x[off:].max(), 0.5))     # clipping at a frozen max
+            want = O.histogram_counts(x[off:], bins, mx, promo)
+            counts = torch.zeros(bins + 1, dtype=torch.int64, device="cuda")
+            ops.hist_nonzero(t, dev(np.array([mx], F32)), bins, counts, promotion=promo)
+            got = host(counts)
+            assert np.array_equal(got[:len(want)], want) and got[len(want):].sum() == 0, (n, off, promo)
+
+
+def test_histogram_without_a_positive_max_counts_nothing(ops):
+    """The reference asserts max_ > 0 before it histograms (distribution_calibrate.py:36); the kernel leaves the
+    counters alone and the deferred assert of collect_feature_maps reports it."""
+    x = dev(np.abs(rng(1).standard_normal(10_000)).astype(F32))
+    for mx in (0.0, -1.0, float("nan")):
+        counts = torch.zeros(2049, dtype=torch.int64, device="cuda")
+        ops.hist_nonzero(x, torch.tensor([mx], device="cuda"), 2048, counts)
+        assert int(counts.sum()) == 0
+    # NaN / negative / -0.0 elements are dropped, +inf lands in the last bin
+    y = dev(np.array([np.nan, -1.0, -0.0, 0.0, np.inf, 0.5, 1.0], F32))
+    counts = torch.zeros(2049, dtype=torch.int64, device="cuda")
+    ops.hist_nonzero(y, torch.tensor([1.0], device="cuda"), 2048, counts)
+    want = O.histogram_counts(np.array([0.0, 0.0, 1.0, 0.5, 1.0], F32), 2048, F32(1.0), "legacy")
+    got = host(counts)
+    assert np.array_equal(got[:len(want)], want) and got[len(want):].sum() == 0
+
+
 def test_hist_accumulate_many_batches_in_one_launch_replays_the_adds_in_order(ops):
     """counts [steps, n]: one float32 add per batch in batch order (distribution_calibrate.py:47,103-104),
     the same bits as one launch per batch (what a deferred all-reduce of many batches relies on)."""
