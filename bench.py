@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BINS, LEVELS = 2048, 256
+RING = 8                             # batches per sum-all-reduce of the integer counts
 BATCH = 128
 MODEL = "mobilenet1.0"
 METRIC = "kl_calibration_images_per_sec"
@@ -42,7 +43,7 @@ def workload_config(n_gpus, extra=None):
         "elements_per_step_per_gpu": ELEMS_PER_IMAGE * BATCH,
         "l2": "inputs (2.56 GB per step) exceed the 126 MB L2; no flush needed",
         "parallelism": "batch sharded over %d GPU(s); NCCL max-all-reduce of first-batch ranges, one sum-all-reduce "
-                       "of the int64 counts per 32 steps (float32 adds replayed per step in batch order)" % n_gpus,
+                       "of the int64 counts per %d steps (float32 adds replayed per step in batch order)" % (n_gpus, RING),
     }
     if extra:
         cfg.update(extra)
@@ -300,8 +301,8 @@ def run_b200(args):
     def fold(c, first):
         ops.hist_accumulate(c.reshape(-1), hist.view(-1), first)
         launches[0] += 1
-    # integer counts of up to 32 batches share ONE sum-all-reduce; the float32 adds are replayed in batch order
-    ring = fqdist.CountsRing(N_LAYERS, BINS + 1, dev, accumulate=fold, slots=32)
+    # integer counts of up to RING batches share ONE sum-all-reduce; the float32 adds are replayed in batch order
+    ring = fqdist.CountsRing(N_LAYERS, BINS + 1, dev, accumulate=fold, slots=RING)
     minmax = torch.zeros(N_LAYERS, 2, dtype=torch.float32, device=dev)
     div = torch.empty(N_LAYERS, BINS, dtype=torch.float64, device=dev)
     thresholds = torch.empty(N_LAYERS, dtype=torch.float32, device=dev)
@@ -337,6 +338,8 @@ def run_b200(args):
     for w in range(W):
         step(w == 0)
     kl_close()
+    # warm-up also covers the collective: NCCL connects an algorithm the first time a message size selects it
+    ring.prime([min(RING, K), K % RING])
     barrier()
 
     clocks = ClockSampler(local).start() if rank == 0 else None

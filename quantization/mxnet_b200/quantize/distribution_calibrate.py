@@ -30,7 +30,7 @@ class _Collector(dict):
     order = ()
 
 
-def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", group=None, ring_slots=32):
+def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", group=None, ring_slots=8):
     """
     Collect feature maps and record discrete histograms.
     :param net: converted torch.nn.Module
@@ -59,6 +59,7 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
             n_blk, bins + 1, dev, group=group, slots=ring_slots,
             accumulate=lambda c, first: ops.hist_accumulate(c.reshape(-1), state["hist"].view(-1), first, None),
             on_reduced=lambda c: state["seen_hist"].append((c[:, :, bins] != 0).to(torch.int32)))
+        state["ring"].prime()        # data parallel: connect NCCL for this message size outside the batch loop
 
     """ Add hooks to quantized blocks """
     hooks = []

@@ -142,8 +142,18 @@ def _ring_worker(rank, port, out):
                 c.zero_()
             ring = fqdist.CountsRing(n_layers, nb, "cpu", accumulate=fold, slots=slots,
                                      on_reduced=lambda c: seen.append(c.clone()))
+            ring.prime([slots, n_batches % slots, 0])             # zeros stay zeros
+            assert int(ring.ring.abs().sum()) == 0 and not seen
             for b in range(n_batches):
                 ring.slot().add_(torch.from_numpy(per_rank[rank, b]))
+                if b == 0 and slots > 1:
+                    ring.used = 1                                   # counts collected: priming now would sum them early
+                    try:
+                        ring.prime()
+                        raise RuntimeError("prime() accepted collected counts")
+                    except AssertionError:
+                        pass
+                    ring.used = 0
                 ring.commit()
             ring.flush()
             assert ring.used == 0 and ring.flushed == n_batches and int(ring.ring.abs().sum()) == 0
