@@ -114,7 +114,9 @@ FQ_API int fq_forward_rows(const DLTensor* x, int64_t rows, const DLTensor* scal
                     const DLTensor* codes, void* stream);
 /* Online input path without a host round trip: a range launch (per-sample absmax; its last block does the
  * Kahan mean and the scale math on the device) and the streaming quantiser, which walks the tensor backwards
- * so that it re-reads from L2.
+ * so that it re-reads from L2.  On latency-bound tensors (<= 4 Mi elements) the quantiser is a programmatic
+ * dependent launch of the range kernel (it loads its tile before griddepcontrol.wait); both launches are plain
+ * stream work and may be captured in a CUDA graph.
  * convert_conv2d.py:56-66 / convert_dense.py:41-49.  cur_max[0] and qparams[4] are written.
  * input_max != NULL selects the offline range (`input_max.asscalar()`, :58) while cur_max is still tracked;
  * y == NULL tracks the range only (quantize_input disabled, :55-57). */
