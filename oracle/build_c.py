@@ -42,6 +42,7 @@ def lib():
         L.fqo_hist_counts.argtypes = [_f, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_int, _l]
         L.fqo_kl_calibrate.argtypes = [_f, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _d]
         L.fqo_kl_calibrate.restype = ctypes.c_int
+        L.fqo_wino_weight.argtypes = [_f, ctypes.c_int64, ctypes.c_int64, _f, _f, _f, ctypes.c_int, ctypes.c_int, _f, _f]
         _lib = L
     return _lib
 
@@ -91,6 +92,15 @@ def kl_calibrate(data, levels, min_bins, bins, promotion="nep50"):
     div = np.full(bins, np.nan, np.float64)
     best = lib().fqo_kl_calibrate(_p(data, _f), data.size, levels, min_bins, bins, int(promotion == "nep50"), _p(div, _d))
     return best, div
+
+
+def wino_weight(w, G, GI, GTI, bits):
+    w = np.ascontiguousarray(w, np.float32)
+    G, GI, GTI = (np.ascontiguousarray(m, np.float32) for m in (G, GI, GTI))
+    wq, s = np.empty_like(w), np.empty(w.shape[0], np.float32)
+    lib().fqo_wino_weight(_p(w, _f), w.shape[0], w.shape[1], _p(G, _f), _p(GI, _f), _p(GTI, _f), G.shape[0], bits,
+                          _p(wq, _f), _p(s, _f))
+    return wq, s
 
 
 if __name__ == "__main__":

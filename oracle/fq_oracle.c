@@ -160,3 +160,64 @@ API int fqo_kl_calibrate(const float* data, int n_data, int levels, int min_bins
     }
   return best;
 }
+
+/* ---------------------------------------------------------------------------------------------------
+ * Winograd-domain per-channel weight quantisation: convert_conv2d.py:71-83, wino_matrix.py:28-60.
+ * U = (G w) G^T per 3x3 kernel, s_o = max|U[o]| / qmax, Uq = roundf(U / (s_o + 1e-10f)) * s_o,
+ * w_q = (GI Uq) GTI.  PARITY UNPINNED (nd.dot is a BLAS sgemm): every dot product is the chain
+ * acc = a0*b0; acc = fmaf(a_k, b_k, acc) over the contraction index in ascending order -- with the real
+ * single-rounding fmaf here, which is what the NumPy oracle's extended-precision emulation is checked against.
+ * G [a,3], GI [3,a], GTI [a,3], a <= 8; w, wq: [cout, cin, 3, 3]; scales: [cout]. */
+static void wino_u(const float* G, int a, const float* w, float* U) {
+  float t[8][3];
+  for (int p = 0; p < a; ++p)
+    for (int c = 0; c < 3; ++c) {
+      float acc = G[p * 3 + 0] * w[0 * 3 + c];
+      acc = fmaf(G[p * 3 + 1], w[1 * 3 + c], acc);
+      acc = fmaf(G[p * 3 + 2], w[2 * 3 + c], acc);
+      t[p][c] = acc;
+    }
+  for (int p = 0; p < a; ++p)
+    for (int q = 0; q < a; ++q) {
+      float acc = t[p][0] * G[q * 3 + 0];
+      acc = fmaf(t[p][1], G[q * 3 + 1], acc);
+      acc = fmaf(t[p][2], G[q * 3 + 2], acc);
+      U[p * a + q] = acc;
+    }
+}
+
+API void fqo_wino_weight(const float* w, int64_t cout, int64_t cin, const float* G, const float* GI, const float* GTI,
+                         int a, int bits, float* wq, float* scales) {
+  const float qmax = (float)((1 << (bits - 1)) - 1);
+#pragma omp parallel for schedule(static)
+  for (int64_t o = 0; o < cout; ++o) {
+    float U[64], m = 0.f;
+    for (int64_t i = 0; i < cin; ++i) {
+      wino_u(G, a, w + (o * cin + i) * 9, U);
+      for (int e = 0; e < a * a; ++e) {
+        const float v = fabsf(U[e]);
+        if (v > m) m = v;
+      }
+    }
+    const float s = m / qmax, d = s + 1e-10f;
+    scales[o] = s;
+    for (int64_t i = 0; i < cin; ++i) {
+      float V[3][8];
+      wino_u(G, a, w + (o * cin + i) * 9, U);
+      for (int e = 0; e < a * a; ++e) U[e] = roundf(U[e] / d) * s;
+      for (int r = 0; r < 3; ++r)
+        for (int q = 0; q < a; ++q) {
+          float acc = GI[r * a + 0] * U[0 * a + q];
+          for (int p = 1; p < a; ++p) acc = fmaf(GI[r * a + p], U[p * a + q], acc);
+          V[r][q] = acc;
+        }
+      float* out = wq + (o * cin + i) * 9;
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          float acc = V[r][0] * GTI[0 * 3 + c];
+          for (int q = 1; q < a; ++q) acc = fmaf(V[r][q], GTI[q * 3 + c], acc);
+          out[r * 3 + c] = acc;
+        }
+    }
+  }
+}

@@ -59,3 +59,18 @@ def test_c_kl_matches_reference_golden(name, levels):
     assert np.allclose(div[levels:], want[levels:], rtol=1e-12, atol=1e-14, equal_nan=True)
     best_l, _ = C.kl_calibrate(h, levels, levels, R.BINS, "legacy")
     assert best_l == O.kl_calibrate(h, levels, levels, R.BINS, "legacy")
+
+
+@pytest.mark.parametrize("name", ["F23", "F43", "F63"])
+def test_c_winograd_weight_path_with_real_fmaf_matches_numpy_oracle(name):
+    """The C restatement uses the hardware's single-rounding fmaf; the NumPy oracle emulates it in extended
+    precision.  Bit-equal results on ~10^6 fused operations pin the emulation."""
+    r = np.random.RandomState(9)
+    w = (r.standard_normal((24, 17, 3, 3)) * r.choice([1e-3, 0.1, 3.0], (24, 1, 1, 1))).astype(np.float32)
+    w[1] = 0
+    G, GI, GTI = O.winograd_matrices(name)
+    for bits in (8, 4):
+        want, want_s, _, _ = O.fake_quant_weight_wino(w, name, bits)
+        got, got_s = C.wino_weight(w, G, GI, GTI, bits)
+        assert np.array_equal(got_s.view(np.uint32), want_s.view(np.uint32))
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
