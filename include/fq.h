@@ -73,6 +73,7 @@ typedef struct {
 
 #define FQ_MAX_BATCH 64     /* tensors one multi-tensor launch takes */
 #define FQ_MAX_ROWS 65536   /* rows (samples / channels / groups) a fused kernel accepts */
+#define FQ_MAX_STAT_BLOCKS 32768 /* channels fq_channel_stats accepts */
 
 /* ---- library ---- */
 FQ_API int fq_version(void);
@@ -172,11 +173,17 @@ FQ_API int fq_ste_backward(const DLTensor* dy, const DLTensor* x, const DLTensor
 FQ_API int fq_ema_update(const DLTensor* state, const DLTensor* cur, double momentum, int scalar_cur,
                   int promotion, void* stream);
 
-/* Per-channel batch statistics of a conv output y [N, C, H, W] for the fake-BN EMA:
- * mean[c] = sum_{n,h,w} y / (N*H*W);  var[c] = sum (y - mean[c])^2 / (N*H*W)  (two passes, as written in
- * convert_conv2d.py:148-153).  fp32 sums in a fixed (deterministic) tree order: equal to the reference's
- * sequential sums to a few ULP, not bit for bit.  C <= 32768. */
-FQ_API int fq_channel_stats(const DLTensor* y, const DLTensor* mean, const DLTensor* var, void* ws, void* stream);
+/* Per-channel batch statistics of a conv output y [N, C, H, W] for the fake-BN EMA (convert_conv2d.py:148-153):
+ *   mean[c] = sum_{n,h,w} y / (N*H*W);  var[c] = sum (y - mean[c])^2 / (N*H*W).
+ * ONE pass over y (4 B/element): float64 shifted moments {n, S1 = sum(y-K), S2 = sum(y-K)^2, K = y[0,c,0,0]} per
+ * channel, from which mean and var follow algebraically with the reference's fp32-rounded mean; within 2 ULP of the
+ * reference's Kahan-compensated fp32 sums, deterministic.  mean/var (together) and parts (float64 [C, 4], the
+ * records) are each optional.  C <= FQ_MAX_STAT_BLOCKS. */
+FQ_API int fq_channel_stats(const DLTensor* y, const DLTensor* mean, const DLTensor* var, const DLTensor* parts,
+                            void* ws, void* stream);
+/* Data parallel: parts float64 [R, C, 4] = the records of R ranks (all-gathered; C may span every fake-BN layer of
+ * a network) -> mean/var [C] of the GLOBAL batch, same formula, same bound. */
+FQ_API int fq_channel_stats_finish(const DLTensor* parts, const DLTensor* mean, const DLTensor* var, void* stream);
 
 /* ---- K5 KL calibration   quantize/distribution_calibrate.py ------------- */
 /* counts[bin] += 1 for every clipped non-zero element; counts is uint64/int64 [bins+1].  :39-45 */

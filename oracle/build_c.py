@@ -43,6 +43,7 @@ def lib():
         L.fqo_kl_calibrate.argtypes = [_f, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _d]
         L.fqo_kl_calibrate.restype = ctypes.c_int
         L.fqo_wino_weight.argtypes = [_f, ctypes.c_int64, ctypes.c_int64, _f, _f, _f, ctypes.c_int, ctypes.c_int, _f, _f]
+        L.fqo_channel_stats.argtypes = [_f, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _f, _f]
         _lib = L
     return _lib
 
@@ -101,6 +102,14 @@ def wino_weight(w, G, GI, GTI, bits):
     lib().fqo_wino_weight(_p(w, _f), w.shape[0], w.shape[1], _p(G, _f), _p(GI, _f), _p(GTI, _f), G.shape[0], bits,
                           _p(wq, _f), _p(s, _f))
     return wq, s
+
+
+def channel_stats(y):
+    y = np.ascontiguousarray(y, np.float32)
+    n, c = y.shape[0], y.shape[1]
+    mean, var = np.empty(c, np.float32), np.empty(c, np.float32)
+    lib().fqo_channel_stats(_p(y, _f), n, c, y.size // (n * c), _p(mean, _f), _p(var, _f))
+    return mean, var
 
 
 if __name__ == "__main__":

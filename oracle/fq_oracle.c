@@ -221,3 +221,38 @@ API void fqo_wino_weight(const float* w, int64_t cout, int64_t cin, const float*
     }
   }
 }
+
+/* convert_conv2d.py:150-153: per-channel mean and two-pass variance of y [N, C, HW]; sequential Kahan fp32 sums in
+ * (n, h, w) order, `/ num` by fl32(num), `** 2` as the fp32 product */
+API void fqo_channel_stats(const float* y, int64_t N, int64_t C, int64_t HW, float* mean, float* var) {
+  const float num = (float)(N * HW);
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < C; ++c) {
+    volatile float s = 0.f, r = 0.f;
+    for (int64_t n = 0; n < N; ++n) {
+      const float* p = y + (n * C + c) * HW;
+      for (int64_t i = 0; i < HW; ++i) {
+        volatile float a = p[i] - r;
+        volatile float t = s + a;
+        r = (t - s) - a;
+        s = t;
+      }
+    }
+    const float m = s / num;
+    mean[c] = m;
+    s = 0.f;
+    r = 0.f;
+    for (int64_t n = 0; n < N; ++n) {
+      const float* p = y + (n * C + c) * HW;
+      for (int64_t i = 0; i < HW; ++i) {
+        volatile float d = p[i] - m;
+        volatile float sq = d * d;
+        volatile float a = sq - r;
+        volatile float t = s + a;
+        r = (t - s) - a;
+        s = t;
+      }
+    }
+    var[c] = s / num;
+  }
+}

@@ -305,6 +305,39 @@ def fold_bn(w, bias, gamma, beta, mean, var):
 
 
 # ---------------------------------------------------------------------------
+# fake-BN batch statistics   convert_conv2d.py:144-154
+# ---------------------------------------------------------------------------
+def kahan_sum_rows_f32(a):
+    """Kahan fp32 sum of every row of a [rows, n] array, sequential in column order (vectorised over the rows):
+    MXNet's CPU ``sum(axis=...)`` walks the reduced coordinates in row-major order with mshadow::red::sum's
+    residual (broadcast_reduce-inl.h seq_reduce_compute)."""
+    a = np.asarray(a, dtype=F32)
+    s = np.zeros(a.shape[0], F32)
+    c = np.zeros(a.shape[0], F32)
+    for k in range(a.shape[1]):
+        y = (a[:, k] - c).astype(F32)
+        t = (s + y).astype(F32)
+        c = ((t - s).astype(F32) - y).astype(F32)
+        s = t
+    return s
+
+
+def channel_stats(y):
+    """convert_conv2d.py:150-153 on the raw conv output y [N, C, H, W] -> (current_mean, current_var) fp32 [C]:
+        num = N*H*W ; mean = y.sum(axis=(0,2,3)) / num ; var = ((y - mean) ** 2).sum(axis=(0,2,3)) / num
+    PARITY UNPINNED (MXNet ops): sums = sequential Kahan fp32 over (n, h, w); ``/ num`` = _div_scalar by fl32(num);
+    ``** 2`` = _power_scalar, taken as the fp32 product a*a."""
+    y = np.asarray(y, dtype=F32)
+    n, c = y.shape[0], y.shape[1]
+    flat = np.moveaxis(y.reshape(n, c, -1), 1, 0).reshape(c, -1)           # [C, N*H*W] in (n, h, w) order
+    num = F32(flat.shape[1])
+    mean = (kahan_sum_rows_f32(flat) / num).astype(F32)
+    diff = (flat - mean[:, None]).astype(F32)
+    var = (kahan_sum_rows_f32((diff * diff).astype(F32)) / num).astype(F32)
+    return mean, var
+
+
+# ---------------------------------------------------------------------------
 # K3  STE backward   ste_func.py:43-44
 # ---------------------------------------------------------------------------
 def ste_backward(dy, x=None, lo=None, hi=None, mode="identity"):

@@ -65,7 +65,8 @@ SIGNATURES = {
     "fq_minmax": (_c.c_int, [P, P, _c.c_void_p, _c.c_void_p]),
     "fq_mean_kahan": (_c.c_int, [P, P, _c.c_void_p]),
     "fq_input_range": (_c.c_int, [P, _c.c_int64, P, P, _c.c_void_p, _c.c_void_p]),
-    "fq_channel_stats": (_c.c_int, [P, P, P, _c.c_void_p, _c.c_void_p]),
+    "fq_channel_stats": (_c.c_int, [P, P, P, P, _c.c_void_p, _c.c_void_p]),
+    "fq_channel_stats_finish": (_c.c_int, [P, P, P, _c.c_void_p]),
     "fq_scale_from_max": (_c.c_int, [P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, P, _c.c_void_p]),
     "fq_forward_scalar": (_c.c_int, [P, P, P, P, _c.c_void_p]),
     "fq_forward_scalar_host": (_c.c_int, [P, _c.c_float, _c.c_float, _c.c_float, _c.c_float, _c.c_int, P, P,

@@ -62,6 +62,7 @@ struct Workspace {
   unsigned int pad[30];
   unsigned int rowmax[FQ_MAX_ROWS];   // |x| bit patterns, atomicMax target
   float minmax_part[2 * 4096];        // per-block partials of fq_minmax
+  double stats_part[2 * FQ_MAX_STAT_BLOCKS];   // per-block {S1, S2} of fq_channel_stats
 };
 
 constexpr int kThreads = 256;

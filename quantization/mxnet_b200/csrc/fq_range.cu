@@ -111,90 +111,6 @@ __global__ void mean_kahan_kernel(const float* __restrict__ v_all, int64_t n, fl
   if (threadIdx.x == 0) out[blockIdx.x] = __fdiv_rn(s, (float)n);
 }
 
-// ---------------------------------------------------------------------------
-// per-channel batch statistics of an NCHW tensor (fake-BN EMA, convert_conv2d.py:148-153)
-// ---------------------------------------------------------------------------
-// Block (c, s) owns samples [s*N/S, (s+1)*N/S) of channel c.  PASS 0 writes the partial sums, PASS 1
-// re-derives the channel mean from those partials (fixed order) and writes partial sums of squared
-// deviations; the finish kernel turns both into mean / var and zeroes the scratch again.
-constexpr int kStatSplitMax = 16;
-
-__device__ __forceinline__ float stats_block_sum(float v, float* red) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) red[warp] = v;
-  __syncthreads();
-  if (warp == 0) {
-    v = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  }
-  return v;
-}
-
-template <int PASS>
-__global__ void __launch_bounds__(kThreads) channel_stats_kernel(const float* __restrict__ y, int64_t N, int64_t C,
-                                                                 int64_t HW, int S, float* __restrict__ part_sum,
-                                                                 float* __restrict__ part_sq) {
-  __shared__ float red[32];
-  const int64_t c = blockIdx.x / S;
-  const int s = blockIdx.x % S;
-  const int64_t n0 = N * s / S, n1 = N * (s + 1) / S;
-  float mean = 0.f;
-  if (PASS == 1) {
-    float tot = 0.f;
-    for (int k = 0; k < S; ++k) tot = __fadd_rn(tot, __ldcg(part_sum + c * S + k));
-    mean = __fdiv_rn(tot, (float)(N * HW));
-  }
-  float acc = 0.f;
-  const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
-  for (int64_t n = n0; n < n1; ++n) {
-    const float* p = y + (n * C + c) * HW;
-    if (vec) {
-      const float4* p4 = reinterpret_cast<const float4*>(p);
-      for (int64_t i = threadIdx.x; i < HW / 4; i += blockDim.x) {
-        const float4 v = ld_stream(p4 + i);
-        if (PASS == 0) {
-          acc += (v.x + v.y) + (v.z + v.w);
-        } else {
-          const float a = v.x - mean, b = v.y - mean, d = v.z - mean, e = v.w - mean;
-          acc += (__fmul_rn(a, a) + __fmul_rn(b, b)) + (__fmul_rn(d, d) + __fmul_rn(e, e));
-        }
-      }
-    } else {
-      for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) {
-        const float v = __ldg(p + i);
-        if (PASS == 0) {
-          acc += v;
-        } else {
-          const float a = v - mean;
-          acc += __fmul_rn(a, a);
-        }
-      }
-    }
-  }
-  acc = stats_block_sum(acc, red);
-  if (threadIdx.x == 0) (PASS == 0 ? part_sum : part_sq)[c * S + s] = acc;
-}
-
-__global__ void channel_stats_finish_kernel(int64_t C, int S, float num, float* __restrict__ part_sum,
-                                            float* __restrict__ part_sq, float* __restrict__ mean,
-                                            float* __restrict__ var) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float a = 0.f, b = 0.f;
-  for (int k = 0; k < S; ++k) {
-    a = __fadd_rn(a, part_sum[c * S + k]);
-    b = __fadd_rn(b, part_sq[c * S + k]);
-    part_sum[c * S + k] = 0.f;          // the scratch is the workspace's row-max area: leave it zeroed
-    part_sq[c * S + k] = 0.f;
-  }
-  mean[c] = __fdiv_rn(a, num);
-  var[c] = __fdiv_rn(b, num);
-}
-
 __global__ void scale_from_max_kernel(const float* __restrict__ max_, int bits, int is_signed, int lo_mode,
                                       int promotion, float* __restrict__ qp) {
   if (threadIdx.x == 0 && blockIdx.x == 0) compute_qparams(max_[0], bits, is_signed, lo_mode, promotion, qp);
@@ -286,40 +202,6 @@ int fq_input_range(const DLTensor* x_, int64_t n_samples, const DLTensor* per_sa
   fin.out_rows = ps.null ? nullptr : ps.as<float>();
   fin.out_mean = cur.as<float>();
   return launch_rows_absmax(x, n_samples, (Workspace*)ws, fin, (cudaStream_t)stream);
-}
-
-int fq_channel_stats(const DLTensor* y_, const DLTensor* mean_, const DLTensor* var_, void* ws, void* stream) {
-  const char* who = "fq_channel_stats";
-  View y, mean, var;
-  FQ_TRY(view_of(y_, "fq_channel_stats: y", false, &y));
-  FQ_TRY(view_of(mean_, "fq_channel_stats: mean", false, &mean));
-  FQ_TRY(view_of(var_, "fq_channel_stats: var", false, &var));
-  FQ_REQUIRE(ws != nullptr, "%s: NULL workspace", who);
-  FQ_REQUIRE(y.is_f32() && mean.is_f32() && var.is_f32(), "%s: float32 only", who);
-  FQ_REQUIRE(y_->ndim >= 2, "%s: y must be [N, C, ...]", who);
-  const int64_t N = y_->shape[0], C = y_->shape[1];
-  FQ_REQUIRE(N >= 1 && C >= 1 && y.numel > 0, "%s: empty tensor", who);
-  const int64_t HW = y.numel / (N * C);
-  FQ_REQUIRE(mean.numel == C && var.numel == C, "%s: mean and var must have C=%lld elements", who, (long long)C);
-  FQ_REQUIRE(C <= FQ_MAX_ROWS / 2, "%s: C=%lld exceeds %d", who, (long long)C, FQ_MAX_ROWS / 2);
-  int S = (int)((int64_t)sm_count() * 8 / C);
-  if (S < 1) S = 1;
-  if (S > kStatSplitMax) S = kStatSplitMax;
-  if (S > N) S = (int)N;
-  while ((int64_t)C * S > FQ_MAX_ROWS / 2) --S;
-  Workspace* w = (Workspace*)ws;
-  float* part_sum = reinterpret_cast<float*>(w->rowmax);
-  float* part_sq = part_sum + FQ_MAX_ROWS / 2;
-  cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = (unsigned)(C * S);
-  channel_stats_kernel<0><<<grid, kThreads, 0, st>>>(y.as<const float>(), N, C, HW, S, part_sum, part_sq);
-  FQ_LAUNCH_CHECK("channel_stats_kernel<0>");
-  channel_stats_kernel<1><<<grid, kThreads, 0, st>>>(y.as<const float>(), N, C, HW, S, part_sum, part_sq);
-  FQ_LAUNCH_CHECK("channel_stats_kernel<1>");
-  channel_stats_finish_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(C, S, (float)(N * HW), part_sum, part_sq,
-                                                                          mean.as<float>(), var.as<float>());
-  FQ_LAUNCH_CHECK("channel_stats_finish_kernel");
-  return 0;
 }
 
 int fq_scale_from_max(const DLTensor* max__, int bits, int is_signed, int lo_mode, int promotion,

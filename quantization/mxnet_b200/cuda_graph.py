@@ -5,7 +5,10 @@ The small-tensor configurations (CIFAR ResNet-20, MobileNetV2 at 32x32) are laun
 Every libfq_b200 entry point is capture-safe (no allocation, no host synchronisation, explicit stream,
 plain launches only), so the whole forward -- framework convolutions and fake-quant kernels
 alike -- can be recorded once and replayed with no host work in between.  The per-block state the
-reference exposes (``current_input_max``, ``input_max``) is updated by the replayed kernels in place.
+reference exposes (``current_input_max``, ``input_max``, fake-BN ``current_mean/var``) lives in arenas whose
+pointers are fixed at conversion time (quantize/convert/_state.py), so the replayed kernels and
+``net.update_ema()`` -- called between replays, as in ``for x in loader: g(x); net.update_ema()`` -- keep
+reading and writing the same memory.
 """
 import torch
 
@@ -22,6 +25,11 @@ class GraphedForward:
 
     def __init__(self, net, example_input, warmup=3):
         self.net = net
+        if hasattr(net, "collect_quantized_blocks"):
+            # the graph records raw pointers: the packed range / statistics arenas must be final before capture
+            # (convert_model builds them; this re-validates after any later move) and must not move afterwards
+            from .quantize.convert import _state
+            _state.pack(net)
         self.static_in = example_input.detach().clone()
         self.stream = torch.cuda.Stream(device=example_input.device)
         self.stream.wait_stream(torch.cuda.current_stream(example_input.device))
@@ -32,6 +40,13 @@ class GraphedForward:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=self.stream), torch.no_grad():
             self.static_out = net(self.static_in)
+        if hasattr(net, "collect_quantized_blocks"):
+            net.__dict__["_fq_graph_live"] = True        # _state.pack raises instead of re-pointing tensors
+
+    def release(self):
+        """Drop the graph; the net may be moved / repacked again."""
+        self.graph = None
+        self.net.__dict__.pop("_fq_graph_live", None)
 
     def __call__(self, x):
         self.static_in.copy_(x, non_blocking=True)

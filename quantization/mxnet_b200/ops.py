@@ -78,15 +78,30 @@ def input_range(x, n_samples=None, cur_max=None, per_sample=None):
     return cur_max
 
 
-def channel_stats(y, mean=None, var=None):
-    """Per-channel batch mean and (two-pass, biased) variance of an [N, C, H, W] tensor for the fake-BN
-    EMA (convert_conv2d.py:148-153): 8 B/element instead of the six passes of the op-by-op formula."""
+def channel_stats(y, mean=None, var=None, parts=None, finish=True):
+    """Per-channel batch mean and (biased) variance of an [N, C, H, W] tensor for the fake-BN EMA
+    (convert_conv2d.py:148-153) in ONE pass over y (4 B/element instead of the six passes of the op-by-op formula).
+    ``parts`` (float64 [C, 4]) also receives the {n, S1, S2, K} records that :func:`channel_stats_finish` combines
+    across ranks; ``finish=False`` writes the records only."""
     y = _f32(y, "y")
     c = y.shape[1]
-    mean = torch.empty(c, dtype=torch.float32, device=y.device) if mean is None else mean
-    var = torch.empty(c, dtype=torch.float32, device=y.device) if var is None else var
-    a, m, v = dl(y), dl(mean), dl(var)
-    check_call(_lib().fq_channel_stats(a.ptr, m.ptr, v.ptr, workspace(y.device), current_stream()))
+    if finish:
+        mean = torch.empty(c, dtype=torch.float32, device=y.device) if mean is None else mean
+        var = torch.empty(c, dtype=torch.float32, device=y.device) if var is None else var
+    else:
+        mean = var = None
+    a, m, v, p = dl(y), dl(mean), dl(var), dl(parts)
+    check_call(_lib().fq_channel_stats(a.ptr, ptr(m), ptr(v), ptr(p), workspace(y.device), current_stream()))
+    return mean, var
+
+
+def channel_stats_finish(parts, mean=None, var=None):
+    """parts: float64 [R, C, 4] records of R ranks -> (mean, var) float32 [C] of the global batch."""
+    c = parts.shape[-2]
+    mean = torch.empty(c, dtype=torch.float32, device=parts.device) if mean is None else mean
+    var = torch.empty(c, dtype=torch.float32, device=parts.device) if var is None else var
+    p, m, v = dl(parts), dl(mean), dl(var)
+    check_call(_lib().fq_channel_stats_finish(p.ptr, m.ptr, v.ptr, current_stream()))
     return mean, var
 
 
@@ -224,7 +239,12 @@ class WeightPlan:
                 if t is None:
                     setattr(rec, name, None)
                 else:
-                    arg = dl(_f32(t.detach(), name))
+                    t = t.detach()
+                    if t.dtype != torch.float32 or not t.is_contiguous():
+                        # a .contiguous() copy would be a snapshot that in-place optimizer updates never reach
+                        raise _ffi.FQError("WeightPlan: %s of job %d must be contiguous float32 (got %s, strides %s)"
+                                           % (name, i, t.dtype, tuple(t.stride())))
+                    arg = dl(t)
                     self.keep.append((arg, t))
                     setattr(rec, name, _ffi._c.pointer(arg.t))
             bits = int(jb["bits"])
@@ -249,10 +269,16 @@ class WeightPlan:
                 self.scale_slices.append(None)
         self.w_total, self.bias_total, self.scale_total = w_off, b_off, s_off
         self.device = jobs[0]["w"].device
-        self.ptrs = tuple(jb["w"].data_ptr() for jb in jobs)
+        self.ptrs = self.pointers(jobs)
+
+    @staticmethod
+    def pointers(jobs):
+        """Identity of every tensor a plan holds: the plan is stale as soon as any of them is replaced."""
+        return tuple((None if jb.get(name) is None else jb[name].data_ptr())
+                     for jb in jobs for name in ("w", "gamma", "beta", "mean", "var", "bias"))
 
     def valid_for(self, jobs):
-        return len(jobs) == self.n and all(jb["w"].data_ptr() == p for jb, p in zip(jobs, self.ptrs))
+        return len(jobs) == self.n and self.pointers(jobs) == self.ptrs
 
 
 def quant_weight_multi(plan):

@@ -12,9 +12,10 @@ import torch
 from torch import nn
 
 from ... import ops
+from . import _state
 from .convert_act import convert_relu_to_relu6, gen_act_converter
 from .convert_bn import bypass_bn
-from .convert_conv2d import gen_conv2d_converter, prequantize_weights, sync_pending_ranges
+from .convert_conv2d import gen_conv2d_converter, prequantize_weights, sync_pending_ranges, sync_pending_stats
 from .convert_dense import gen_dense_converter
 
 __all__ = ["convert_model", "convert_to_relu6", 'default_convert_fn']
@@ -26,33 +27,6 @@ default_convert_fn = {nn.Conv2d: gen_conv2d_converter(), nn.Linear: gen_dense_co
 
 _WEIGHTED = (nn.Linear, nn.Conv2d)
 _QUANTISABLE = _WEIGHTED + (nn.ReLU,)
-
-
-def _packed(blocks, state_name, current_name):
-    """(state vector, current vector) holding every block's (1,) ``state_name`` parameter and its (1,)
-    ``current_name`` buffer contiguously, so one launch updates them all.  The per-block tensors become
-    views; the packing is redone whenever .cuda()/.to() has moved them."""
-    owners = [m for m in blocks if getattr(m, state_name, None) is not None]
-    if not owners:
-        return None
-    first = owners[0]
-    arena = getattr(first, "_fq_arena_" + state_name, None)
-    intact = arena is not None and arena[0].numel() == len(owners) and \
-        arena[0].device == getattr(first, state_name).device
-    if intact:
-        s0, c0 = arena[0].data_ptr(), arena[1].data_ptr()
-        intact = all(getattr(m, state_name).data.data_ptr() == s0 + 4 * i and
-                     getattr(m, current_name).data_ptr() == c0 + 4 * i for i, m in enumerate(owners))
-    if not intact:
-        dev = getattr(first, state_name).device
-        state = torch.cat([getattr(m, state_name).data.reshape(1).to(dev) for m in owners])
-        current = torch.cat([getattr(m, current_name).reshape(1).to(dev) for m in owners])
-        arena = (state, current)
-        for i, m in enumerate(owners):
-            getattr(m, state_name).data = state[i:i + 1]
-            setattr(m, current_name, current[i:i + 1])
-            setattr(m, "_fq_arena_" + state_name, arena)
-    return arena
 
 
 class _Controls:
@@ -74,14 +48,13 @@ class _Controls:
             bucket.defer_ema(momentum)
             return
         sync_pending_ranges(blocks)       # data parallel only: shard-local ranges -> global-batch ranges
-        for state_name, current_name in (("input_max", "current_input_max"), ("act_max", "current_act_max")):
-            arena = _packed(blocks, state_name, current_name)
+        arenas = _state.pack(self, blocks)
+        sync_pending_stats(blocks, arenas)     # data parallel only: shard-local fake-BN statistics -> global batch
+        # one launch per kind for the whole net (the reference: one or two ops per block, convert.py:68-78)
+        for state_name, _, scalar_cur in _state.KINDS:
+            arena = arenas.get(state_name)
             if arena is not None:
-                ops.ema_update(arena[0], arena[1], momentum, scalar_cur=True)
-        for m in blocks:
-            for stat, cur in (("running_mean", "current_mean"), ("running_var", "current_var")):
-                if getattr(m, stat, None) is not None and getattr(m, cur, None) is not None:
-                    ops.ema_update(getattr(m, stat).data, getattr(m, cur), momentum, scalar_cur=False)
+                ops.ema_update(arena["state"], arena["current"], momentum, scalar_cur=scalar_cur)
 
     def quantize_input(self, enable=True, online=True):
         """Switch input (or activation) quantisation on/off and between online and offline ranges."""
@@ -114,11 +87,20 @@ _CONTROL_NAMES = ("update_ema", "collect_quantized_blocks", "quantize_input", "e
 
 
 def _before_net_forward(net, args):
+    # The reference's convolutions are plain fp32; torch would run them in TF32 on this GPU unless told otherwise
+    # (cudnn.allow_tf32 defaults to True), which breaks the 1e-5 logits contract and the fake-BN statistics.
+    net.__dict__["_fq_tf32_saved"] = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    if getattr(net, "force_fp32_framework_ops", True):
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
     if getattr(net, "batch_weight_paths", True):           # set to False to force the per-block launches
         prequantize_weights(net, net._fq_hook_blocks)
 
 
 def _after_net_forward(net, args, output):
+    saved = net.__dict__.pop("_fq_tf32_saved", None)
+    if saved is not None:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
     for m in net._fq_hook_blocks:                 # a block the forward did not reach must not keep a stale result
         m.__dict__.pop("_fq_pre", None)
 
@@ -141,6 +123,12 @@ def convert_model(net, exclude=[], convert_fn=default_convert_fn, custom_fn={}):
         if fn is not None:
             fn(m)
     net.apply(visit)
+    # converters of weightless blocks (ReLU) cannot know the net's device: put their state where the net lives
+    first = next(net.parameters(), None)
+    if first is not None:
+        for m in net.modules():
+            if type(m) == nn.ReLU and hasattr(m, "quantize_args") and m.act_max.device != first.device:
+                m.to(first.device)
     for name in _CONTROL_NAMES:
         setattr(net, name, types.MethodType(getattr(_Controls, name), net))
     # B200 execution detail (not part of the reference's API): the weight paths of ALL blocks run as one
@@ -150,8 +138,11 @@ def convert_model(net, exclude=[], convert_fn=default_convert_fn, custom_fn={}):
     net._fq_hook_blocks = net.collect_quantized_blocks()   # blocks converted later simply keep their per-block path
     if not getattr(net, "_fq_weight_hooks", False):
         net.register_forward_pre_hook(_before_net_forward)
-        net.register_forward_hook(_after_net_forward)
+        net.register_forward_hook(_after_net_forward, always_call=True)
         net._fq_weight_hooks = True
+    # every range / statistic of the net in a few arenas, built now so that pointers are stable before any
+    # CUDA-graph capture, and rebuilt whenever the net is moved
+    _state.install(net)
 
 
 def convert_to_relu6(net, exclude=[]):

@@ -25,6 +25,10 @@ def _quantised_activation(self, x):
     act = self.origin_forward(x)
     if not (self.enable_quantize and self.quantize_args.quantize_act):
         return act
+    if self.current_act_max.device != act.device:
+        # a ReLU has no weight to take a device from: its state follows the first activation it sees
+        # (convert_model already moves it to the net's device; this covers a block converted on its own)
+        self.to(act.device)
     # act >= 0 after a ReLU, so max == absmax (convert_act.py:50)
     ops.input_range(act.detach(), cur_max=self.current_act_max)
     if self.quantize_act:

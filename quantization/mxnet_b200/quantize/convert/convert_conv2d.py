@@ -308,12 +308,15 @@ def prequantize_weights(net, blocks):
             continue
         if not m.weight.is_cuda:
             return
+        if any(t is not None and (t.dtype != torch.float32 or not t.is_contiguous()) for t in jb.values()
+               if isinstance(t, torch.Tensor)):
+            continue                          # e.g. a channels_last weight: the per-block path copies it afresh each call
         jobs.append(jb)
         owners.append(m)
     if len(jobs) < 2:
         return                                # nothing to batch: the per-block path is just as good
-    key = tuple((id(m), jb["bits"], jb["rows"], jb.get("gamma") is not None, jb["w"].data_ptr())
-                for m, jb in zip(owners, jobs))
+    # the cached plan holds raw DLTensors: it is only valid while EVERY tensor of every job is the same storage
+    key = (tuple((id(m), jb["bits"], jb["rows"]) for m, jb in zip(owners, jobs)), ops.WeightPlan.pointers(jobs))
     plan = getattr(net, "_fq_weight_plan", None)
     if plan is None or plan[0] != key:
         plan = (key, ops.WeightPlan(jobs))
@@ -410,6 +413,9 @@ def _add_fake_bn_params(m):
     m.register_parameter("beta", nn.Parameter(torch.zeros(c, device=dev)))
     m.register_parameter("running_mean", nn.Parameter(torch.zeros(c, device=dev), requires_grad=False))
     m.register_parameter("running_var", nn.Parameter(torch.ones(c, device=dev), requires_grad=False))
+    # plain attributes in the reference (set by the pre-hook, :151-153); buffers here so that they follow the net
+    m.register_buffer("current_mean", torch.zeros(c, device=dev), persistent=False)
+    m.register_buffer("current_var", torch.zeros(c, device=dev), persistent=False)
 
 
 def _add_fake_bn_ema_hook(m):
@@ -418,8 +424,32 @@ def _add_fake_bn_ema_hook(m):
         with torch.no_grad():
             y = m.origin_forward(x[0], m.weight, m.bias)        # the reference's second convolution (:149)
             # mean = y.sum(axis=(0,2,3)) / num ; var = ((y - mean) ** 2).sum(axis=(0,2,3)) / num   (:150-153)
-            m.current_mean, m.current_var = ops.channel_stats(y)
+            # one pass over y; written in place so that the net's packed state (and a captured graph) sees it
+            group = getattr(m, "_fq_dist_group", None)
+            parts = m.__dict__.get("_fq_stats_parts") if group is not None else None
+            ops.channel_stats(y, mean=m.current_mean, var=m.current_var, parts=parts)
+            m._fq_stats_pending = parts is not None             # shard-local until update_ema() combines the ranks
     m.register_forward_pre_hook(_ema_hook)
+
+
+def sync_pending_stats(blocks, arenas):
+    """Data parallel: the fake-BN batch statistics of every block become those of the GLOBAL batch -- ONE all-gather
+    of all layers' float64 {n, S1, S2, K} records and one finish launch (the reference's
+    current_mean/current_var, convert_conv2d.py:150-153, over N = sum of the ranks' shards)."""
+    todo = [m for m in blocks if getattr(m, "_fq_stats_pending", False)]
+    rec = arenas.get("stats_parts")
+    if not todo or rec is None:
+        return
+    group = todo[0]._fq_dist_group
+    parts = rec["parts"]
+    world = torch.distributed.get_world_size(group)
+    gathered = rec.get("gathered")
+    if gathered is None or gathered.shape[0] != world or gathered.device != parts.device:
+        gathered = rec["gathered"] = torch.empty((world,) + tuple(parts.shape), dtype=parts.dtype, device=parts.device)
+    torch.distributed.all_gather_into_tensor(gathered, parts, group=group)
+    ops.channel_stats_finish(gathered, mean=arenas["running_mean"]["current"], var=arenas["running_var"]["current"])
+    for m in todo:
+        m._fq_stats_pending = False
 
 
 def gen_conv2d_converter(weight_width=8, quant_type="layer",

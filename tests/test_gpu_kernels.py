@@ -549,21 +549,65 @@ def test_beyond_2_31_elements_uses_64_bit_indexing(ops):
     assert int(counts[R.BINS - 1] + counts[R.BINS]) >= 1          # the 7.5 landed in the top bin
 
 
-@pytest.mark.parametrize("shape", [(8, 16, 14, 14), (128, 64, 8, 8), (4, 3, 7, 7), (32, 256, 1, 1), (2, 2048, 7, 7),
-                                   (16, 5, 13, 11), (1, 8, 32, 32)])
-def test_channel_stats_fake_bn(ops, shape):
-    y = (rng(sum(shape)).standard_normal(shape) * 2 + 0.5).astype(F32)
-    mean, var = ops.channel_stats(dev(y))
-    y64 = y.astype(np.float64)
-    want_m = y64.mean(axis=(0, 2, 3))
-    want_v = ((y64 - want_m.reshape(1, -1, 1, 1)) ** 2).mean(axis=(0, 2, 3))
-    # fp32 tree sums vs the reference's sequential fp32 sums: a few ULP of each other, both ~1e-6 from exact
-    assert np.allclose(host(mean), want_m, rtol=2e-6, atol=2e-6)
-    assert np.allclose(host(var), want_v, rtol=5e-6, atol=1e-7)
+def mean_close(got, want, y):
+    """1 ULP of the result + 2^-23 of mean |y| (Kahan's bound is relative to sum |y|: see test_channel_stats_math)."""
+    mag = np.abs(y.astype(np.float64)).mean(axis=(0, 2, 3))
+    tol = np.spacing(np.abs(want)).astype(np.float64) + 2.0 ** -23 * mag
+    return bool(np.all(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= tol))
+
+
+def ulp_diff(a, b):
+    """Largest distance in units of the last place between two float32 arrays of one sign pattern."""
+    a = np.ascontiguousarray(a, F32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b, F32).view(np.int32).astype(np.int64)
+    return int(np.abs(a - b).max())
+
+
+@pytest.mark.parametrize("shape,offset", [((8, 16, 14, 14), 0.5), ((128, 64, 8, 8), 0.5), ((4, 3, 7, 7), 0.5),
+                                          ((32, 256, 1, 1), 0.5), ((2, 2048, 7, 7), 0.5), ((16, 5, 13, 11), 0.5),
+                                          ((1, 8, 32, 32), 0.5), ((16, 8, 56, 56), 100.0), ((64, 32, 28, 28), -3.0),
+                                          ((3, 4, 33, 33), 1e4)])
+def test_channel_stats_fake_bn(ops, shape, offset):
+    """convert_conv2d.py:150-153.  One-pass float64 shifted moments vs the oracle's two-pass sequential Kahan fp32
+    sums: both sit within ~1 ULP of the exact value, so they agree to <= 2 ULP (measured: 0-1)."""
+    from oracle import build_c as C
+    y = (rng(sum(shape)).standard_normal(shape) * 2 + offset).astype(F32)
+    parts = torch.empty(shape[1], 4, dtype=torch.float64, device="cuda")
+    mean, var = ops.channel_stats(dev(y), parts=parts)
+    want_m, want_v = C.channel_stats(y)
+    assert mean_close(host(mean), want_m, y), ulp_diff(host(mean), want_m)
+    assert ulp_diff(host(var), want_v) <= 2, ulp_diff(host(var), want_v)
     m2, v2 = ops.channel_stats(dev(y))            # deterministic, and the workspace is left clean
     bits_equal(host(m2), host(mean))
     bits_equal(host(v2), host(var))
     bits_equal(host(ops.absmax_rows(dev(y), shape[0])), O.absmax_rows(y, shape[0]))
+    # the records: n, and K = the channel's first element
+    rec = host(parts)
+    assert np.all(rec[:, 0] == shape[0] * shape[2] * shape[3])
+    assert np.array_equal(rec[:, 3].astype(F32), y[0, :, 0, 0])
+    # a constant channel has exactly zero variance and its own value as mean, whatever its magnitude
+    yc = np.full((4, 3, 9, 9), 1234.5678, F32)
+    mc, vc = ops.channel_stats(dev(yc))
+    wm, wv = C.channel_stats(yc)
+    bits_equal(host(mc), wm)
+    assert float(host(vc).max()) <= float(wv.max()) + 1e-12
+
+
+@pytest.mark.parametrize("ranks", [2, 4, 8])
+def test_channel_stats_records_of_shards_reproduce_the_global_batch(ops, ranks):
+    """Data parallel: every rank's {n, S1, S2, K} records, all-gathered and combined by fq_channel_stats_finish,
+    give the statistics of the global batch to the single-GPU bound."""
+    from oracle import build_c as C
+    shape = (16 * ranks, 24, 14, 14)
+    y = (rng(ranks).standard_normal(shape) * 1.5 + rng(ranks + 1).standard_normal((1, 24, 1, 1)) * 4).astype(F32)
+    recs = torch.empty(ranks, 24, 4, dtype=torch.float64, device="cuda")
+    for r in range(ranks):
+        ops.channel_stats(dev(y[16 * r:16 * (r + 1)]), parts=recs[r], finish=False)
+    mean, var = ops.channel_stats_finish(recs)
+    want_m, want_v = C.channel_stats(y)
+    one_m, one_v = ops.channel_stats(dev(y))
+    assert mean_close(host(mean), want_m, y) and ulp_diff(host(var), want_v) <= 2
+    assert mean_close(host(mean), host(one_m), y) and ulp_diff(host(var), host(one_v)) <= 1
 
 
 def test_randomised_shapes_against_oracle(ops):

@@ -101,6 +101,9 @@ def test_kahan_mean_properties(v):
 @given(hnp.arrays(np.float32, st.tuples(st.integers(1, 4), st.integers(1, 3), st.just(3), st.just(3)),
                   elements=st.floats(-4, 4, allow_nan=False, width=32)), st.sampled_from(["F23", "F43", "F63"]))
 def test_winograd_transform_scales_exactly_and_backward_is_near_identity(w, name):
+    # "x2 is exact" only holds while no product or partial sum is subnormal (3.788e-42 * G loses bits that the
+    # doubled input keeps), so tiny magnitudes are flushed to zero before the property is checked
+    w = np.where(np.abs(w) < F32(2.0 ** -60), F32(0), w).astype(F32)
     G, GI, GTI = O.winograd_matrices(name)
     U = O.wino_transform(w, G)
     assert np.array_equal(O.wino_transform((w * F32(2)).astype(F32), G), (U * F32(2)).astype(F32))
