@@ -186,15 +186,18 @@ FQ_API int fq_channel_stats(const DLTensor* y, const DLTensor* mean, const DLTen
 FQ_API int fq_channel_stats_finish(const DLTensor* parts, const DLTensor* mean, const DLTensor* var, void* stream);
 
 /* ---- K5 KL calibration   quantize/distribution_calibrate.py ------------- */
-/* counts[bin] += 1 for every clipped non-zero element; counts is uint64/int64 [bins+1].  :39-45 */
+/* counts[bin] += 1 for every clipped non-zero element; counts is uint64/int64 [bins+1].  :39-45
+ * bad_flag (NULL or int32 [1]): |= 1 when the tensor holds a negative value or a NaN, or max_ is not > 0 -- the
+ * reference's asserts of :35-36, which it evaluates on every batch; the kernel itself drops such elements. */
 FQ_API int fq_hist_nonzero(const DLTensor* x, const DLTensor* max_, int bins, int promotion,
-                    const DLTensor* counts, void* stream);
+                    const DLTensor* counts, const DLTensor* bad_flag, void* stream);
 /* The same for n_tensors (<= FQ_MAX_BATCH per launch, more are chunked) layer inputs in ONE launch: the
  * thread blocks are shared out in proportion to the tensor sizes, so small layers cost no launch of their own.
  * xs[i]: float32, 16-byte aligned; its frozen max is maxes[i * max_stride + max_offset];
- * counts: (u)int64 [n_tensors, bins+1]. */
+ * counts: (u)int64 [n_tensors, bins+1]; bad_flags: NULL or int32 [n_tensors] (see fq_hist_nonzero). */
 FQ_API int fq_hist_nonzero_multi(const DLTensor* const* xs, int n_tensors, const DLTensor* maxes, int max_stride,
-                                 int max_offset, int bins, int promotion, const DLTensor* counts, void* stream);
+                                 int max_offset, int bins, int promotion, const DLTensor* counts,
+                                 const DLTensor* bad_flags, void* stream);
 /* hist = (first ? 0 : hist) + float32(counts); counts <- 0; seen_last[0] |= counts[bins] != 0.  :47,103-104
  * hist: float32 [n]; counts: (u)int64 [steps, n] (steps >= 1) -- the batches are folded in order, one float32
  * add per batch as the reference does, so a data-parallel run may all-reduce the counts of many batches at once. */
@@ -203,9 +206,10 @@ FQ_API int fq_hist_accumulate_f32(const DLTensor* counts, const DLTensor* hist, 
 /* best[l] = first strict arg-min of the KL divergence over i in [min_bins, bins).  :117-171
  * hist: float32 [n_data] or [layers, n_data] with n_data in {bins, bins+1}; best: int32 [layers];
  * divergence: caller-provided float64 [layers, bins] scratch that receives D_i (entries below
- * min_bins are left untouched). */
+ * min_bins are left untouched); margin: NULL or float64 [layers] receiving (runner-up - best) / |best| -- below
+ * ~1e-12 the reference's own choice depends on the last place of its libm's log, so callers flag small margins. */
 FQ_API int fq_kl_search(const DLTensor* hist, int levels, int min_bins, int bins, int promotion,
-                 const DLTensor* best, const DLTensor* divergence, void* stream);
+                 const DLTensor* best, const DLTensor* divergence, const DLTensor* margin, void* stream);
 /* input_max[0] = (best + 0.5) * (fm_max / bins).  examples/simulate_quantization.py:310,314 */
 FQ_API int fq_kl_threshold(const DLTensor* best, const DLTensor* fm_max, int bins, const DLTensor* input_max,
                     void* stream);

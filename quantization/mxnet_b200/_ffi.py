@@ -80,11 +80,11 @@ SIGNATURES = {
     "fq_wino_backward": (_c.c_int, [P, P, P, P, P, _c.c_void_p]),
     "fq_ste_backward": (_c.c_int, [P, P, P, P, _c.c_int, _c.c_void_p]),
     "fq_ema_update": (_c.c_int, [P, P, _c.c_double, _c.c_int, _c.c_int, _c.c_void_p]),
-    "fq_hist_nonzero": (_c.c_int, [P, P, _c.c_int, _c.c_int, P, _c.c_void_p]),
-    "fq_hist_nonzero_multi": (_c.c_int, [_c.POINTER(P), _c.c_int, P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, P,
+    "fq_hist_nonzero": (_c.c_int, [P, P, _c.c_int, _c.c_int, P, P, _c.c_void_p]),
+    "fq_hist_nonzero_multi": (_c.c_int, [_c.POINTER(P), _c.c_int, P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, P, P,
                                          _c.c_void_p]),
     "fq_hist_accumulate_f32": (_c.c_int, [P, P, _c.c_int, P, _c.c_void_p]),
-    "fq_kl_search": (_c.c_int, [P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, P, P, _c.c_void_p]),
+    "fq_kl_search": (_c.c_int, [P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, P, P, P, _c.c_void_p]),
     "fq_kl_threshold": (_c.c_int, [P, P, _c.c_int, P, _c.c_void_p]),
     "fq_quantize_int8_export": (_c.c_int, [P, P, P, P, _c.c_void_p]),
     "fq_qconv_quantize": (_c.c_int, [P, P, P, P, _c.c_void_p]),

@@ -68,6 +68,30 @@ struct HistBins {
   }
 };
 
+// The reference asserts `np.min(fm) >= 0` on EVERY batch (distribution_calibrate.py:35) and its np.max / np.min
+// turn a NaN anywhere into a failed assert.  The histogram kernel silently drops negatives and NaN, so when the
+// caller passes a flag word it also keeps a NaN-propagating running minimum (min.NaN.f32: one instruction per
+// pair of elements) and raises the flag when that minimum is not >= 0 (-0.0 passes, as it does in NumPy).
+template <bool CHECK>
+struct MinCheck {
+  float m = 0.f;
+  __device__ __forceinline__ void see(float v) {
+    if (CHECK) asm("min.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(v));
+  }
+  __device__ __forceinline__ void see4(float4 v) {
+    if (CHECK) {
+      float a, b;
+      asm("min.NaN.f32 %0, %1, %2;" : "=f"(a) : "f"(v.x), "f"(v.y));
+      asm("min.NaN.f32 %0, %1, %2;" : "=f"(b) : "f"(v.z), "f"(v.w));
+      asm("min.NaN.f32 %0, %0, %1;" : "+f"(a) : "f"(b));
+      asm("min.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(a));
+    }
+  }
+  __device__ __forceinline__ void publish(int* flag) const {
+    if (CHECK && !(m >= 0.f)) atomicOr(flag, 1);
+  }
+};
+
 __device__ __forceinline__ void hist_zero(unsigned int* sh, int bins) {
   for (int b = threadIdx.x; b < bins + 1 + 32; b += blockDim.x) sh[b] = 0u;
   __syncthreads();
@@ -90,7 +114,9 @@ constexpr int kHistTileVec = kHistThreads * kUnroll;        // float4 per tile
 
 // Block j of the nblk blocks of a 16 B aligned tensor: tiles of kHistTileVec float4 go round-robin over the
 // tensor's blocks, so the resident blocks stream one contiguous window of it.
-__device__ __forceinline__ void hist_stream(const float* __restrict__ x, int64_t n, int j, int nblk, const HistBins& hb) {
+template <bool CHECK>
+__device__ __forceinline__ void hist_stream(const float* __restrict__ x, int64_t n, int j, int nblk, const HistBins& hb,
+                                            MinCheck<CHECK>& mc) {
   const float4* p4 = reinterpret_cast<const float4*>(x);
   const int64_t nvec = n >> 2;
   int64_t v0 = (int64_t)j * kHistTileVec + threadIdx.x;
@@ -100,15 +126,26 @@ __device__ __forceinline__ void hist_stream(const float* __restrict__ x, int64_t
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream(p4 + v0 + u * kHistThreads);
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) hb.add4(v[u]);
+    for (int u = 0; u < kUnroll; ++u) {
+      hb.add4(v[u]);
+      mc.see4(v[u]);
+    }
   }
   // the tensor's last, partial tile: only the block whose turn it is still has v0 < nvec
 #pragma unroll 1
   for (int u = 0; u < kUnroll; ++u) {
     const int64_t vi = v0 + (int64_t)u * kHistThreads;
-    if (vi < nvec) hb.add4(ld_stream(p4 + vi));
+    if (vi < nvec) {
+      const float4 v = ld_stream(p4 + vi);
+      hb.add4(v);
+      mc.see4(v);
+    }
   }
-  if (j == nblk - 1 && threadIdx.x < (n & 3)) hb.add(x[(nvec << 2) + threadIdx.x]);
+  if (j == nblk - 1 && threadIdx.x < (n & 3)) {
+    const float v = x[(nvec << 2) + threadIdx.x];
+    hb.add(v);
+    mc.see(v);
+  }
 }
 
 // Multi-tensor launch: block -> (tensor, block within the tensor) through a table passed by value.
@@ -119,9 +156,11 @@ struct HistBatch {
   int count;
 };
 
+template <bool CHECK>
 __global__ void __launch_bounds__(kHistThreads, kHistBlocksPerSM)
     hist_multi_kernel(const __grid_constant__ HistBatch tb, const float* __restrict__ maxes, int max_stride,
-                      int max_offset, int bins, int promotion, unsigned long long* __restrict__ counts) {
+                      int max_offset, int bins, int promotion, unsigned long long* __restrict__ counts,
+                      int* __restrict__ bad_flags) {
   extern __shared__ unsigned int sh[];     // bins + 1 private counters, 32 trash counters
   int t = 0;
   while (t + 1 < tb.count && (int)blockIdx.x >= tb.first_block[t + 1]) ++t;
@@ -130,23 +169,36 @@ __global__ void __launch_bounds__(kHistThreads, kHistBlocksPerSM)
   hb.init(sh, max_, bins, promotion);
   hist_zero(sh, bins);
   // the reference asserts max_ > 0 (:36); with max_ <= 0 everything would clip to <= 0 and be dropped
+  MinCheck<CHECK> mc;
   if (max_ > 0.f)
-    hist_stream(tb.x[t], tb.n[t], (int)blockIdx.x - tb.first_block[t], tb.first_block[t + 1] - tb.first_block[t], hb);
+    hist_stream(tb.x[t], tb.n[t], (int)blockIdx.x - tb.first_block[t], tb.first_block[t + 1] - tb.first_block[t], hb, mc);
+  else if (CHECK)
+    mc.m = -1.f;                  // `assert max_ > 0` (:36); a NaN max lands here as well
+  if (CHECK) mc.publish(bad_flags + t);
   hist_flush(sh, bins, counts + (int64_t)t * (bins + 1));
 }
 
 // Any alignment: grid-stride scalar loads (views at odd offsets; never the hot path).
 __global__ void __launch_bounds__(kThreads) hist_unaligned_kernel(const float* __restrict__ x, int64_t n,
                                                                   const float* __restrict__ max_dev, int bins,
-                                                                  int promotion, unsigned long long* __restrict__ counts) {
+                                                                  int promotion, unsigned long long* __restrict__ counts,
+                                                                  int* __restrict__ bad_flag) {
   extern __shared__ unsigned int sh[];
   const float max_ = __ldg(max_dev);
   HistBins hb;
   hb.init(sh, max_, bins, promotion);
   hist_zero(sh, bins);
-  if (max_ > 0.f)
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-      hb.add(x[i]);
+  MinCheck<true> mc;
+  if (max_ > 0.f) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const float v = x[i];
+      hb.add(v);
+      mc.see(v);
+    }
+  } else {
+    mc.m = -1.f;
+  }
+  if (bad_flag != nullptr) mc.publish(bad_flag);
   hist_flush(sh, bins, counts);
 }
 
@@ -454,35 +506,51 @@ __global__ void __launch_bounds__(kKlGroupThreads) kl_group_kernel(const float* 
   }
 }
 
-// first strict minimum, NaN never wins (:167-169)
-__global__ void kl_argmin_kernel(const double* __restrict__ div_all, int min_bins, int bins, int* __restrict__ best) {
-  __shared__ double sv[kThreads];
+// first strict minimum, NaN never wins (:167-169).  margin[l] (optional) = (runner-up - best) / |best|, the relative
+// gap to the smallest divergence of any OTHER candidate: D_i is a float64 sum of p*log(p/q) terms whose `log` may
+// differ from the reference's libm in the last place (relative 1e-16 per term), so a margin below ~1e-12 means the
+// reference's own choice between the two candidates depends on its math library; callers flag margins < 1e-9.
+__global__ void kl_argmin_kernel(const double* __restrict__ div_all, int min_bins, int bins, int* __restrict__ best,
+                                 double* __restrict__ margin) {
+  __shared__ double sv[kThreads], s2[kThreads];
   __shared__ int si[kThreads];
   const double* div = div_all + (int64_t)blockIdx.x * bins;
-  double bv = INFINITY;
+  double bv = INFINITY, second = INFINITY;
   int bi = min_bins;
   for (int i = min_bins + threadIdx.x; i < bins; i += blockDim.x) {
     const double d = div[i];
     if (d < bv) {
+      second = bv;
       bv = d;
       bi = i;
+    } else if (d < second) {
+      second = d;
     }
   }
   sv[threadIdx.x] = bv;
+  s2[threadIdx.x] = second;
   si[threadIdx.x] = bi;
   __syncthreads();
   for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) {
-      const double ov = sv[threadIdx.x + o];
+      const double ov = sv[threadIdx.x + o], o2 = s2[threadIdx.x + o];
       const int oi = si[threadIdx.x + o];
-      if (ov < sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) {
+      const double mv = sv[threadIdx.x], m2 = s2[threadIdx.x];
+      const bool other_wins = ov < mv || (ov == mv && oi < si[threadIdx.x]);
+      const double loser = other_wins ? mv : ov;
+      s2[threadIdx.x] = fmin(loser, fmin(m2, o2));         // fmin ignores NaN: a NaN divergence never counts
+      if (other_wins) {
         sv[threadIdx.x] = ov;
         si[threadIdx.x] = oi;
       }
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) best[blockIdx.x] = (sv[0] < INFINITY) ? si[0] : min_bins;
+  if (threadIdx.x == 0) {
+    best[blockIdx.x] = (sv[0] < INFINITY) ? si[0] : min_bins;
+    if (margin != nullptr)
+      margin[blockIdx.x] = (sv[0] < INFINITY && s2[0] < INFINITY) ? (s2[0] - sv[0]) / fmax(fabs(sv[0]), 1e-300) : INFINITY;
+  }
 }
 
 __global__ void kl_threshold_kernel(const int* __restrict__ best, const float* __restrict__ fm_max, int bins,
@@ -531,9 +599,31 @@ static int hist_share_blocks(HistBatch* tb, int budget) {
   return blocks;
 }
 
+static int launch_hist_multi(const HistBatch& tb, int blocks, const float* maxes, int max_stride, int max_offset,
+                             int bins, int promotion, unsigned long long* counts, int* flags, cudaStream_t st) {
+  const size_t smem = sizeof(unsigned int) * (bins + 1 + 32);
+  if (flags != nullptr)
+    hist_multi_kernel<true><<<blocks, kHistThreads, smem, st>>>(tb, maxes, max_stride, max_offset, bins, promotion,
+                                                                counts, flags);
+  else
+    hist_multi_kernel<false><<<blocks, kHistThreads, smem, st>>>(tb, maxes, max_stride, max_offset, bins, promotion,
+                                                                 counts, nullptr);
+  FQ_LAUNCH_CHECK("hist_multi_kernel");
+  return 0;
+}
+
+static bool flags_ok(const char* who, const View& f, int64_t n) {
+  if (f.null) return true;
+  if (f.code == kDLInt && f.bits == 32 && f.numel == n) return true;
+  set_error("%s: bad_flags must be int32 [%lld]", who, (long long)n);
+  return false;
+}
+
 int fq_hist_nonzero(const DLTensor* x_, const DLTensor* max__, int bins, int promotion, const DLTensor* counts_,
-                    void* stream) {
-  View x, mx, counts;
+                    const DLTensor* bad_flag_, void* stream) {
+  View x, mx, counts, flag;
+  FQ_TRY(view_of(bad_flag_, "fq_hist_nonzero: bad_flag", true, &flag));
+  FQ_TRY(flags_ok("fq_hist_nonzero", flag, 1));
   FQ_TRY(view_of(x_, "fq_hist_nonzero: x", false, &x));
   FQ_TRY(view_of(max__, "fq_hist_nonzero: max_", false, &mx));
   FQ_TRY(view_of(counts_, "fq_hist_nonzero: counts", false, &counts));
@@ -550,23 +640,26 @@ int fq_hist_nonzero(const DLTensor* x_, const DLTensor* max__, int bins, int pro
     tb.n[0] = x.numel;
     tb.count = 1;
     const int blocks = hist_share_blocks(&tb, sm_count() * kHistBlocksPerSM);
-    hist_multi_kernel<<<blocks, kHistThreads, smem, (cudaStream_t)stream>>>(
-        tb, mx.as<const float>(), 1, 0, bins, promotion, counts.as<unsigned long long>());
-    FQ_LAUNCH_CHECK("hist_multi_kernel");
+    FQ_TRY(launch_hist_multi(tb, blocks, mx.as<const float>(), 1, 0, bins, promotion, counts.as<unsigned long long>(),
+                             flag.null ? nullptr : flag.as<int>(), (cudaStream_t)stream) == 0);
   } else {
     const int64_t b = (x.numel + kThreads - 1) / kThreads;
     const int grid = (int)(b > sm_count() * 8 ? sm_count() * 8 : b);
     hist_unaligned_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
-        x.as<const float>(), x.numel, mx.as<const float>(), bins, promotion, counts.as<unsigned long long>());
+        x.as<const float>(), x.numel, mx.as<const float>(), bins, promotion, counts.as<unsigned long long>(),
+        flag.null ? nullptr : flag.as<int>());
     FQ_LAUNCH_CHECK("hist_unaligned_kernel");
   }
   return 0;
 }
 
 int fq_hist_nonzero_multi(const DLTensor* const* xs, int n_tensors, const DLTensor* maxes_, int max_stride,
-                          int max_offset, int bins, int promotion, const DLTensor* counts_, void* stream) {
+                          int max_offset, int bins, int promotion, const DLTensor* counts_,
+                          const DLTensor* bad_flags_, void* stream) {
   const char* who = "fq_hist_nonzero_multi";
-  View mx, counts;
+  View mx, counts, flags;
+  FQ_TRY(view_of(bad_flags_, "fq_hist_nonzero_multi: bad_flags", true, &flags));
+  FQ_TRY(flags_ok(who, flags, n_tensors));
   FQ_REQUIRE(xs != nullptr && n_tensors >= 1, "%s: no tensors", who);
   FQ_TRY(view_of(maxes_, "fq_hist_nonzero_multi: maxes", false, &mx));
   FQ_TRY(view_of(counts_, "fq_hist_nonzero_multi: counts", false, &counts));
@@ -592,10 +685,9 @@ int fq_hist_nonzero_multi(const DLTensor* const* xs, int n_tensors, const DLTens
     tb.count = cnt;
     const int blocks = hist_share_blocks(&tb, budget);
     if (blocks == 0) continue;
-    hist_multi_kernel<<<blocks, kHistThreads, sizeof(unsigned int) * (bins + 1 + 32), (cudaStream_t)stream>>>(
-        tb, mx.as<const float>() + (int64_t)base * max_stride, max_stride, max_offset, bins, promotion,
-        counts.as<unsigned long long>() + (int64_t)base * (bins + 1));
-    FQ_LAUNCH_CHECK("hist_multi_kernel");
+    FQ_TRY(launch_hist_multi(tb, blocks, mx.as<const float>() + (int64_t)base * max_stride, max_stride, max_offset, bins,
+                             promotion, counts.as<unsigned long long>() + (int64_t)base * (bins + 1),
+                             flags.null ? nullptr : flags.as<int>() + base, (cudaStream_t)stream) == 0);
   }
   return 0;
 }
@@ -620,9 +712,10 @@ int fq_hist_accumulate_f32(const DLTensor* counts_, const DLTensor* hist_, int f
 }
 
 int fq_kl_search(const DLTensor* hist_, int levels, int min_bins, int bins, int promotion, const DLTensor* best_,
-                 const DLTensor* divergence_, void* stream) {
+                 const DLTensor* divergence_, const DLTensor* margin_, void* stream) {
   const char* who = "fq_kl_search";
-  View hist, best, dv;
+  View hist, best, dv, mg;
+  FQ_TRY(view_of(margin_, "fq_kl_search: margin", true, &mg));
   FQ_TRY(view_of(hist_, "fq_kl_search: hist", false, &hist));
   FQ_TRY(view_of(best_, "fq_kl_search: best", false, &best));
   FQ_TRY(view_of(divergence_, "fq_kl_search: divergence", false, &dv));
@@ -637,6 +730,8 @@ int fq_kl_search(const DLTensor* hist_, int levels, int min_bins, int bins, int 
   FQ_REQUIRE(dv.code == kDLFloat && dv.bits == 64 && dv.numel == (int64_t)layers * bins,
              "%s: divergence must be float64 [layers, bins] scratch", who);
   FQ_REQUIRE(promotion == FQ_PROMOTION_LEGACY || promotion == FQ_PROMOTION_NEP50, "%s: bad promotion", who);
+  FQ_REQUIRE(mg.null || (mg.code == kDLFloat && mg.bits == 64 && mg.numel == layers), "%s: margin must be float64 [layers=%d]",
+             who, layers);
   if (layers == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int ncand = bins - min_bins;
@@ -655,7 +750,8 @@ int fq_kl_search(const DLTensor* hist_, int levels, int min_bins, int bins, int 
                                                       dv.as<double>());
     FQ_LAUNCH_CHECK("kl_candidate_kernel");
   }
-  kl_argmin_kernel<<<layers, kThreads, 0, st>>>(dv.as<const double>(), min_bins, bins, best.as<int>());
+  kl_argmin_kernel<<<layers, kThreads, 0, st>>>(dv.as<const double>(), min_bins, bins, best.as<int>(),
+                                                mg.null ? nullptr : mg.as<double>());
   FQ_LAUNCH_CHECK("kl_argmin_kernel");
   return 0;
 }

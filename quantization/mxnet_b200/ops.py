@@ -318,21 +318,22 @@ def ema_update(state, cur, momentum=0.9, scalar_cur=True, promotion=None):
 
 
 # ---- K5 ------------------------------------------------------------------------------------------
-def hist_nonzero(x, max_, bins, counts, promotion=None):
-    """counts[bin] += 1 over the clipped non-zero elements.  distribution_calibrate.py:39-45."""
-    a, m, c = dl(_f32(x)), dl(max_), dl(counts)
-    check_call(_lib().fq_hist_nonzero(a.ptr, m.ptr, bins, _promo(promotion), c.ptr, current_stream()))
+def hist_nonzero(x, max_, bins, counts, promotion=None, bad_flag=None):
+    """counts[bin] += 1 over the clipped non-zero elements.  distribution_calibrate.py:39-45.
+    ``bad_flag`` (int32 [1]) is raised when the reference's asserts (:35-36) would fail on this tensor."""
+    a, m, c, f = dl(_f32(x)), dl(max_), dl(counts), dl(bad_flag)
+    check_call(_lib().fq_hist_nonzero(a.ptr, m.ptr, bins, _promo(promotion), c.ptr, ptr(f), current_stream()))
     return counts
 
 
-def hist_nonzero_multi(xs, maxes, max_stride, max_offset, bins, counts, promotion=None):
+def hist_nonzero_multi(xs, maxes, max_stride, max_offset, bins, counts, promotion=None, bad_flags=None):
     """Histograms of several layer inputs in one launch; ``counts`` is int64 [len(xs), bins + 1] and the
-    frozen max of ``xs[i]`` is ``maxes.view(-1)[i * max_stride + max_offset]``."""
+    frozen max of ``xs[i]`` is ``maxes.view(-1)[i * max_stride + max_offset]``; ``bad_flags``: int32 [len(xs)]."""
     args = [dl(_f32(x)) for x in xs]
     arr = (_ffi.P * len(args))(*[_ffi._c.pointer(a.t) for a in args])
-    m, c = dl(maxes), dl(counts)
+    m, c, f = dl(maxes), dl(counts), dl(bad_flags)
     check_call(_lib().fq_hist_nonzero_multi(arr, len(args), m.ptr, max_stride, max_offset, bins, _promo(promotion),
-                                            c.ptr, current_stream()))
+                                            c.ptr, ptr(f), current_stream()))
     return counts
 
 
@@ -343,18 +344,26 @@ def hist_accumulate(counts, hist, first, seen_last=None):
     return hist
 
 
-def kl_search(hist, levels, min_bins, bins, promotion=None, divergence=None):
+def kl_search(hist, levels, min_bins, bins, promotion=None, divergence=None, margin=None):
     """Best threshold bin per histogram (hist: [n_data] or [layers, n_data]).  :117-171.
 
-    Returns (best int32 [layers], divergence float64 [layers, bins])."""
+    Returns (best int32 [layers], divergence float64 [layers, bins]); ``margin`` (float64 [layers]) receives the
+    relative gap between the best and the runner-up divergence (see :data:`KL_TIE_MARGIN`)."""
     hist = _f32(hist, "hist")
     layers = 1 if hist.dim() == 1 else hist.shape[0]
     best = torch.empty(layers, dtype=torch.int32, device=hist.device)
     if divergence is None:
         divergence = torch.full((layers, bins), float("nan"), dtype=torch.float64, device=hist.device)
-    h, b, d = dl(hist), dl(best), dl(divergence)
-    check_call(_lib().fq_kl_search(h.ptr, levels, min_bins, bins, _promo(promotion), b.ptr, d.ptr, current_stream()))
+    h, b, d, m = dl(hist), dl(best), dl(divergence), dl(margin)
+    check_call(_lib().fq_kl_search(h.ptr, levels, min_bins, bins, _promo(promotion), b.ptr, d.ptr, ptr(m),
+                                   current_stream()))
     return best, divergence
+
+
+# A chosen bin whose divergence beats the runner-up by less than this (relative) is reported as a near-tie: the
+# divergences are float64 sums of p*log(p/q) and agree with NumPy's to ~1e-13 relative, so above the margin the
+# arg-min is the reference's; below it the reference's own answer hinges on the last place of its libm's log.
+KL_TIE_MARGIN = 1e-9
 
 
 def kl_threshold(best, fm_max, bins, out=None):

@@ -446,7 +446,7 @@ def sync_pending_stats(blocks, arenas):
     gathered = rec.get("gathered")
     if gathered is None or gathered.shape[0] != world or gathered.device != parts.device:
         gathered = rec["gathered"] = torch.empty((world,) + tuple(parts.shape), dtype=parts.dtype, device=parts.device)
-    torch.distributed.all_gather_into_tensor(gathered, parts, group=group)
+    torch.distributed.all_gather_into_tensor(gathered.view(-1), parts.view(-1), group=group)
     ops.channel_stats_finish(gathered, mean=arenas["running_mean"]["current"], var=arenas["running_var"]["current"])
     for m in todo:
         m._fq_stats_pending = False

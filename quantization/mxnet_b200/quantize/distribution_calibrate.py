@@ -11,8 +11,13 @@ the bit-identical histograms of a single-GPU run over the global batches.
 
 Reference behaviours kept: the first batch's max is frozen for all later batches (:97-101); zeros
 are ignored (:40); float32 accumulation in batch order (:47,:103-104); the 2049th bin when
-``max_ >= 256`` (and the ValueError when only some batches have it); the asserts of :35-36.
+``max_ >= 256`` (and the ValueError when only some batches have it); the asserts of :35-36, evaluated on
+EVERY batch by a flag the histogram kernel raises (negative value, NaN, non-positive max) and reported once
+at the end.  The hooked inputs are histogrammed after the forward, not copied at hook time; an input that is
+modified in place later in the same forward is detected (tensor version counter) and raises.
 """
+import warnings
+
 import numpy as np
 import torch
 from tqdm import tqdm
@@ -53,6 +58,7 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
     def _alloc(dev):
         state["hist"] = torch.zeros(n_blk, bins + 1, dtype=torch.float32, device=dev)
         state["minmax"] = torch.zeros(n_blk, 2, dtype=torch.float32, device=dev)
+        state["bad"] = torch.zeros(n_blk, dtype=torch.int32, device=dev)      # asserts of :35-36, every batch
         state["seen_hist"] = []
         # per-block flag "this batch produced a 2049th bin" (deferred length check), taken from the GLOBAL counts
         state["ring"] = fqdist.CountsRing(
@@ -65,7 +71,9 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
     hooks = []
     first_batch = {}        # block index -> inputs seen in batch 0 (kept until its max is known)
     called = set()
+    called_rows = []        # per batch: which blocks were called (the 2049th-bin check only looks at those)
     pending = {}            # block index -> this batch's input, for the single multi-tensor launch
+    versions = {}           # id(tensor) -> version at hook time: an in-place change before the launch is an error
     n_batches = 0
 
     def _collect(m, x, y):
@@ -74,12 +82,23 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
             _alloc(x.device)
         i = index[id(m)]
         called.add(i)
+        batch_called.add(i)
         if n_batches == 0:
             first_batch.setdefault(i, []).append(x)
+            versions[id(x)] = x._version
         elif x.data_ptr() % 16 == 0 and i not in pending:
             pending[i] = x          # histogrammed together with the other layers after the forward
+            versions[id(x)] = x._version
         else:
-            ops.hist_nonzero(x, state["minmax"][i, 1:2], bins, state["ring"].slot()[i])
+            ops.hist_nonzero(x, state["minmax"][i, 1:2], bins, state["ring"].slot()[i], bad_flag=state["bad"][i:i + 1])
+
+    def _unchanged(x):
+        if versions.get(id(x), x._version) != x._version:
+            raise RuntimeError("a hooked layer input was modified in place after its block ran and before its "
+                               "histogram was taken (the reference copies it at hook time, "
+                               "distribution_calibrate.py:80); make that op out-of-place for calibration")
+        return x
+    batch_called = set()
     for blk in quantized_blocks:
         hooks.append(blk.register_forward_hook(_collect))
 
@@ -92,30 +111,37 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
                     # First chunk: min/max of everything the block saw, then its histogram
                     for i, xs in first_batch.items():
                         mm = state["minmax"][i]
-                        ops.minmax(xs[0], out=mm)
+                        ops.minmax(_unchanged(xs[0]), out=mm)
                         for extra in xs[1:]:
-                            mm2 = ops.minmax(extra)
+                            mm2 = ops.minmax(_unchanged(extra))
                             mm[0:1].copy_(torch.minimum(mm[0:1], mm2[0:1]))
                             mm[1:2].copy_(torch.maximum(mm[1:2], mm2[1:2]))
                     fqdist.sync_first_batch_minmax(state["minmax"], group)
                     for i, xs in first_batch.items():
                         for x in xs:
-                            ops.hist_nonzero(x, state["minmax"][i, 1:2], bins, state["ring"].slot()[i])
+                            ops.hist_nonzero(x, state["minmax"][i, 1:2], bins, state["ring"].slot()[i],
+                                             bad_flag=state["bad"][i:i + 1])
                     first_batch.clear()
                 if pending:
                     # every layer of the batch in ONE launch, blocks shared out by tensor size
                     order = sorted(pending)
                     if order == list(range(n_blk)):
-                        ops.hist_nonzero_multi([pending[i] for i in order], state["minmax"], 2, 1, bins,
-                                               state["ring"].slot())
+                        ops.hist_nonzero_multi([_unchanged(pending[i]) for i in order], state["minmax"], 2, 1, bins,
+                                               state["ring"].slot(), bad_flags=state["bad"])
                     else:
                         for i in order:
-                            ops.hist_nonzero(pending[i], state["minmax"][i, 1:2], bins, state["ring"].slot()[i])
+                            ops.hist_nonzero(_unchanged(pending[i]), state["minmax"][i, 1:2], bins,
+                                             state["ring"].slot()[i], bad_flag=state["bad"][i:i + 1])
                     pending.clear()
+                versions.clear()
                 if state:
                     # hist_collector[m] = last_hist + hist.astype(float32), all blocks in one launch; with
                     # ranks, one sum-all-reduce per `ring_slots` batches and the adds replayed in batch order
                     state["ring"].commit()
+                    row = np.zeros(n_blk, bool)
+                    row[list(batch_called)] = True
+                    called_rows.append(row)
+                batch_called.clear()
                 n_batches += 1
                 pbar.update(1)
             if state:
@@ -133,12 +159,20 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
     hist = state["hist"].cpu().numpy()
     minmax = state["minmax"].cpu().numpy()
     seen = torch.cat(state["seen_hist"]).cpu().numpy() if state["seen_hist"] else np.zeros((0, n_blk), np.int32)
+    bad = state["bad"].cpu().numpy()
+    if group is not None:       # an assert that fires on any rank fires on all
+        t = state["bad"].clone()
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=group)
+        bad = t.cpu().numpy()
+    was_called = np.stack(called_rows) if called_rows else np.zeros((0, n_blk), bool)
     for i, m in enumerate(quantized_blocks):
         if i not in called:
             continue
         assert minmax[i, 0] >= 0., "Activation should >=0"
         assert minmax[i, 1] > 0, "Bad distribution: all zero-value"
-        col = seen[:, i]
+        # the same two asserts on the later batches (and NaN anywhere), from the kernels' device flags
+        assert not bad[i], "Activation should >=0"
+        col = seen[:len(was_called), i][was_called[:len(seen), i]]     # batches in which this block ran
         if col.any() and not col.all():
             # np.bincount gave 2049 bins for some batches and 2048 for others: `last_hist + hist` raises
             raise ValueError("operands could not be broadcast together with shapes (%d,) (%d,)" % (bins, bins + 1))
@@ -208,14 +242,29 @@ def kl_calibrate(data, levels, min_bins, bins):
     assert min_bins >= levels, f"min_bins should be greater than levels ({min_bins} vs. {levels})"
     if isinstance(data, np.ndarray):
         data = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).cuda()
-    best, _ = ops.kl_search(data.reshape(1, -1), levels, min_bins, bins)
+    margin = torch.empty(1, dtype=torch.float64, device=data.device)
+    best, _ = ops.kl_search(data.reshape(1, -1), levels, min_bins, bins, margin=margin)
+    _flag_near_ties(best, margin)
     return int(best[0])
 
 
-def kl_calibrate_all(hists, levels, min_bins, bins, fm_max=None):
+def _flag_near_ties(best, margin):
+    """Warn when a chosen bin wins by less than ops.KL_TIE_MARGIN (relative): see fq.h fq_kl_search."""
+    m = margin.cpu().numpy()
+    tied = np.flatnonzero(m < ops.KL_TIE_MARGIN)
+    if tied.size:
+        b = best.cpu().numpy()
+        warnings.warn("KL threshold search: near-tie between candidate bins for layer(s) %s (best bin(s) %s, relative "
+                      "margin(s) %s): the reference's own choice here depends on its math library's rounding"
+                      % (tied.tolist(), b[tied].tolist(), m[tied].tolist()), RuntimeWarning, stacklevel=3)
+    return m
+
+
+def kl_calibrate_all(hists, levels, min_bins, bins, fm_max=None, check_ties=True):
     """All layers at once: ``hists`` is a [layers, n] tensor (or a hist_collector from
     :func:`collect_feature_maps`).  Returns int32 best bins on the device and, when ``fm_max`` is
-    given, the float32 thresholds ``(best + 0.5) * (fm_max / bins)`` (simulate_quantization.py:310)."""
+    given, the float32 thresholds ``(best + 0.5) * (fm_max / bins)`` (simulate_quantization.py:310).
+    ``check_ties`` reads back one float64 per layer and warns about near-ties (ops.KL_TIE_MARGIN)."""
     assert min_bins >= levels, f"min_bins should be greater than levels ({min_bins} vs. {levels})"
     if isinstance(hists, _Collector):
         dev_h = hists.device
@@ -225,11 +274,18 @@ def kl_calibrate_all(hists, levels, min_bins, bins, fm_max=None):
             n = lens.pop()
             hists = dev_h[:, :n].contiguous()
         else:
-            outs = [kl_calibrate_all(dev_h[i:i + 1, :len(hists[m])].contiguous(), levels, min_bins, bins)
+            # blocks the calibration never reached have no histogram: their row keeps best = min_bins
+            outs = [kl_calibrate_all(dev_h[i:i + 1, :len(hists[m])].contiguous(), levels, min_bins, bins,
+                                     check_ties=check_ties)
+                    if m in hists else torch.full((1,), min_bins, dtype=torch.int32, device=dev_h.device)
                     for i, m in enumerate(hists.order)]
             best = torch.cat(outs)
             return (best, ops.kl_threshold(best, _max_of(fm_max), bins)) if fm_max is not None else best
-    best, _ = ops.kl_search(hists, levels, min_bins, bins)
+    margin = torch.empty(1 if hists.dim() == 1 else hists.shape[0], dtype=torch.float64, device=hists.device) \
+        if check_ties else None
+    best, _ = ops.kl_search(hists, levels, min_bins, bins, margin=margin)
+    if check_ties:
+        _flag_near_ties(best, margin)
     if fm_max is None:
         return best
     return best, ops.kl_threshold(best, _max_of(fm_max), bins)

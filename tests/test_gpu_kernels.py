@@ -765,3 +765,61 @@ def test_wino_backward_matches_oracle(ops, name):
     G, GI, GTI = O.winograd_matrices(name)
     got = ops.wino_backward(dev(g), dev(G), dev(GI), dev(GTI))
     bits_equal(host(got), O.wino_backward(g, name))
+
+
+def _near_tie_histograms():
+    """Two histograms that differ in ONE ULP of ONE bin and whose KL arg-mins are 259 bins apart: a mix of the
+    'relu' and 'lognormal' recipes at the point where the best candidate switches from 1792 to 1533, fine-tuned on
+    bin 1063 by bisection against the oracle (found offline; the oracle re-checks both below)."""
+    cases = R.kl_hist_cases()
+    hA, hB = cases["relu"].astype(np.float64), cases["lognormal"].astype(np.float64)
+    hB = hB * (hA.sum() / hB.sum())
+    t = 0.5085390468650866
+    h = ((1 - t) * hA + t * hB).astype(F32)
+    out = []
+    for bits in (0x40dc07d8, 0x40dc07d7):
+        g = h.copy()
+        g[1063] = np.uint32(bits).view(F32)
+        out.append(g)
+    return out
+
+
+def test_kl_search_reports_the_margin_of_a_constructed_near_tie(ops):
+    """north_star: chosen KL bins bit-exact.  The divergences agree with NumPy's to ~1e-13 relative, so the arg-min
+    can only differ where two candidates are closer than that; fq_kl_search reports the relative gap to the
+    runner-up and the Python layer flags gaps < 1e-9.  Here the gap is 8e-11 / 3e-11 and the choice flips with one
+    ULP of one bin -- the kernel follows the oracle on both sides of the flip and flags both."""
+    import warnings
+    from quantization.mxnet_b200.quantize import distribution_calibrate as DC
+    prev = ops.get_promotion()
+    ops.set_promotion("nep50")          # the regime the histograms were tuned in (and the golden fixtures use)
+    try:
+        _near_tie_body(ops, DC, warnings)
+    finally:
+        ops.set_promotion(prev)
+
+
+def _near_tie_body(ops, DC, warnings):
+    want_best = []
+    for h in _near_tie_histograms():
+        div = O.kl_divergences(h, 256, 256, R.BINS, "nep50")
+        d = np.where(np.isnan(div), np.inf, div)
+        o = np.argsort(d, kind="stable")
+        want_margin = (d[o[1]] - d[o[0]]) / abs(d[o[0]])
+        assert sorted(o[:2].tolist()) == [1533, 1792] and want_margin < 1e-10
+        margin = torch.empty(1, dtype=torch.float64, device="cuda")
+        best, got = ops.kl_search(dev(h), 256, 256, R.BINS, promotion="nep50", margin=margin)
+        assert abs(float(margin[0]) - want_margin) < 1e-12, (float(margin[0]), want_margin)
+        assert int(best[0]) == int(o[0]) == O.kl_calibrate(h, 256, 256, R.BINS, "nep50")
+        want_best.append(int(o[0]))
+        with pytest.warns(RuntimeWarning, match="near-tie"):
+            assert DC.kl_calibrate(h, 256, 256, R.BINS) in (1533, 1792)
+    assert want_best == [1792, 1533]
+    # an ordinary histogram has a comfortable margin and raises nothing
+    h = R.kl_hist_cases()["relu"]
+    margin = torch.empty(1, dtype=torch.float64, device="cuda")
+    ops.kl_search(dev(h), 256, 256, R.BINS, promotion="nep50", margin=margin)
+    assert float(margin[0]) > 1e-3
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        assert DC.kl_calibrate(h, 256, 256, R.BINS) == 1792
