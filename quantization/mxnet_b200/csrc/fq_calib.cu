@@ -96,11 +96,26 @@ __device__ __forceinline__ void hist_zero(unsigned int* sh, int bins) {
   for (int b = threadIdx.x; b < bins + 1 + 32; b += blockDim.x) sh[b] = 0u;
   __syncthreads();
 }
-__device__ __forceinline__ void hist_flush(const unsigned int* sh, int bins, unsigned long long* __restrict__ counts) {
+// counts: 64-bit, or 32-bit (`wide` == 0) for callers whose per-bin totals stay below 2^32 -- a data-parallel
+// calibration then moves half the bytes in its sum-all-reduce (quantization/mxnet_b200/dist.py CountsRing)
+struct CountsOut {
+  void* p;
+  int wide;
+  __host__ __device__ __forceinline__ CountsOut at(int64_t off) const {
+    CountsOut o;
+    o.p = wide ? (void*)((unsigned long long*)p + off) : (void*)((unsigned int*)p + off);
+    o.wide = wide;
+    return o;
+  }
+};
+__device__ __forceinline__ void hist_flush(const unsigned int* sh, int bins, CountsOut counts) {
   __syncthreads();
   for (int b = threadIdx.x; b <= bins; b += blockDim.x) {
     const unsigned int c = sh[b];
-    if (c) atomicAdd(&counts[b], (unsigned long long)c);
+    if (c) {
+      if (counts.wide) atomicAdd((unsigned long long*)counts.p + b, (unsigned long long)c);
+      else atomicAdd((unsigned int*)counts.p + b, c);
+    }
   }
 }
 
@@ -159,8 +174,7 @@ struct HistBatch {
 template <bool CHECK>
 __global__ void __launch_bounds__(kHistThreads, kHistBlocksPerSM)
     hist_multi_kernel(const __grid_constant__ HistBatch tb, const float* __restrict__ maxes, int max_stride,
-                      int max_offset, int bins, int promotion, unsigned long long* __restrict__ counts,
-                      int* __restrict__ bad_flags) {
+                      int max_offset, int bins, int promotion, CountsOut counts, int* __restrict__ bad_flags) {
   extern __shared__ unsigned int sh[];     // bins + 1 private counters, 32 trash counters
   int t = 0;
   while (t + 1 < tb.count && (int)blockIdx.x >= tb.first_block[t + 1]) ++t;
@@ -175,13 +189,13 @@ __global__ void __launch_bounds__(kHistThreads, kHistBlocksPerSM)
   else if (CHECK)
     mc.m = -1.f;                  // `assert max_ > 0` (:36); a NaN max lands here as well
   if (CHECK) mc.publish(bad_flags + t);
-  hist_flush(sh, bins, counts + (int64_t)t * (bins + 1));
+  hist_flush(sh, bins, counts.at((int64_t)t * (bins + 1)));
 }
 
 // Any alignment: grid-stride scalar loads (views at odd offsets; never the hot path).
 __global__ void __launch_bounds__(kThreads) hist_unaligned_kernel(const float* __restrict__ x, int64_t n,
                                                                   const float* __restrict__ max_dev, int bins,
-                                                                  int promotion, unsigned long long* __restrict__ counts,
+                                                                  int promotion, CountsOut counts,
                                                                   int* __restrict__ bad_flag) {
   extern __shared__ unsigned int sh[];
   const float max_ = __ldg(max_dev);
@@ -205,15 +219,23 @@ __global__ void __launch_bounds__(kThreads) hist_unaligned_kernel(const float* _
 // counts holds `steps` consecutive batches ([steps, nb]); they are folded in batch order, so that a data-parallel
 // run may all-reduce the integer counts of many batches at once and still replay the reference's per-batch
 // float32 accumulation exactly.
-__global__ void hist_accumulate_kernel(unsigned long long* __restrict__ counts, float* __restrict__ hist, int nb,
-                                       int steps, int first, int* __restrict__ seen_last) {
+__global__ void hist_accumulate_kernel(CountsOut counts, float* __restrict__ hist, int nb, int steps, int first,
+                                       int* __restrict__ seen_last) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   float h = first ? 0.f : hist[b];
   bool any = false;
   for (int s = 0; s < steps; ++s) {
-    const unsigned long long c = counts[(int64_t)s * nb + b];
-    counts[(int64_t)s * nb + b] = 0ull;
+    unsigned long long c;
+    if (counts.wide) {
+      unsigned long long* q = (unsigned long long*)counts.p + (int64_t)s * nb + b;
+      c = *q;
+      *q = 0ull;
+    } else {
+      unsigned int* q = (unsigned int*)counts.p + (int64_t)s * nb + b;
+      c = *q;
+      *q = 0u;
+    }
     const float f = __ull2float_rn(c);                         // hist.astype("float32")  (:47)
     h = (first && s == 0) ? f : __fadd_rn(h, f);               // last_hist + hist        (:103-104)
     any |= (c != 0ull);
@@ -600,7 +622,7 @@ static int hist_share_blocks(HistBatch* tb, int budget) {
 }
 
 static int launch_hist_multi(const HistBatch& tb, int blocks, const float* maxes, int max_stride, int max_offset,
-                             int bins, int promotion, unsigned long long* counts, int* flags, cudaStream_t st) {
+                             int bins, int promotion, CountsOut counts, int* flags, cudaStream_t st) {
   const size_t smem = sizeof(unsigned int) * (bins + 1 + 32);
   if (flags != nullptr)
     hist_multi_kernel<true><<<blocks, kHistThreads, smem, st>>>(tb, maxes, max_stride, max_offset, bins, promotion,
@@ -610,6 +632,17 @@ static int launch_hist_multi(const HistBatch& tb, int blocks, const float* maxes
                                                                  counts, nullptr);
   FQ_LAUNCH_CHECK("hist_multi_kernel");
   return 0;
+}
+
+// counts tensors: (u)int64 or (u)int32, `n` elements
+static bool counts_ok(const char* who, const View& c, int64_t n, CountsOut* out) {
+  if ((c.code == kDLInt || c.code == kDLUInt) && (c.bits == 64 || c.bits == 32) && c.numel == n) {
+    out->p = c.data;
+    out->wide = c.bits == 64;
+    return true;
+  }
+  set_error("%s: counts must be (u)int64 or (u)int32 with %lld elements", who, (long long)n);
+  return false;
 }
 
 static bool flags_ok(const char* who, const View& f, int64_t n) {
@@ -629,8 +662,9 @@ int fq_hist_nonzero(const DLTensor* x_, const DLTensor* max__, int bins, int pro
   FQ_TRY(view_of(counts_, "fq_hist_nonzero: counts", false, &counts));
   FQ_REQUIRE(x.is_f32() && mx.is_f32() && mx.numel >= 1, "fq_hist_nonzero: x and max_ must be float32");
   FQ_REQUIRE(bins >= 1 && bins <= 8192, "fq_hist_nonzero: bins=%d outside [1, 8192]", bins);
-  FQ_REQUIRE((counts.code == kDLInt || counts.code == kDLUInt) && counts.bits == 64 && counts.numel == bins + 1,
-             "fq_hist_nonzero: counts must be (u)int64 [bins+1]");
+  CountsOut cout_;
+  FQ_TRY(counts_ok("fq_hist_nonzero", counts, bins + 1, &cout_));
+  FQ_REQUIRE(cout_.wide || x.numel < (1LL << 32), "fq_hist_nonzero: 32-bit counts need fewer than 2^32 elements");
   FQ_REQUIRE(promotion == FQ_PROMOTION_LEGACY || promotion == FQ_PROMOTION_NEP50, "fq_hist_nonzero: bad promotion");
   if (x.numel == 0) return 0;
   const size_t smem = sizeof(unsigned int) * (bins + 1 + 32);
@@ -640,13 +674,13 @@ int fq_hist_nonzero(const DLTensor* x_, const DLTensor* max__, int bins, int pro
     tb.n[0] = x.numel;
     tb.count = 1;
     const int blocks = hist_share_blocks(&tb, sm_count() * kHistBlocksPerSM);
-    FQ_TRY(launch_hist_multi(tb, blocks, mx.as<const float>(), 1, 0, bins, promotion, counts.as<unsigned long long>(),
+    FQ_TRY(launch_hist_multi(tb, blocks, mx.as<const float>(), 1, 0, bins, promotion, cout_,
                              flag.null ? nullptr : flag.as<int>(), (cudaStream_t)stream) == 0);
   } else {
     const int64_t b = (x.numel + kThreads - 1) / kThreads;
     const int grid = (int)(b > sm_count() * 8 ? sm_count() * 8 : b);
     hist_unaligned_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
-        x.as<const float>(), x.numel, mx.as<const float>(), bins, promotion, counts.as<unsigned long long>(),
+        x.as<const float>(), x.numel, mx.as<const float>(), bins, promotion, cout_,
         flag.null ? nullptr : flag.as<int>());
     FQ_LAUNCH_CHECK("hist_unaligned_kernel");
   }
@@ -667,9 +701,8 @@ int fq_hist_nonzero_multi(const DLTensor* const* xs, int n_tensors, const DLTens
   FQ_REQUIRE(mx.is_f32() && max_stride >= 1 && max_offset >= 0 &&
                  mx.numel >= (int64_t)(n_tensors - 1) * max_stride + max_offset + 1,
              "%s: maxes must be float32 with an entry for every tensor", who);
-  FQ_REQUIRE((counts.code == kDLInt || counts.code == kDLUInt) && counts.bits == 64 &&
-                 counts.numel == (int64_t)n_tensors * (bins + 1),
-             "%s: counts must be (u)int64 [n_tensors, bins+1]", who);
+  CountsOut cout_;
+  FQ_TRY(counts_ok(who, counts, (int64_t)n_tensors * (bins + 1), &cout_));
   FQ_REQUIRE(promotion == FQ_PROMOTION_LEGACY || promotion == FQ_PROMOTION_NEP50, "%s: bad promotion", who);
   const int budget = sm_count() * kHistBlocksPerSM;
   for (int base = 0; base < n_tensors; base += FQ_MAX_BATCH) {
@@ -679,6 +712,7 @@ int fq_hist_nonzero_multi(const DLTensor* const* xs, int n_tensors, const DLTens
       View x;
       FQ_TRY(view_of(xs[base + i], "fq_hist_nonzero_multi: x", false, &x));
       FQ_REQUIRE(x.is_f32() && aligned16(x.data), "%s: tensor %d must be float32 and 16-byte aligned", who, base + i);
+      FQ_REQUIRE(cout_.wide || x.numel < (1LL << 32), "%s: 32-bit counts need fewer than 2^32 elements per tensor", who);
       tb.x[i] = x.as<const float>();
       tb.n[i] = x.numel;
     }
@@ -686,7 +720,7 @@ int fq_hist_nonzero_multi(const DLTensor* const* xs, int n_tensors, const DLTens
     const int blocks = hist_share_blocks(&tb, budget);
     if (blocks == 0) continue;
     FQ_TRY(launch_hist_multi(tb, blocks, mx.as<const float>() + (int64_t)base * max_stride, max_stride, max_offset, bins,
-                             promotion, counts.as<unsigned long long>() + (int64_t)base * (bins + 1),
+                             promotion, cout_.at((int64_t)base * (bins + 1)),
                              flags.null ? nullptr : flags.as<int>() + base, (cudaStream_t)stream) == 0);
   }
   return 0;
@@ -698,14 +732,18 @@ int fq_hist_accumulate_f32(const DLTensor* counts_, const DLTensor* hist_, int f
   FQ_TRY(view_of(counts_, "fq_hist_accumulate_f32: counts", false, &counts));
   FQ_TRY(view_of(hist_, "fq_hist_accumulate_f32: hist", false, &hist));
   FQ_TRY(view_of(seen_last_, "fq_hist_accumulate_f32: seen_last", true, &seen));
-  FQ_REQUIRE((counts.code == kDLInt || counts.code == kDLUInt) && counts.bits == 64, "fq_hist_accumulate_f32: counts must be (u)int64");
+  FQ_REQUIRE((counts.code == kDLInt || counts.code == kDLUInt) && (counts.bits == 64 || counts.bits == 32),
+             "fq_hist_accumulate_f32: counts must be (u)int64 or (u)int32");
+  CountsOut cout_;
+  cout_.p = counts.data;
+  cout_.wide = counts.bits == 64;
   FQ_REQUIRE(hist.is_f32() && hist.numel > 0 && counts.numel >= hist.numel && counts.numel % hist.numel == 0 &&
                  hist.numel <= INT32_MAX && counts.numel / hist.numel <= INT32_MAX,
              "fq_hist_accumulate_f32: hist must be float32 [n] and counts [steps, n]");
   FQ_REQUIRE(seen.null || (seen.code == kDLInt && seen.bits == 32 && seen.numel >= 1), "fq_hist_accumulate_f32: seen_last must be int32");
   const int nb = (int)hist.numel;
   hist_accumulate_kernel<<<(nb + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      counts.as<unsigned long long>(), hist.as<float>(), nb, (int)(counts.numel / hist.numel), first,
+      cout_, hist.as<float>(), nb, (int)(counts.numel / hist.numel), first,
       seen.null ? nullptr : seen.as<int>());
   FQ_LAUNCH_CHECK("hist_accumulate_kernel");
   return 0;

@@ -3,7 +3,8 @@ weights replicated.  Every statistic on this path is a max, an integ
 per-sample maxima, so the collectives below make an N-GPU run reproduce the single-GPU result:
 
   first-batch maxima (KL)      all_reduce(MAX)   [L]          exact
-  per-batch histogram counts   all_reduce(SUM)   [S, L, bins+1]  exact (int64); S (8) batches per collective
+  per-batch histogram counts   all_reduce(SUM)   [S, L, bins+1]  exact (32-bit on the wire when the totals fit, else
+                                                              int64); S (8) batches per collective, asynchronous
   per-sample input maxima      all_gather        [N]          exact; the Kahan mean then runs on every rank
   QAT gradients                all_reduce(SUM)/R one flat fp32 bucket
 
@@ -63,7 +64,7 @@ def sync_counts(counts, group=None):
 
 
 class CountsRing:
-    """Per-batch integer counts of up to ``slots`` batches, all-reduced TOGETHER.
+    """Per-batch integer counts of up to ``slots`` batches, all-reduced TOGETHER and off the critical path.
 
     The reference adds ``float32(counts)`` of one batch after the other (distribution_calibrate.py:47,103-104),
     so the counts of a global batch must be summed over the ranks before they are folded -- but nothing needs
@@ -71,28 +72,47 @@ class CountsRing:
     batch order after ONE collective per ``slots`` batches gives the same bits as an all-reduce per batch, without
     a latency-bound collective in every step (and one fold launch per ``slots`` batches instead of one per batch).
 
+    Two rings take turns: while the histogram kernels fill one, the other one's sum-all-reduce runs asynchronously on
+    the communicator's stream; its fold is queued when the next ring is full (or at ``flush()``), so no histogram
+    launch ever waits for a collective.  On the wire the counts are 32-bit whenever the per-bin totals of a global
+    batch provably fit (``max_count`` < 2^32 summed over the ranks): half the message.  Both are invisible in the
+    result (integer sums are exact; the folds still run in batch order).
+
     ``accumulate(counts_2d [S, n], first)`` is the fold (ops.hist_accumulate on the GPU); ``on_reduced(counts_3d)``
     sees the global counts before they are folded (deferred 2049th-bin check).
     """
 
-    def __init__(self, n_layers, n_bins, device, accumulate, group=None, slots=8, on_reduced=None):
-        self.group = active_group(group)
+    def __init__(self, n_layers, n_bins, device, accumulate, group=None, slots=8, on_reduced=None, max_count=None,
+                 local=False):
+        self.group = None if local else active_group(group)      # local: no exchange even with ranks present
         self.slots = max(1, int(slots))
-        self.ring = torch.zeros(self.slots, n_layers, n_bins, dtype=torch.int64, device=device)
+        world = dist.get_world_size(self.group) if self.group is not None else 1
+        # max_count: an upper bound on one rank's count in any bin of any batch (= its largest layer input)
+        narrow = max_count is not None and int(max_count) * world < (1 << 32) and torch.device(device).type == "cuda"
+        self.dtype = torch.int32 if narrow else torch.int64     # int32 carries uint32 sums (two's complement add)
+        self.rings = [torch.zeros(self.slots, n_layers, n_bins, dtype=self.dtype, device=device)
+                      for _ in range(2 if self.group is not None else 1)]
+        self.cur = 0
         self.used = 0
         self.flushed = 0
         self.accumulate = accumulate
         self.on_reduced = on_reduced
+        self._inflight = None          # (work handle, ring index, slots used)
+
+    @property
+    def ring(self):
+        return self.rings[self.cur]
 
     def prime(self, slot_counts=None):
-        """Run the collective once on the (all-zero) ring for every message size that will occur.  NCCL connects an
+        """Run the collective once on the (all-zero) rings for every message size that will occur.  NCCL connects an
         algorithm/protocol the first time a message size selects it (runtime connect): on 8 GPUs the first 14 MB
         all-reduce of a calibration took 11 ms instead of ~0.1 ms.  Zeros stay zeros, so this changes nothing."""
         if self.group is None:
             return
-        assert self.used == 0, "prime() must not see collected counts"
+        assert self.used == 0 and self._inflight is None, "prime() must not see collected counts"
         for n in sorted({min(max(int(c), 1), self.slots) for c in (slot_counts or [self.slots])}):
-            dist.all_reduce(self.ring[:n], op=dist.ReduceOp.SUM, group=self.group)
+            for ring in self.rings:
+                dist.all_reduce(ring[:n], op=dist.ReduceOp.SUM, group=self.group)
 
     def slot(self):
         """[n_layers, n_bins] zeroed counters for the batch being collected."""
@@ -102,19 +122,41 @@ class CountsRing:
         """The current slot holds a complete batch."""
         self.used += 1
         if self.used == self.slots:
-            self.flush()
+            self._rotate()
 
-    def flush(self):
-        if self.used == 0:
+    def _retire(self):
+        """Fold the ring whose all-reduce was started earlier (the current stream waits for it; the host does not)."""
+        if self._inflight is None:
             return
-        part = self.ring[:self.used]
-        if self.group is not None:
-            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
+        work, idx, used = self._inflight
+        self._inflight = None
+        if work is not None:
+            work.wait()
+        part = self.rings[idx][:used]
         if self.on_reduced is not None:
             self.on_reduced(part)
-        self.accumulate(part.view(self.used, -1), self.flushed == 0)     # zeroes the slots again
-        self.flushed += self.used
+        self.accumulate(part.view(used, -1), self.flushed == 0)     # zeroes the slots again
+        self.flushed += used
+
+    def _rotate(self):
+        if self.used == 0:
+            return
+        self._retire()                  # batch order: the older ring is folded first (and is free again)
+        part = self.ring[:self.used]
+        work = None
+        if self.group is not None:
+            work = dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._inflight = (work, self.cur, self.used)
+        if self.group is None:
+            self._retire()              # single process: nothing to overlap, fold right away
+        else:
+            self.cur = 1 - self.cur
         self.used = 0
+
+    def flush(self):
+        """Everything collected so far is folded into the histograms when this returns (stream order)."""
+        self._rotate()
+        self._retire()
 
 
 def gather_per_sample(per_sample, group=None):

@@ -60,9 +60,15 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
         state["minmax"] = torch.zeros(n_blk, 2, dtype=torch.float32, device=dev)
         state["bad"] = torch.zeros(n_blk, dtype=torch.int32, device=dev)      # asserts of :35-36, every batch
         state["seen_hist"] = []
-        # per-block flag "this batch produced a 2049th bin" (deferred length check), taken from the GLOBAL counts
+        state["dev"] = dev
+
+    def _alloc_ring(max_numel):
+        # per-block flag "this batch produced a 2049th bin" (deferred length check), taken from the GLOBAL counts.
+        # Data parallel: 32-bit counts on the wire while no bin of a global batch can reach 2^32 (max_numel bounds
+        # one rank's count per bin; the hook re-checks every later input against it).
+        state["max_numel"] = max_numel if group is not None else None
         state["ring"] = fqdist.CountsRing(
-            n_blk, bins + 1, dev, group=group, slots=ring_slots,
+            n_blk, bins + 1, state["dev"], group=group, slots=ring_slots, max_count=state["max_numel"],
             accumulate=lambda c, first: ops.hist_accumulate(c.reshape(-1), state["hist"].view(-1), first, None),
             on_reduced=lambda c: state["seen_hist"].append((c[:, :, bins] != 0).to(torch.int32)))
         state["ring"].prime()        # data parallel: connect NCCL for this message size outside the batch loop
@@ -83,6 +89,10 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
         i = index[id(m)]
         called.add(i)
         batch_called.add(i)
+        if state.get("max_numel") is not None and x.numel() > state["max_numel"] and \
+                state["ring"].dtype == torch.int32:
+            raise RuntimeError("a layer input of %d elements is larger than any of the first batch (%d): the 32-bit "
+                               "count exchange was sized for the first batch" % (x.numel(), state["max_numel"]))
         if n_batches == 0:
             first_batch.setdefault(i, []).append(x)
             versions[id(x)] = x._version
@@ -117,6 +127,7 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
                             mm[0:1].copy_(torch.minimum(mm[0:1], mm2[0:1]))
                             mm[1:2].copy_(torch.maximum(mm[1:2], mm2[1:2]))
                     fqdist.sync_first_batch_minmax(state["minmax"], group)
+                    _alloc_ring(max(x.numel() for xs in first_batch.values() for x in xs))
                     for i, xs in first_batch.items():
                         for x in xs:
                             ops.hist_nonzero(x, state["minmax"][i, 1:2], bins, state["ring"].slot()[i],

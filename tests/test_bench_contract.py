@@ -22,7 +22,14 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
     assert d["config"]["workload"].startswith("mobilenet1.0 KL calibration")
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    # the reference's own file when build() has staged it under oracle/_ref/, else the oracle port
+    staged = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "distribution_calibrate.py"))
+    assert cb["kind"] == ("reference" if staged else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    # like for like with the GPU arm: same config block (no extra keys), one KL search amortised over K batches
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(1) and "amortised over K=1 batches of 128" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
 
