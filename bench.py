@@ -630,6 +630,7 @@ def run_b200(args):
         dist.all_gather_object(clock_all, clock_info)
     else:
         clock_all = [clock_info]
+    clocks_e2e = ClockSampler(local).start() if rank == 0 else None     # a second window: parity + e2e legs
     min_margin = float(margin.min())
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -712,6 +713,10 @@ def run_b200(args):
                        "api": "quantize.distribution_calibrate.collect_feature_maps + kl_calibrate_all on the torch "
                               "mobilenet1.0 (fp32 cuDNN forward included), pinned host images"}
         barrier()
+    if clocks_e2e is not None:
+        c2 = clocks_e2e.stop()
+        line["clocks"]["e2e_window"] = c2
+        line["clocks"]["reasons"] = sorted(set(line["clocks"]["reasons"]) | set(c2.get("reasons", [])))
     del net, X
     torch.cuda.empty_cache()
 

@@ -570,8 +570,13 @@ __global__ void kl_argmin_kernel(const double* __restrict__ div_all, int min_bin
   }
   if (threadIdx.x == 0) {
     best[blockIdx.x] = (sv[0] < INFINITY) ? si[0] : min_bins;
-    if (margin != nullptr)
-      margin[blockIdx.x] = (sv[0] < INFINITY && s2[0] < INFINITY) ? (s2[0] - sv[0]) / fmax(fabs(sv[0]), 1e-300) : INFINITY;
+    if (margin != nullptr) {
+      // both exactly 0: P == Q term by term for both candidates (a histogram with one occupied bin), and log(1) is
+      // 0 in every libm -- an exact tie that the reference's "first strict minimum" resolves the same way
+      const bool exact_zero_tie = sv[0] == 0.0 && s2[0] == 0.0;
+      margin[blockIdx.x] = (sv[0] < INFINITY && s2[0] < INFINITY && !exact_zero_tie)
+                               ? (s2[0] - sv[0]) / fmax(fabs(sv[0]), 1e-300) : INFINITY;
+    }
   }
 }
 

@@ -8,6 +8,8 @@
 //       12 B/element worst case, 8 B/element of HBM traffic when the tensor fits in L2.)
 //  fq_quant_weight   : optional BN fold -> per-row absmax -> scale -> quantise      (weights)
 //      reference: convert_conv2d.py:47-51, 70-95; convert_dense.py:52-63; merge_bn.py:65-74
+#include <stdlib.h>
+
 #include "fq_fused.cuh"
 
 namespace fq {
@@ -139,11 +141,15 @@ __global__ void __launch_bounds__(kThreads, 6) input_path_kernel(InputArgs a) {
   if (threadIdx.x == 0) a.ws->ticket = 0;
 }
 
-// Offline range + tracking for long rows (L >= one tile, so a tile meets at most two rows): one tile per
-// block like the plain quantiser, the per-row maxima ride along -- block reduction, then an atomicMax only
-// when the tile beats the row's running maximum (after the first few tiles almost never).
-__global__ void __launch_bounds__(kThreads, 6) offline_track_tiles_kernel(InputArgs a) {
-  __shared__ float red[2][kThreads / 32];
+// Offline range + tracking for long rows (L >= one tile, so a tile meets at most two rows).  A block streams
+// `tiles_per_block` CONSECUTIVE tiles like the plain quantiser and keeps the running |x| maximum of the row it is in
+// in registers; only when the row changes (or the block ends) does it reduce over the block and issue ONE atomicMax.
+// The first version reduced and touched its row slot once per tile: 2048 blocks per row reading (and sometimes
+// atomically updating) one address was visible at streaming speed (6.3 instead of 6.9 TB/s at 2^30 elements).
+constexpr int kTrackTilesMax = 8;
+
+__global__ void __launch_bounds__(kThreads, 5) offline_track_tiles_kernel(InputArgs a, int tiles_per_block) {
+  __shared__ float red[32];
   __shared__ float qp[4];
   if (threadIdx.x == 0)
     compute_qparams(a.fin.input_max[0], a.fin.bits, a.fin.is_signed, a.fin.lo_mode, a.fin.promotion, qp);
@@ -151,33 +157,43 @@ __global__ void __launch_bounds__(kThreads, 6) offline_track_tiles_kernel(InputA
   const float s = qp[1], lo = qp[2], hi = qp[3];
   const QDiv qd = QDiv::make(qp[0]);
   const int64_t nvec = a.n >> 2;
+  const int64_t ntiles = (nvec + kTileElems / 4 - 1) / (kTileElems / 4);
   const float4* p4 = reinterpret_cast<const float4*>(a.x);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int64_t tile = blockIdx.x; tile * (kTileElems / 4) < nvec; tile += gridDim.x) {
-    const int64_t row0 = (tile * kTileElems) / a.L;
-    const int64_t boundary = (row0 + 1) * a.L;
+  const int64_t t0 = (int64_t)blockIdx.x * tiles_per_block;
+  const int64_t t1 = min(ntiles, t0 + tiles_per_block);
+  int64_t row = (t0 * kTileElems) / a.L;             // one 64-bit division per block
+  int64_t boundary = (row + 1) * a.L;                // first element of the next row
+  float m_cur = 0.f, m_nxt = 0.f;
+  auto flush = [&](int64_t r, float m) {             // block-uniform: depends on tile indices and L only
+    m = block_max(m, red);
+    if (threadIdx.x == 0 && r < a.rows) atomicMax(&a.ws->rowmax[r], __float_as_uint(m));
+  };
+  for (int64_t tile = t0; tile < t1; ++tile) {
     const int64_t v0 = tile * (kTileElems / 4) + threadIdx.x;
+    // the row boundary relative to the tile start, in elements (32-bit: anything beyond the tile is "far")
+    const int64_t rel64 = boundary - tile * kTileElems;
+    const int rel = rel64 > (int64_t)kTileElems ? (int)kTileElems + 8 : (int)rel64;
     float4 v[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const int64_t j = v0 + u * kThreads;
       v[u] = j < nvec ? ld_stream(p4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    float m0 = 0.f, m1 = 0.f;
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const int64_t j = v0 + u * kThreads;
       const int64_t i = 4 * j;
-      if (i + 3 < boundary) {
-        m0 = absmax4(m0, v[u]);
-      } else if (i >= boundary) {
-        m1 = absmax4(m1, v[u]);
+      const int ir = 4 * ((int)threadIdx.x + u * kThreads);        // element offset inside the tile
+      if (ir + 3 < rel) {
+        m_cur = absmax4(m_cur, v[u]);
+      } else if (ir >= rel) {
+        m_nxt = absmax4(m_nxt, v[u]);
       } else {
         const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          if (i + t < boundary) m0 = fmaxf(m0, fabsf(e[t]));
-          else m1 = fmaxf(m1, fabsf(e[t]));
+          if (ir + t < rel) m_cur = fmaxf(m_cur, fabsf(e[t]));
+          else m_nxt = fmaxf(m_nxt, fabsf(e[t]));
         }
       }
       if (j < nvec) {
@@ -188,22 +204,15 @@ __global__ void __launch_bounds__(kThreads, 6) offline_track_tiles_kernel(InputA
         if (a.code_kind) put_code4(a.codes, a.code_kind, i, c);
       }
     }
-    m0 = warp_max(m0);
-    m1 = warp_max(m1);
-    __syncthreads();
-    if (lane == 0) {
-      red[0][warp] = m0;
-      red[1][warp] = m1;
-    }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-      float m = 0.f;
-#pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) m = fmaxf(m, red[threadIdx.x][w]);
-      const int64_t r = row0 + threadIdx.x;
-      if (r < a.rows && m > __uint_as_float(__ldcg(&a.ws->rowmax[r]))) atomicMax(&a.ws->rowmax[r], __float_as_uint(m));
+    if ((tile + 1) * kTileElems >= boundary) {       // the next tile starts in the next row (L >= one tile)
+      flush(row, m_cur);
+      ++row;
+      boundary += a.L;
+      m_cur = m_nxt;
+      m_nxt = 0.f;
     }
   }
+  if (t0 < t1) flush(row, m_cur);
   const int64_t tail0 = nvec << 2;
   if (blockIdx.x == 0 && threadIdx.x < a.n - tail0) {
     const int64_t i = tail0 + threadIdx.x;
@@ -213,6 +222,128 @@ __global__ void __launch_bounds__(kThreads, 6) offline_track_tiles_kernel(InputA
     a.y[i] = __fmul_rn(c, s);
     if (a.code_kind) put_code1(a.codes, a.code_kind, i, c);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Online input path of a SMALL tensor in ONE launch (the launch-bound layers of configs 1 and 3).
+// ---------------------------------------------------------------------------------------------
+// Every block keeps its one tile (4096 elements) in registers: fold it into the per-sample maxima (shared-memory
+// atomicMax per float4, then one global atomicMax per sample the tile touches), meet the other blocks at a grid
+// barrier, read the N maxima back, run the reference's sequential Kahan mean and the scale math ITSELF (every block
+// redundantly -- a microsecond of one thread, but no block waits for another one's result), quantise out of its
+// registers and store.  x is read from HBM once (8 B/element instead of 12) and the ticket / last-block phase /
+// second launch of the two-kernel path leave the critical path.  The barrier is a plain spin on a counter in the
+// workspace: the host only takes this path when the whole grid is resident at once (grid <= SMs x occupancy), so
+// every block the spinners wait for is already running or will be scheduled as soon as other work drains.
+constexpr int kFusedRowsPerTileMax = 136;     // L >= 32  =>  a tile touches at most 4096/32 + 2 samples
+constexpr int kFusedRowsMax = 2048;
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 4) online_fused_kernel(InputArgs a) {
+  __shared__ unsigned int smax[kFusedRowsPerTileMax];
+  __shared__ float stage[kFusedRowsMax];
+  __shared__ float qp[4];
+  const unsigned int nvec = (unsigned int)(a.n >> 2);
+  const unsigned int L = (unsigned int)a.L;
+  const unsigned int tile_first = blockIdx.x * (unsigned int)kTileElems;
+  const unsigned int row_first = tile_first / L;
+  const unsigned int tile_last = min((unsigned int)a.n, tile_first + (unsigned int)kTileElems) - 1u;
+  const unsigned int rows_here = tile_last / L - row_first + 1u;
+  const float4* p4 = reinterpret_cast<const float4*>(a.x);
+  const unsigned int v0 = blockIdx.x * (unsigned int)(kTileElems / 4) + threadIdx.x;
+  float4 v[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const unsigned int j = v0 + u * kThreads;
+    v[u] = j < nvec ? ld_stream(p4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (unsigned int r = threadIdx.x; r < rows_here; r += kThreads) smax[r] = 0u;
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const unsigned int j = v0 + u * kThreads;
+    if (j < nvec) {                 // L % 4 == 0: a float4 never straddles two samples
+      const float m = absmax4(0.f, v[u]);
+      atomicMax(&smax[(4u * j) / L - row_first], __float_as_uint(m));
+    }
+  }
+  __syncthreads();
+  for (unsigned int r = threadIdx.x; r < rows_here; r += kThreads) {
+    const unsigned int m = smax[r];
+    if (m != 0u) atomicMax(&a.ws->rowmax[row_first + r], m);
+  }
+  // ---- grid barrier: every block's maxima have landed ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&a.ws->ticket, 1u);
+    while (ld_acquire_u32(&a.ws->ticket) < gridDim.x) {
+    }
+  }
+  __syncthreads();
+  const int rows = (int)a.rows;
+  for (int i = threadIdx.x; i < rows; i += kThreads) stage[i] = __uint_as_float(__ldcg(&a.ws->rowmax[i]));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f, c = 0.f;
+    for (int i = 0; i < rows; ++i) kahan_add(s, c, stage[i]);
+    const float mean = __fdiv_rn(s, (float)rows);                  // MXNet mean: Kahan sum / fp32(N)
+    compute_qparams(mean, a.fin.bits, a.fin.is_signed, a.fin.lo_mode, a.fin.promotion, qp);
+    if (blockIdx.x == 0) {
+      a.fin.out_mean[0] = mean;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a.fin.qparams[k] = qp[k];
+    }
+    // everyone has read the maxima once the second counter is full: the last block restores the workspace
+    __threadfence();
+    if (atomicAdd(&a.ws->ticket2, 1u) == gridDim.x - 1) {
+      for (int i = 0; i < rows; ++i) a.ws->rowmax[i] = 0u;
+      a.ws->ticket2 = 0u;
+      __threadfence();
+      a.ws->ticket = 0u;
+    }
+  }
+  if (blockIdx.x == 0 && a.fin.out_rows != nullptr)
+    for (int i = threadIdx.x; i < rows; i += kThreads) a.fin.out_rows[i] = stage[i];
+  __syncthreads();
+  const float s = qp[1], lo = qp[2], hi = qp[3];
+  const QDiv qd = QDiv::make(qp[0]);
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const unsigned int j = v0 + u * kThreads;
+    if (j < nvec) {
+      const float4 c = qd.code4(make_float4(clipf(v[u].x, lo, hi), clipf(v[u].y, lo, hi), clipf(v[u].z, lo, hi),
+                                            clipf(v[u].w, lo, hi)));
+      st_stream(reinterpret_cast<float4*>(a.y) + j,
+                make_float4(__fmul_rn(c.x, s), __fmul_rn(c.y, s), __fmul_rn(c.z, s), __fmul_rn(c.w, s)));
+      if (a.code_kind) put_code4(a.codes, a.code_kind, 4 * (int64_t)j, c);
+    }
+  }
+}
+
+// largest grid of online_fused_kernel that is resident all at once on the current device (0 = path disabled)
+static int fused_online_capacity() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (cached[dev] == 0) {
+    const char* env = getenv("FQ_ONLINE_FUSED");
+    int per_sm = 0;
+    if (env != nullptr && env[0] == '0') {
+      cached[dev] = -1;
+    } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, online_fused_kernel, kThreads, 0) == cudaSuccess &&
+               per_sm > 0) {
+      cached[dev] = per_sm * sm_count();
+    } else {
+      cached[dev] = -1;
+    }
+  }
+  return cached[dev] > 0 ? cached[dev] : 0;
 }
 
 __global__ void __launch_bounds__(kThreads) finish_rows_kernel(Workspace* ws, int64_t rows, FinishParams fin) {
@@ -548,7 +679,11 @@ int fq_forward_online(const DLTensor* x_, int64_t n_samples, int bits, int is_si
   FQ_TRY(code_kind_of(who, codes, x.numel, &a.code_kind) == 0);
 
   if (!imax.null && a.L >= kTileElems) {   // offline range + tracking, long rows: streaming tile kernel
-    offline_track_tiles_kernel<<<tile_grid(a.n, 1 << 30), kThreads, 0, st>>>(a);
+    // enough blocks to fill the machine first (6 resident per SM), then up to kTrackTilesMax tiles per block
+    const int64_t ntiles = (a.n + kTileElems - 1) / kTileElems;
+    int64_t tpb = ntiles / ((int64_t)sm_count() * 6 * 4);
+    tpb = tpb < 1 ? 1 : (tpb > kTrackTilesMax ? kTrackTilesMax : tpb);
+    offline_track_tiles_kernel<<<(unsigned)((ntiles + tpb - 1) / tpb), kThreads, 0, st>>>(a, (int)tpb);
     FQ_LAUNCH_CHECK("offline_track_tiles_kernel");
     finish_rows_kernel<<<1, kThreads, 0, st>>>(a.ws, a.rows, a.fin);
     FQ_LAUNCH_CHECK("finish_rows_kernel");
@@ -559,6 +694,15 @@ int fq_forward_online(const DLTensor* x_, int64_t n_samples, int bits, int is_si
     input_path_kernel<kOfflineTrack><<<grid, kThreads, 0, st>>>(a);
     FQ_LAUNCH_CHECK("input_path_kernel<offline>");
     return 0;
+  }
+  // Small tensors whose whole grid is resident at once: one launch, x read once (see online_fused_kernel)
+  {
+    const int64_t ntiles = (a.n + kTileElems - 1) / kTileElems;
+    if (a.L % 4 == 0 && a.L >= 32 && a.rows <= kFusedRowsMax && ntiles <= fused_online_capacity()) {
+      online_fused_kernel<<<(unsigned)ntiles, kThreads, 0, st>>>(a);
+      FQ_LAUNCH_CHECK("online_fused_kernel");
+      return 0;
+    }
   }
   // Online: the range pass (per-sample absmax, then the last block's Kahan mean and scale math) followed by
   // the streaming quantiser reading its qparams from device memory -- no host round trip.  Two plain launches
