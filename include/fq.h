@@ -163,6 +163,16 @@ FQ_API int fq_quant_weight_multi(const FqWeightJob* jobs, int n_jobs, const DLTe
                                  const DLTensor* bias_out_flat, const DLTensor* scale_out_flat, void* ws,
                                  void* stream);
 
+/* Backward of the fake-BN fold (convert_conv2d.py:47-51 behind the identity STE) for many blocks in one launch:
+ *   dw = (dwq / sd) * gamma;  dgamma = sum_row((dwq / sd) * w) + (dbq / sd) * (bias - mean);
+ *   dbias = (dbq / sd) * gamma;  dbeta = dbq;   sd = sqrt(var + 1e-10).
+ * dbq / bias / dbias / dbeta may be NULL.  Replaces 6-8 framework launches per block per QAT step. */
+typedef struct {
+  const DLTensor *dwq, *dbq, *w, *gamma, *mean, *var, *bias;   /* inputs  */
+  const DLTensor *dw, *dgamma, *dbias, *dbeta;                 /* outputs */
+} FqFoldBwdJob;
+FQ_API int fq_fold_backward_multi(const FqFoldBwdJob* jobs, int n_jobs, void* stream);
+
 /* ---- K3 straight-through estimator backward ----------------------------- */
 FQ_API int fq_ste_backward(const DLTensor* dy, const DLTensor* x, const DLTensor* qparams, const DLTensor* dx,
                     int mode, void* stream);

@@ -43,6 +43,10 @@ class FqWeightJob(_c.Structure):
                 ("bits", _c.c_int32), ("reserved", _c.c_int32), ("w_off", _c.c_int64), ("bias_off", _c.c_int64),
                 ("scale_off", _c.c_int64)]
 
+class FqFoldBwdJob(_c.Structure):
+    _fields_ = [(n, P) for n in ("dwq", "dbq", "w", "gamma", "mean", "var", "bias", "dw", "dgamma", "dbias", "dbeta")]
+
+
 kDLCPU, kDLCUDA = 1, 2
 _DTYPES = {
     torch.float32: (2, 32), torch.float64: (2, 64),
@@ -76,6 +80,7 @@ SIGNATURES = {
                                      _c.c_void_p, _c.c_void_p]),
     "fq_quant_weight": (_c.c_int, [P, _c.c_int64, _c.c_int, P, P, P, P, P, P, P, P, P, _c.c_void_p, _c.c_void_p]),
     "fq_quant_weight_multi": (_c.c_int, [_c.POINTER(FqWeightJob), _c.c_int, P, P, P, _c.c_void_p, _c.c_void_p]),
+    "fq_fold_backward_multi": (_c.c_int, [_c.POINTER(FqFoldBwdJob), _c.c_int, _c.c_void_p]),
     "fq_quant_weight_wino": (_c.c_int, [P, P, P, P, _c.c_int, P, P, _c.c_void_p, _c.c_void_p]),
     "fq_wino_backward": (_c.c_int, [P, P, P, P, P, _c.c_void_p]),
     "fq_ste_backward": (_c.c_int, [P, P, P, P, _c.c_int, _c.c_void_p]),

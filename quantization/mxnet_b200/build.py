@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfq_b200.so")
-SOURCES = ["fq_api.cu", "fq_range.cu", "fq_quant.cu", "fq_fused.cu", "fq_calib.cu", "fq_wino.cu", "fq_stats.cu"]
+SOURCES = ["fq_api.cu", "fq_range.cu", "fq_quant.cu", "fq_fused.cu", "fq_calib.cu", "fq_wino.cu", "fq_stats.cu", "fq_foldbwd.cu"]
 HEADERS = [os.path.join(CSRC, "fq_common.cuh"), os.path.join(CSRC, "fq_fused.cuh"),
            os.path.join(ROOT, "include", "fq.h")]
 

@@ -25,6 +25,7 @@ struct InputArgs {
   int64_t n, rows, L, per_block;
   Workspace* ws;
   FinishParams fin;
+  int defer_finish;       // range kernel: leave the maxima in ws->rowmax, online_quant_small_kernel finishes
 };
 
 __device__ __forceinline__ void put_code1(void* p, int kind, int64_t i, float c) {
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(kThreads, 6) input_path_kernel(InputArgs a) {
     }
   } else {
     absmax_segments<true>(a.x, begin, end, a.L, a.ws, red);     // plain loads: leave the lines in L2 for the quantiser
+    if (a.defer_finish) return;                                 // the dependent quantiser derives mean and scale itself
   }
   __threadfence();
   __syncthreads();
@@ -144,8 +146,10 @@ __global__ void __launch_bounds__(kThreads, 6) input_path_kernel(InputArgs a) {
 // Offline range + tracking for long rows (L >= one tile, so a tile meets at most two rows).  A block streams
 // `tiles_per_block` CONSECUTIVE tiles like the plain quantiser and keeps the running |x| maximum of the row it is in
 // in registers; only when the row changes (or the block ends) does it reduce over the block and issue ONE atomicMax.
-// The first version reduced and touched its row slot once per tile: 2048 blocks per row reading (and sometimes
-// atomically updating) one address was visible at streaming speed (6.3 instead of 6.9 TB/s at 2^30 elements).
+// The first version took one tile per block and reduced + touched its row slot once per tile: 5.9 TB/s at 2^30
+// elements in its branch-free form; consecutive tiles per block: 6.4 TB/s (0.97 of what a plain device copy
+// reaches on this GPU).  Prefetching the next tile into a second register set (64 registers, 4 blocks per SM)
+// measured the same (profiles/README.md, round 2).
 constexpr int kTrackTilesMax = 8;
 
 __global__ void __launch_bounds__(kThreads, 5) offline_track_tiles_kernel(InputArgs a, int tiles_per_block) {
@@ -162,46 +166,40 @@ __global__ void __launch_bounds__(kThreads, 5) offline_track_tiles_kernel(InputA
   const int64_t t0 = (int64_t)blockIdx.x * tiles_per_block;
   const int64_t t1 = min(ntiles, t0 + tiles_per_block);
   int64_t row = (t0 * kTileElems) / a.L;             // one 64-bit division per block
-  int64_t boundary = (row + 1) * a.L;                // first element of the next row
+  int64_t boundary = (row + 1) * a.L;                // first element of the next row (L % 4 == 0: never inside a float4)
   float m_cur = 0.f, m_nxt = 0.f;
   auto flush = [&](int64_t r, float m) {             // block-uniform: depends on tile indices and L only
     m = block_max(m, red);
     if (threadIdx.x == 0 && r < a.rows) atomicMax(&a.ws->rowmax[r], __float_as_uint(m));
   };
-  for (int64_t tile = t0; tile < t1; ++tile) {
+  auto load_tile = [&](int64_t tile, float4* v) {
     const int64_t v0 = tile * (kTileElems / 4) + threadIdx.x;
-    // the row boundary relative to the tile start, in elements (32-bit: anything beyond the tile is "far")
-    const int64_t rel64 = boundary - tile * kTileElems;
-    const int rel = rel64 > (int64_t)kTileElems ? (int)kTileElems + 8 : (int)rel64;
-    float4 v[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const int64_t j = v0 + u * kThreads;
       v[u] = j < nvec ? ld_stream(p4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  float4 v[kUnroll];
+  for (int64_t tile = t0; tile < t1; ++tile) {
+    load_tile(tile, v);
+    const int64_t v0 = tile * (kTileElems / 4) + threadIdx.x;
+    // the row boundary relative to the tile start, in elements (32-bit: anything beyond the tile is "far")
+    const int64_t rel64 = boundary - tile * kTileElems;
+    const int rel = rel64 > (int64_t)kTileElems ? (int)kTileElems + 8 : (int)rel64;
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const int64_t j = v0 + u * kThreads;
-      const int64_t i = 4 * j;
       const int ir = 4 * ((int)threadIdx.x + u * kThreads);        // element offset inside the tile
-      if (ir + 3 < rel) {
-        m_cur = absmax4(m_cur, v[u]);
-      } else if (ir >= rel) {
-        m_nxt = absmax4(m_nxt, v[u]);
-      } else {
-        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if (ir + t < rel) m_cur = fmaxf(m_cur, fabsf(e[t]));
-          else m_nxt = fmaxf(m_nxt, fabsf(e[t]));
-        }
-      }
+      const float m = absmax4(0.f, v[u]);                          // zeros beyond the end of the tensor
+      if (ir < rel) m_cur = fmaxf(m_cur, m);                       // selects, not branches
+      else m_nxt = fmaxf(m_nxt, m);
       if (j < nvec) {
         const float4 c = qd.code4(make_float4(clipf(v[u].x, lo, hi), clipf(v[u].y, lo, hi), clipf(v[u].z, lo, hi),
                                               clipf(v[u].w, lo, hi)));
-        st_stream(reinterpret_cast<float4*>(a.y + i),
+        st_stream(reinterpret_cast<float4*>(a.y) + j,
                   make_float4(__fmul_rn(c.x, s), __fmul_rn(c.y, s), __fmul_rn(c.z, s), __fmul_rn(c.w, s)));
-        if (a.code_kind) put_code4(a.codes, a.code_kind, i, c);
+        if (a.code_kind) put_code4(a.codes, a.code_kind, 4 * j, c);
       }
     }
     if ((tile + 1) * kTileElems >= boundary) {       // the next tile starts in the next row (L >= one tile)
@@ -213,47 +211,24 @@ __global__ void __launch_bounds__(kThreads, 5) offline_track_tiles_kernel(InputA
     }
   }
   if (t0 < t1) flush(row, m_cur);
-  const int64_t tail0 = nvec << 2;
-  if (blockIdx.x == 0 && threadIdx.x < a.n - tail0) {
-    const int64_t i = tail0 + threadIdx.x;
-    const float x = a.x[i];
-    atomicMax(&a.ws->rowmax[i / a.L], __float_as_uint(fabsf(x)));
-    const float c = qd.code(clipf(x, lo, hi));
-    a.y[i] = __fmul_rn(c, s);
-    if (a.code_kind) put_code1(a.codes, a.code_kind, i, c);
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Online input path of a SMALL tensor in ONE launch (the launch-bound layers of configs 1 and 3).
+// Online input path of a latency-bound tensor (<= 1024 tiles): quantiser that finishes the range itself.
 // ---------------------------------------------------------------------------------------------
-// Every block keeps its one tile (4096 elements) in registers: fold it into the per-sample maxima (shared-memory
-// atomicMax per float4, then one global atomicMax per sample the tile touches), meet the other blocks at a grid
-// barrier, read the N maxima back, run the reference's sequential Kahan mean and the scale math ITSELF (every block
-// redundantly -- a microsecond of one thread, but no block waits for another one's result), quantise out of its
-// registers and store.  x is read from HBM once (8 B/element instead of 12) and the ticket / last-block phase /
-// second launch of the two-kernel path leave the critical path.  The barrier is a plain spin on a counter in the
-// workspace: the host only takes this path when the whole grid is resident at once (grid <= SMs x occupancy), so
-// every block the spinners wait for is already running or will be scheduled as soon as other work drains.
-constexpr int kFusedRowsPerTileMax = 136;     // L >= 32  =>  a tile touches at most 4096/32 + 2 samples
-constexpr int kFusedRowsMax = 2048;
+// Launched as a programmatic dependent of input_path_kernel<range> running with defer_finish: that kernel ends as
+// soon as its per-sample atomicMax'es are out -- no fence, no "last block" ticket, no Kahan mean on ITS tail.  Every
+// block here loads its tile of x first (the range kernel only reads x), waits for the range grid, reads the N
+// maxima, and runs the reference's sequential Kahan mean and scale math itself: redundant across blocks, but a
+// block never waits for a value another block has to compute, publish and fence.  That takes the ticket atomic, two
+// fences and one L2 round trip (publish qparams -> read qparams) off a chain that is nothing but round trips.
+// Block 0 writes cur_max / qparams / per_sample; the last block to have read the maxima zeroes the workspace.
+constexpr int kSelfFinishRowsMax = 2048;
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__global__ void __launch_bounds__(kThreads, 4) online_fused_kernel(InputArgs a) {
-  __shared__ unsigned int smax[kFusedRowsPerTileMax];
-  __shared__ float stage[kFusedRowsMax];
+__global__ void __launch_bounds__(kThreads, 4) online_quant_small_kernel(InputArgs a) {
+  __shared__ float stage[kSelfFinishRowsMax];
   __shared__ float qp[4];
   const unsigned int nvec = (unsigned int)(a.n >> 2);
-  const unsigned int L = (unsigned int)a.L;
-  const unsigned int tile_first = blockIdx.x * (unsigned int)kTileElems;
-  const unsigned int row_first = tile_first / L;
-  const unsigned int tile_last = min((unsigned int)a.n, tile_first + (unsigned int)kTileElems) - 1u;
-  const unsigned int rows_here = tile_last / L - row_first + 1u;
   const float4* p4 = reinterpret_cast<const float4*>(a.x);
   const unsigned int v0 = blockIdx.x * (unsigned int)(kTileElems / 4) + threadIdx.x;
   float4 v[kUnroll];
@@ -262,30 +237,7 @@ __global__ void __launch_bounds__(kThreads, 4) online_fused_kernel(InputArgs a) 
     const unsigned int j = v0 + u * kThreads;
     v[u] = j < nvec ? ld_stream(p4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (unsigned int r = threadIdx.x; r < rows_here; r += kThreads) smax[r] = 0u;
-  __syncthreads();
-#pragma unroll
-  for (int u = 0; u < kUnroll; ++u) {
-    const unsigned int j = v0 + u * kThreads;
-    if (j < nvec) {                 // L % 4 == 0: a float4 never straddles two samples
-      const float m = absmax4(0.f, v[u]);
-      atomicMax(&smax[(4u * j) / L - row_first], __float_as_uint(m));
-    }
-  }
-  __syncthreads();
-  for (unsigned int r = threadIdx.x; r < rows_here; r += kThreads) {
-    const unsigned int m = smax[r];
-    if (m != 0u) atomicMax(&a.ws->rowmax[row_first + r], m);
-  }
-  // ---- grid barrier: every block's maxima have landed ----
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    atomicAdd(&a.ws->ticket, 1u);
-    while (ld_acquire_u32(&a.ws->ticket) < gridDim.x) {
-    }
-  }
-  __syncthreads();
+  pdl_wait();                                   // the range grid has completed and its atomics are visible
   const int rows = (int)a.rows;
   for (int i = threadIdx.x; i < rows; i += kThreads) stage[i] = __uint_as_float(__ldcg(&a.ws->rowmax[i]));
   __syncthreads();
@@ -299,12 +251,8 @@ __global__ void __launch_bounds__(kThreads, 4) online_fused_kernel(InputArgs a) 
 #pragma unroll
       for (int k = 0; k < 4; ++k) a.fin.qparams[k] = qp[k];
     }
-    // everyone has read the maxima once the second counter is full: the last block restores the workspace
-    __threadfence();
-    if (atomicAdd(&a.ws->ticket2, 1u) == gridDim.x - 1) {
+    if (atomicAdd(&a.ws->ticket, 1u) == gridDim.x - 1) {           // everyone has read the maxima
       for (int i = 0; i < rows; ++i) a.ws->rowmax[i] = 0u;
-      a.ws->ticket2 = 0u;
-      __threadfence();
       a.ws->ticket = 0u;
     }
   }
@@ -326,24 +274,21 @@ __global__ void __launch_bounds__(kThreads, 4) online_fused_kernel(InputArgs a) 
   }
 }
 
-// largest grid of online_fused_kernel that is resident all at once on the current device (0 = path disabled)
-static int fused_online_capacity() {
-  static int cached[64] = {0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
-  if (cached[dev] == 0) {
-    const char* env = getenv("FQ_ONLINE_FUSED");
-    int per_sm = 0;
-    if (env != nullptr && env[0] == '0') {
-      cached[dev] = -1;
-    } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, online_fused_kernel, kThreads, 0) == cudaSuccess &&
-               per_sm > 0) {
-      cached[dev] = per_sm * sm_count();
-    } else {
-      cached[dev] = -1;
-    }
+// FQ_ONLINE_MODE (environment, read once): how fq_forward_online runs a latency-bound tensor.
+//   0  range kernel with last-block finish + dependent streaming quantiser (round 1; still the path of large,
+//      ragged or > 2048-sample tensors)
+//   2  range kernel without finish + dependent quantiser that finishes itself (default)
+// Measured under CUDA-graph replay (profiles/r2_graph_probe_online_path.txt): 5.5 / 6.4 / 6.9 / 8.2 us per call at
+// 2^14 / 2^18 / 2^20 / 2^21 elements against 7.1 / 7.9 / 8.4 / 10.0 us for mode 0.  A third variant -- ONE launch
+// with a spinning grid barrier, x kept in registers, 8 B/element -- was built and measured slower than mode 2
+// everywhere (6.1 / 7.5 / 8.6 / 10.9 us): the barrier's two extra L2 round trips cost more than the launch saved.
+static int online_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* env = getenv("FQ_ONLINE_MODE");
+    mode = (env != nullptr && env[0] == '0') ? 0 : 2;
   }
-  return cached[dev] > 0 ? cached[dev] : 0;
+  return mode;
 }
 
 __global__ void __launch_bounds__(kThreads) finish_rows_kernel(Workspace* ws, int64_t rows, FinishParams fin) {
@@ -678,7 +623,7 @@ int fq_forward_online(const DLTensor* x_, int64_t n_samples, int bits, int is_si
   a.codes = codes.null ? nullptr : codes.data;
   FQ_TRY(code_kind_of(who, codes, x.numel, &a.code_kind) == 0);
 
-  if (!imax.null && a.L >= kTileElems) {   // offline range + tracking, long rows: streaming tile kernel
+  if (!imax.null && a.L >= kTileElems && a.L % 4 == 0) {   // offline range + tracking, long rows: streaming tile kernel
     // enough blocks to fill the machine first (6 resident per SM), then up to kTrackTilesMax tiles per block
     const int64_t ntiles = (a.n + kTileElems - 1) / kTileElems;
     int64_t tpb = ntiles / ((int64_t)sm_count() * 6 * 4);
@@ -695,12 +640,16 @@ int fq_forward_online(const DLTensor* x_, int64_t n_samples, int bits, int is_si
     FQ_LAUNCH_CHECK("input_path_kernel<offline>");
     return 0;
   }
-  // Small tensors whose whole grid is resident at once: one launch, x read once (see online_fused_kernel)
   {
     const int64_t ntiles = (a.n + kTileElems - 1) / kTileElems;
-    if (a.L % 4 == 0 && a.L >= 32 && a.rows <= kFusedRowsMax && ntiles <= fused_online_capacity()) {
-      online_fused_kernel<<<(unsigned)ntiles, kThreads, 0, st>>>(a);
-      FQ_LAUNCH_CHECK("online_fused_kernel");
+    // latency-bound tensors: the dependent quantiser finishes the range itself (see online_quant_small_kernel)
+    if (online_mode() == 2 && a.n % 4 == 0 && a.rows <= kSelfFinishRowsMax && ntiles <= 1024) {
+      a.defer_finish = 1;
+      const int grid = row_grid(a.n, a.L, sm_count() * 8, &a.per_block);
+      input_path_kernel<kRangeOnly><<<grid, kThreads, 0, st>>>(a);
+      FQ_LAUNCH_CHECK("input_path_kernel<range, deferred>");
+      FQ_CUDA(launch_dependent(online_quant_small_kernel, dim3((unsigned)ntiles), dim3(kThreads), 0, st, a));
+      FQ_LAUNCH_CHECK("online_quant_small_kernel");
       return 0;
     }
   }

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kThreads) channel_stats_kernel(const float* __
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int nw = kThreads / 32;
   const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
-  StatAcc a, b;          // two independent chains
+  StatAcc a, b, e, f;    // independent chains: four 16 B loads in flight per thread in the streaming case
   if (HW >= 1024) {      // the whole block walks one (n, c) plane at a time
     for (int64_t n = n0; n < n1; ++n) {
       const float* p = y + (n * C + c) * HW;
@@ -83,12 +83,15 @@ __global__ void __launch_bounds__(kThreads) channel_stats_kernel(const float* __
         const float4* p4 = reinterpret_cast<const float4*>(p);
         const int64_t nvec = HW >> 2;
         int64_t i = threadIdx.x;
-        for (; i + kThreads < nvec; i += 2 * kThreads) {
+        for (; i + 3 * kThreads < nvec; i += 4 * kThreads) {
           const float4 v0 = ld_stream(p4 + i), v1 = ld_stream(p4 + i + kThreads);
+          const float4 v2 = ld_stream(p4 + i + 2 * kThreads), v3 = ld_stream(p4 + i + 3 * kThreads);
           a.add4(v0, K);
           b.add4(v1, K);
+          e.add4(v2, K);
+          f.add4(v3, K);
         }
-        if (i < nvec) a.add4(ld_stream(p4 + i), K);
+        for (; i < nvec; i += kThreads) a.add4(ld_stream(p4 + i), K);
       } else {
         int64_t i = threadIdx.x;
         for (; i + kThreads < HW; i += 2 * kThreads) {
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(kThreads) channel_stats_kernel(const float* __
       }
     }
   }
-  double s1 = a.s1 + b.s1, s2 = a.s2 + b.s2;
+  double s1 = (a.s1 + b.s1) + (e.s1 + f.s1), s2 = (a.s2 + b.s2) + (e.s2 + f.s2);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s1 += __shfl_xor_sync(0xffffffffu, s1, o);

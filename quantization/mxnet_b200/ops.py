@@ -296,6 +296,42 @@ def quant_weight_multi(plan):
     return ws, bs, ss
 
 
+def fold_backward_multi(jobs):
+    """Backward of the fake-BN fold of many blocks in ONE launch.  ``jobs``: dicts with dwq, w, gamma, mean, var and
+    optionally dbq, bias (all float32, contiguous).  Returns per job (dw, dgamma, dbias or None, dbeta or None); the
+    outputs are views of three freshly allocated flat buffers."""
+    dev = jobs[0]["w"].device
+    n_w = sum(jb["w"].numel() for jb in jobs)
+    n_c = sum(jb["w"].shape[0] for jb in jobs)
+    dw_flat = torch.empty(n_w, dtype=torch.float32, device=dev)
+    vec_flat = torch.empty(3 * n_c, dtype=torch.float32, device=dev)
+    table = (_ffi.FqFoldBwdJob * len(jobs))()
+    keep, outs = [], []
+    wo = co = 0
+    for rec, jb in zip(table, jobs):
+        w = jb["w"]
+        c, n = w.shape[0], w.numel()
+        has_b = jb.get("dbq") is not None
+        dw = dw_flat[wo:wo + n].view(w.shape)
+        dgamma, dbias, dbeta = vec_flat[co:co + c], vec_flat[n_c + co:n_c + co + c], vec_flat[2 * n_c + co:2 * n_c + co + c]
+        wo += n
+        co += c
+        fields = dict(dwq=_f32(jb["dwq"], "dwq"), dbq=jb.get("dbq"), w=w.detach(), gamma=jb["gamma"].detach(),
+                      mean=jb["mean"].detach(), var=jb["var"].detach(),
+                      bias=None if jb.get("bias") is None else jb["bias"].detach(),
+                      dw=dw, dgamma=dgamma, dbias=dbias if has_b else None, dbeta=dbeta if has_b else None)
+        for name, t in fields.items():
+            if t is None:
+                setattr(rec, name, None)
+            else:
+                arg = dl(_f32(t, name))
+                keep.append(arg)
+                setattr(rec, name, _ffi._c.pointer(arg.t))
+        outs.append((dw, dgamma, dbias if has_b else None, dbeta if has_b else None))
+    check_call(_lib().fq_fold_backward_multi(table, len(jobs), current_stream()))
+    return outs
+
+
 # ---- K3 ------------------------------------------------------------------------------------------
 def ste_backward(dy, x=None, qparams=None, mode=STE_IDENTITY):
     """ste_func.py:43-44.  Identity aliases dy (zero bytes moved); the clip mask is an extension."""

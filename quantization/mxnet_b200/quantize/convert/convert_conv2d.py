@@ -219,18 +219,38 @@ class _WeightPath(torch.autograd.Function):
         if not ctx.fold:
             return dwq, dbq, None, None, None, None, None, None
         weight, bias, gamma, mean, var = ctx.saved_tensors
+        dweight, dgamma, dbias, dbeta = _fold_backward([dict(dwq=dwq, dbq=dbq, w=weight, gamma=gamma, mean=mean, var=var,
+                                                             bias=bias if ctx.has_bias else None)])[0]
+        return dweight, (dbias if ctx.has_bias else None), dgamma, dbeta, None, None, None, None
+
+
+def _fold_backward(jobs):
+    """(dweight, dgamma, dbias, dbeta) per job: one fused launch for all jobs that have a weight gradient
+    (ops.fold_backward_multi), the op-by-op formula for the rest."""
+    out = [None] * len(jobs)
+    fused = [i for i, jb in enumerate(jobs) if jb["dwq"] is not None and jb["dwq"].is_cuda]
+    if fused:
+        for i, res in zip(fused, ops.fold_backward_multi([jobs[i] for i in fused])):
+            out[i] = res
+    for i, jb in enumerate(jobs):
+        if out[i] is not None:
+            continue
+        weight, gamma, mean, var, bias, dwq, dbq = (jb[k] for k in ("w", "gamma", "mean", "var", "bias", "dwq", "dbq"))
         cout = weight.shape[0]
         sd = torch.sqrt(var + 1e-10)
-        da = dwq.reshape(cout, -1) / sd.reshape(-1, 1)
-        dweight = (da * gamma.reshape(-1, 1)).reshape(weight.shape)
-        dgamma = (da * weight.reshape(cout, -1)).sum(dim=1)
-        dbias = dbeta = None
+        dweight = dgamma = dbias = dbeta = None
+        if dwq is not None:
+            da = dwq.reshape(cout, -1) / sd.reshape(-1, 1)
+            dweight = (da * gamma.reshape(-1, 1)).reshape(weight.shape)
+            dgamma = (da * weight.reshape(cout, -1)).sum(dim=1)
         if dbq is not None:
             dn = dbq / sd
-            dgamma = dgamma + dn * (bias - mean)
-            dbias = dn * gamma if ctx.has_bias else None
+            b = bias if bias is not None else torch.zeros_like(gamma)
+            dgamma = dn * (b - mean) if dgamma is None else dgamma + dn * (b - mean)
+            dbias = dn * gamma
             dbeta = dbq
-        return dweight, dbias, dgamma, dbeta, None, None, None, None
+        out[i] = (dweight, dgamma, dbias, dbeta)
+    return out
 
 
 class _MultiWeightPath(torch.autograd.Function):
@@ -254,28 +274,20 @@ class _MultiWeightPath(torch.autograd.Function):
     def backward(ctx, *grads):
         out = [None, None]
         g = iter(grads)
+        fold_jobs, slots = [], []
         for jb in ctx.jobs:
             dwq = next(g)
             if jb.get("gamma") is None:
                 out.extend([dwq, None, None, None])
                 continue
             dbq = next(g)
-            weight, gamma, mean, var = jb["w"], jb["gamma"], jb["mean"], jb["var"]
-            bias = jb.get("bias")
-            cout = weight.shape[0]
-            sd = torch.sqrt(var + 1e-10)
-            dweight = dgamma = dbias = dbeta = None
-            if dwq is not None:
-                da = dwq.reshape(cout, -1) / sd.reshape(-1, 1)
-                dweight = (da * gamma.reshape(-1, 1)).reshape(weight.shape)
-                dgamma = (da * weight.reshape(cout, -1)).sum(dim=1)
-            if dbq is not None:
-                dn = dbq / sd
-                b = bias if bias is not None else torch.zeros_like(gamma)
-                dgamma = dn * (b - mean) if dgamma is None else dgamma + dn * (b - mean)
-                dbias = dn * gamma if bias is not None else None
-                dbeta = dbq
-            out.extend([dweight, dbias, dgamma, dbeta])
+            fold_jobs.append(dict(dwq=dwq, dbq=dbq, w=jb["w"], gamma=jb["gamma"], mean=jb["mean"], var=jb["var"],
+                                  bias=jb.get("bias")))
+            slots.append(len(out))
+            out.extend([None, None, None, None])
+        # the fold backward of every block in ONE launch (the op-by-op formula is 6-8 launches per block)
+        for pos, jb, (dweight, dgamma, dbias, dbeta) in zip(slots, fold_jobs, _fold_backward(fold_jobs) if fold_jobs else []):
+            out[pos:pos + 4] = [dweight, dbias if jb["bias"] is not None else None, dgamma, dbeta]
         return tuple(out)
 
 

@@ -823,3 +823,44 @@ def _near_tie_body(ops, DC, warnings):
     with warnings.catch_warnings():
         warnings.simplefilter("error")
         assert DC.kl_calibrate(h, 256, 256, R.BINS) == 1792
+
+
+_ONLINE_MODE_SNIPPET = r"""
+import sys
+import numpy as np, torch
+sys.path.insert(0, %r)
+from oracle import fq_oracle as O
+from quantization.mxnet_b200 import ops
+r = np.random.RandomState(5)
+for shape, bits, signed in [((128, 16, 32, 32), 8, False), ((128, 64, 8, 8), 4, True), ((32, 64), 8, False),
+                            ((7, 36), 5, True), ((16, 3, 30, 30), 8, False), ((128, 32, 16, 16), 2, False),
+                            ((64, 96, 28, 28), 8, False)]:
+    x = r.standard_normal(shape).astype(np.float32)
+    if not signed:
+        x = np.abs(x)
+    xd = torch.from_numpy(x).cuda()
+    per = torch.empty(shape[0], device="cuda")
+    for rep in range(3):            # the workspace must come back clean every time
+        y, cur, qp = ops.forward_online(xd, bits, signed, ops.LO_NEG_MAX if signed else ops.LO_ZERO, per_sample=per)
+        oy, _, ocur, oqp = O.fake_quant_input(x, bits, signed, None, "legacy", "conv")
+        assert np.array_equal(y.cpu().numpy().view(np.uint32), oy.view(np.uint32)), (shape, rep)
+        assert np.float32(cur.item()) == ocur and np.array_equal(qp.cpu().numpy(), np.array(oqp, np.float32))
+        assert np.array_equal(per.cpu().numpy(), O.absmax_rows(x, shape[0]))
+    # and the kernels that share the workspace still see it zeroed
+    assert np.array_equal(ops.absmax_rows(xd, shape[0]).cpu().numpy(), O.absmax_rows(x, shape[0]))
+print("ok")
+"""
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_forward_online_every_execution_mode_is_bit_exact(mode):
+    """FQ_ONLINE_MODE selects how a latency-bound tensor runs (csrc/fq_fused.cu): 0 = last-block finish + dependent
+    streaming quantiser, 2 = dependent quantiser that finishes the range itself (default).  The choice is read once
+    per process, hence the subprocess; both must match the oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FQ_ONLINE_MODE=mode)
+    out = subprocess.run([sys.executable, "-c", _ONLINE_MODE_SNIPPET % root], capture_output=True, text=True,
+                         timeout=600, env=env, cwd=root)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-3000:]
