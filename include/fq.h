@@ -125,6 +125,12 @@ FQ_API int fq_forward_online(const DLTensor* x, int64_t n_samples, int bits, int
                       int promotion, const DLTensor* input_max, const DLTensor* y, const DLTensor* codes,
                       const DLTensor* cur_max, const DLTensor* qparams, const DLTensor* per_sample,
                       void* ws, void* stream);
+/* The online input path when the per-sample maxima come from outside (data parallel: the all-gathered maxima of
+ * the GLOBAL batch, [N] in sample order): Kahan mean -> cur_max[0], scale math -> qparams[4], quantise -- one launch
+ * for latency-bound tensors (every block derives the mean itself), three for large or ragged ones. */
+FQ_API int fq_forward_from_maxima(const DLTensor* x, const DLTensor* maxima, int bits, int is_signed, int lo_mode,
+                                  int promotion, const DLTensor* y, const DLTensor* codes, const DLTensor* cur_max,
+                                  const DLTensor* qparams, void* stream);
 /* Weight path, two launches and no host round trip: optional BN fold -> per-row absmax -> scale -> quantise.
  * rows in {1 (layer), G (group), Cout (channel)}; bits <= 0 folds only (merge_bn.py:65-74).
  * gamma/beta/mean/var all NULL = no fold; bias may be NULL (treated as zeros, initialize.py:65-70).
@@ -235,6 +241,49 @@ FQ_API int fq_qconv_quantize(const DLTensor* x, const DLTensor* range2, const DL
 /* nn/quantized_conv.py:74-76: y = float(acc) * (s_in * s_w). */
 FQ_API int fq_qconv_dequantize(const DLTensor* acc_i32, const DLTensor* s_in, const DLTensor* s_w,
                         const DLTensor* y, void* stream);
+
+/* ---- QConv2D integer convolution on the tensor cores (nn/quantized_conv.py:106-159) -------
+ * fq_qconv_pack_input: fp32 NCHW x -> spatially zero-padded NHWC 8-bit codes xq [N, H+2ph, W+2pw, C] with the
+ *   arithmetic of fq_qconv_quantize (clip, divide by scale, roundf); the padding holds the code of 0.0, because the
+ *   reference pads first and quantises the padded tensor (:108-116).  int8 xq for symmetric ranges, uint8 xq for
+ *   [0, max] ranges (the caller guarantees that the codes fit).  scale_out[0] receives the scale.
+ * fq_qconv_pack_weight: fp32 [Cout, Cg, KH, KW] -> int8 codes [Cout, KH, KW, Cg] (K-major for the GEMM).
+ * fq_qconv_igemm: implicit GEMM on tcgen05 (kind::i8, int32 accumulators in tensor memory), fused epilogue
+ *   out = float(max?(acc + bias_q)) * (s_in * s_w)  (:143-158).  Cg % 16 == 0; out float32 [N, Cout, Ho, Wo]. */
+FQ_API int fq_qconv_pack_input(const DLTensor* x, const DLTensor* range2, int pad_h, int pad_w, const DLTensor* xq,
+                               const DLTensor* scale_out, void* stream);
+FQ_API int fq_qconv_pack_weight(const DLTensor* w, const DLTensor* range2, const DLTensor* wq, const DLTensor* scale_out,
+                                void* stream);
+FQ_API int fq_qconv_igemm(const DLTensor* xq, const DLTensor* wq, const DLTensor* bias_q, const DLTensor* s_in,
+                          const DLTensor* s_w, int stride_h, int stride_w, int groups, int relu, const DLTensor* out,
+                          void* stream);
+
+/* ---- data-parallel collectives for hosts that own an ncclComm_t ------------------------
+ * One process per GPU, batch sharded by sample, weights replicated.  `nccl_comm` is the host's ncclComm_t passed as
+ * void*; libnccl is resolved at run time from the libraries the process already carries (so that the communicator
+ * and the functions belong to the same NCCL instance), else from fq_nccl_load(path) / libnccl.so.2 -- it is not a
+ * link-time dependency of libfq_b200.so.  Everything is enqueued on `stream`; nothing synchronises the host.
+ * A torch host uses torch.distributed instead (quantization/mxnet_b200/dist.py). */
+#define FQ_REDUCE_SUM 0
+#define FQ_REDUCE_MAX 1
+#define FQ_REDUCE_MIN 2
+FQ_API int fq_nccl_load(const char* path);            /* NULL: whatever NCCL is already loaded, else libnccl.so.2 */
+/* in place; float32/float64/(u)int32/(u)int64.  KL first-batch maxima: MAX on [L]; QAT gradients: SUM on the bucket. */
+FQ_API int fq_dist_all_reduce(const DLTensor* t, int op, void* nccl_comm, void* stream);
+/* out = [world x in] in rank order. */
+FQ_API int fq_dist_all_gather(const DLTensor* in, const DLTensor* out, void* nccl_comm, void* stream);
+/* current_input_max of the GLOBAL batch (convert_conv2d.py:56): all-gather of the shard's per-sample maxima
+ * ([N/R] -> per_sample_all [N], sample order) + the reference's Kahan mean -> cur_max[0], on every rank. */
+FQ_API int fq_dist_input_range(const DLTensor* per_sample_local, const DLTensor* per_sample_all,
+                               const DLTensor* cur_max, void* nccl_comm, void* stream);
+/* Histogram counts of `steps` batches ([steps, n], 32- or 64-bit): integer SUM over the ranks, then
+ * fq_hist_accumulate_f32 -- every rank ends with the float32 histograms of a single-GPU run (:47,103-104). */
+FQ_API int fq_dist_hist_fold(const DLTensor* counts, const DLTensor* hist, int first, const DLTensor* seen_last,
+                             void* nccl_comm, void* stream);
+/* fake-BN batch statistics of the GLOBAL batch (convert_conv2d.py:150-153): all-gather of the ranks' float64 records
+ * (parts_local [C, 4] from fq_channel_stats -> parts_all [R, C, 4]) + fq_channel_stats_finish. */
+FQ_API int fq_dist_channel_stats(const DLTensor* parts_local, const DLTensor* parts_all, const DLTensor* mean,
+                                 const DLTensor* var, void* nccl_comm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -78,6 +78,7 @@ SIGNATURES = {
     "fq_forward_rows": (_c.c_int, [P, _c.c_int64, P, P, P, _c.c_void_p]),
     "fq_forward_online": (_c.c_int, [P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, P, P, P, P, P, P,
                                      _c.c_void_p, _c.c_void_p]),
+    "fq_forward_from_maxima": (_c.c_int, [P, P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, P, P, P, P, _c.c_void_p]),
     "fq_quant_weight": (_c.c_int, [P, _c.c_int64, _c.c_int, P, P, P, P, P, P, P, P, P, _c.c_void_p, _c.c_void_p]),
     "fq_quant_weight_multi": (_c.c_int, [_c.POINTER(FqWeightJob), _c.c_int, P, P, P, _c.c_void_p, _c.c_void_p]),
     "fq_fold_backward_multi": (_c.c_int, [_c.POINTER(FqFoldBwdJob), _c.c_int, _c.c_void_p]),
@@ -91,6 +92,15 @@ SIGNATURES = {
     "fq_hist_accumulate_f32": (_c.c_int, [P, P, _c.c_int, P, _c.c_void_p]),
     "fq_kl_search": (_c.c_int, [P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, P, P, P, _c.c_void_p]),
     "fq_kl_threshold": (_c.c_int, [P, P, _c.c_int, P, _c.c_void_p]),
+    "fq_qconv_pack_input": (_c.c_int, [P, P, _c.c_int, _c.c_int, P, P, _c.c_void_p]),
+    "fq_qconv_pack_weight": (_c.c_int, [P, P, P, P, _c.c_void_p]),
+    "fq_qconv_igemm": (_c.c_int, [P, P, P, P, P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, P, _c.c_void_p]),
+    "fq_nccl_load": (_c.c_int, [_c.c_char_p]),
+    "fq_dist_all_reduce": (_c.c_int, [P, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    "fq_dist_all_gather": (_c.c_int, [P, P, _c.c_void_p, _c.c_void_p]),
+    "fq_dist_input_range": (_c.c_int, [P, P, P, _c.c_void_p, _c.c_void_p]),
+    "fq_dist_hist_fold": (_c.c_int, [P, P, _c.c_int, P, _c.c_void_p, _c.c_void_p]),
+    "fq_dist_channel_stats": (_c.c_int, [P, P, P, P, _c.c_void_p, _c.c_void_p]),
     "fq_quantize_int8_export": (_c.c_int, [P, P, P, P, _c.c_void_p]),
     "fq_qconv_quantize": (_c.c_int, [P, P, P, P, _c.c_void_p]),
     "fq_qconv_dequantize": (_c.c_int, [P, P, P, P, _c.c_void_p]),

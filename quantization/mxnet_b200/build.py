@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfq_b200.so")
-SOURCES = ["fq_api.cu", "fq_range.cu", "fq_quant.cu", "fq_fused.cu", "fq_calib.cu", "fq_wino.cu", "fq_stats.cu", "fq_foldbwd.cu"]
+SOURCES = ["fq_api.cu", "fq_range.cu", "fq_quant.cu", "fq_fused.cu", "fq_calib.cu", "fq_wino.cu", "fq_stats.cu", "fq_foldbwd.cu", "fq_nccl.cu", "fq_qconv_mma.cu"]
 HEADERS = [os.path.join(CSRC, "fq_common.cuh"), os.path.join(CSRC, "fq_fused.cuh"),
            os.path.join(ROOT, "include", "fq.h")]
 
@@ -63,7 +63,8 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % s)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"]
+    # libnccl is resolved with dlsym at run time (csrc/fq_nccl.cu): -ldl, no -lnccl
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -26,6 +26,8 @@ struct InputArgs {
   Workspace* ws;
   FinishParams fin;
   int defer_finish;       // range kernel: leave the maxima in ws->rowmax, online_quant_small_kernel finishes
+  const float* maxima;    // online_quant_small_kernel: per-sample maxima given by the caller (data parallel: the
+                          // all-gathered ones) instead of ws->rowmax; no workspace clean-up then
 };
 
 __device__ __forceinline__ void put_code1(void* p, int kind, int64_t i, float c) {
@@ -239,7 +241,11 @@ __global__ void __launch_bounds__(kThreads, 4) online_quant_small_kernel(InputAr
   }
   pdl_wait();                                   // the range grid has completed and its atomics are visible
   const int rows = (int)a.rows;
-  for (int i = threadIdx.x; i < rows; i += kThreads) stage[i] = __uint_as_float(__ldcg(&a.ws->rowmax[i]));
+  if (a.maxima != nullptr) {
+    for (int i = threadIdx.x; i < rows; i += kThreads) stage[i] = __ldcg(a.maxima + i);
+  } else {
+    for (int i = threadIdx.x; i < rows; i += kThreads) stage[i] = __uint_as_float(__ldcg(&a.ws->rowmax[i]));
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     float s = 0.f, c = 0.f;
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 4) online_quant_small_kernel(InputAr
 #pragma unroll
       for (int k = 0; k < 4; ++k) a.fin.qparams[k] = qp[k];
     }
-    if (atomicAdd(&a.ws->ticket, 1u) == gridDim.x - 1) {           // everyone has read the maxima
+    if (a.maxima == nullptr && atomicAdd(&a.ws->ticket, 1u) == gridDim.x - 1) {   // everyone has read the maxima
       for (int i = 0; i < rows; ++i) a.ws->rowmax[i] = 0u;
       a.ws->ticket = 0u;
     }
@@ -661,6 +667,50 @@ int fq_forward_online(const DLTensor* x_, int64_t n_samples, int bits, int is_si
   input_path_kernel<kRangeOnly><<<grid, kThreads, 0, st>>>(a);
   FQ_LAUNCH_CHECK("input_path_kernel<range>");
   return launch_forward_scalar_dev(x_, a.fin.qparams, y_, codes_, a.n <= kL2ReuseElems, stream);
+}
+
+int fq_forward_from_maxima(const DLTensor* x_, const DLTensor* maxima_, int bits, int is_signed, int lo_mode,
+                           int promotion, const DLTensor* y_, const DLTensor* codes_, const DLTensor* cur_max_,
+                           const DLTensor* qparams_, void* stream) {
+  const char* who = "fq_forward_from_maxima";
+  View x, mx, y, codes, cur, qp;
+  FQ_TRY(view_of(x_, "fq_forward_from_maxima: x", false, &x));
+  FQ_TRY(view_of(maxima_, "fq_forward_from_maxima: maxima", false, &mx));
+  FQ_TRY(view_of(y_, "fq_forward_from_maxima: y", false, &y));
+  FQ_TRY(view_of(codes_, "fq_forward_from_maxima: codes", true, &codes));
+  FQ_TRY(view_of(cur_max_, "fq_forward_from_maxima: cur_max", false, &cur));
+  FQ_TRY(view_of(qparams_, "fq_forward_from_maxima: qparams", false, &qp));
+  FQ_REQUIRE(x.is_f32() && y.is_f32() && mx.is_f32() && cur.is_f32() && qp.is_f32() && y.numel == x.numel &&
+                 cur.numel >= 1 && qp.numel == 4 && mx.numel >= 1,
+             "%s: float32 tensors; y like x, qparams [4]", who);
+  FQ_TRY(check_quant_args(who, bits, lo_mode, promotion));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t ntiles = (x.numel + kTileElems - 1) / kTileElems;
+  const bool small = x.numel > 0 && x.numel % 4 == 0 && mx.numel <= kSelfFinishRowsMax && ntiles <= 1024 &&
+                     aligned16(x.data) && aligned16(y.data) && (codes.null || aligned16(codes.data));
+  if (!small) {   // large or ragged tensors: mean, scale and the streaming quantiser as three launches
+    FQ_TRY(fq_mean_kahan(maxima_, cur_max_, stream) == 0);
+    FQ_TRY(fq_scale_from_max(cur_max_, bits, is_signed, lo_mode, promotion, qparams_, stream) == 0);
+    return x.numel == 0 ? 0 : launch_forward_scalar_dev(x_, qp.as<const float>(), y_, codes_, false, stream);
+  }
+  InputArgs a = {};
+  a.x = x.as<const float>();
+  a.y = y.as<float>();
+  a.codes = codes.null ? nullptr : codes.data;
+  FQ_TRY(code_kind_of(who, codes, x.numel, &a.code_kind) == 0);
+  a.n = x.numel;
+  a.rows = mx.numel;
+  a.L = x.numel / mx.numel;
+  a.maxima = mx.as<const float>();
+  a.fin.out_mean = cur.as<float>();
+  a.fin.qparams = qp.as<float>();
+  a.fin.bits = bits;
+  a.fin.is_signed = is_signed;
+  a.fin.lo_mode = lo_mode;
+  a.fin.promotion = promotion;
+  online_quant_small_kernel<<<(unsigned)ntiles, kThreads, 0, st>>>(a);     // plain launch: griddepcontrol.wait is a no-op
+  FQ_LAUNCH_CHECK("online_quant_small_kernel");
+  return 0;
 }
 
 int fq_quant_weight(const DLTensor* w_, int64_t rows, int bits, const DLTensor* gamma_, const DLTensor* beta_,

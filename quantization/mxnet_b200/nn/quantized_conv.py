@@ -2,11 +2,15 @@
 (8-bit hard-coded, no zero point) and dequantises the int32 accumulator.
 
 On the hot path: ``quantize`` / ``_quantize`` / ``dequantize`` -- range reduction and
-integer codes run in the CUDA kernels.  The convolution itself stays a framework call on
-integer-valued float tensors, exactly as the reference computes it with ``F.dot`` on float32 casts
-(nn/quantized_conv.py:149-153); an int8 tensor-core convolution is outside the north star.
-The reference's im2col output-size quirk (``(H - kh + 1) // sh``, :49) is not reproduced: the
-framework convolution yields the correct number of windows.
+integer codes run in the CUDA kernels.  The integer convolution itself (outside the
+north star) runs on the tensor cores when its operands are 8-bit friendly -- symmetric int8 weights,
+int8 inputs (or uint8 inputs with a preset [0, max] range), input channels per group a multiple of 16:
+``ops.qconv_pack_input`` writes padded NHWC codes, ``ops.qconv_igemm`` is an implicit GEMM on
+``tcgen05.mma.kind::i8`` with exact int32 accumulators in tensor memory and the bias / ReLU /
+dequantise epilogue fused (csrc/fq_qconv_mma.cu).  Everything else takes the reference's own route:
+a framework convolution on integer-valued float tensors (``F.dot`` on float32 casts, :149-153).
+The reference's im2col output-size quirk (``(H - kh + 1) // sh``, :49) is not reproduced: both
+routes yield the correct number of windows.
 """
 import torch
 from torch import nn
@@ -69,6 +73,7 @@ class Conv2D(nn.Module):
         self._weight_dtype = weight_dtype
         self._input_range = None
         self._weight_range = None
+        self.use_tensor_cores = True       # set to False to force the framework convolution on float codes
 
         self.weight = nn.Parameter(torch.empty(channels, in_channels // groups, *self._kernel_size))
         nn.init.uniform_(self.weight, -0.07, 0.07)          # mxnet's default Uniform(0.07)
@@ -77,9 +82,50 @@ class Conv2D(nn.Module):
         if activation not in (None, 'relu'):
             raise NotImplementedError("activation %r" % (activation,))
 
+    def _tensor_core_ranges(self, inputs):
+        """(input range2, unsigned codes?, weight range2) when the tcgen05 path applies, else None."""
+        if not (self.use_tensor_cores and inputs.is_cuda and (self._in_channels // self._groups) % 16 == 0):
+            return None
+        dev = inputs.device
+        if self._weight_range is None:
+            if self._weight_dtype != 'int8':
+                return None
+            mx = ops.absmax_rows(self.weight.detach(), 1)
+            w_rng = torch.cat([-mx, mx])
+        else:
+            lo, hi = (float(v) for v in self._weight_range)
+            if hi != -lo:
+                return None
+            w_rng = torch.tensor([lo, hi], dtype=torch.float32, device=dev)
+        if self._input_range is None:
+            if self._input_dtype != 'int8':
+                return None             # an automatic uint8 range has no zero point: its codes need not fit 8 bits
+            mx = ops.absmax_rows(inputs, 1)       # zero padding does not change max |x|
+            return torch.cat([-mx, mx]), False, w_rng
+        lo, hi = (float(v) for v in self._input_range)
+        if hi == -lo:
+            return torch.tensor([lo, hi], dtype=torch.float32, device=dev), False, w_rng
+        if lo == 0.0 and hi > 0.0:
+            return torch.tensor([lo, hi], dtype=torch.float32, device=dev), True, w_rng       # codes in [0, 255]
+        return None
+
     def forward(self, inputs):
         weight, bias = self.weight, self.bias
         ph, pw = self._padding
+        if self._quantized:
+            tc = self._tensor_core_ranges(inputs)
+            if tc is not None:
+                in_rng, unsigned, w_rng = tc
+                xq, in_scale = ops.qconv_pack_input(inputs, in_rng, ph, pw, unsigned=unsigned)
+                wq, w_scale = ops.qconv_pack_weight(weight.detach(), w_rng)
+                bias_q = None
+                if bias is not None:
+                    b_scale = in_scale * w_scale
+                    b_max = b_scale * float(2 ** 31)
+                    _, bias_q = ops.forward_scalar(bias.detach(), torch.cat([b_scale, b_scale, -b_max, b_max]),
+                                                   codes_dtype=torch.int32)
+                return ops.qconv_igemm(xq, wq, bias_q, in_scale, w_scale, self._strides, self._groups,
+                                       relu=self.act is not None)
         inputs = nn.functional.pad(inputs, (pw, pw, ph, ph))
         if self._quantized:
             if self._input_range is None:

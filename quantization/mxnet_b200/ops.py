@@ -172,6 +172,21 @@ def forward_online(x, bits=8, signed=False, lo_mode=LO_ZERO, input_max=None, qua
     return (y, cur_max, qparams, codes) if codes_dtype is not None else (y, cur_max, qparams)
 
 
+def forward_from_maxima(x, maxima, bits=8, signed=False, lo_mode=LO_ZERO, out=None, cur_max=None, qparams=None,
+                        promotion=None):
+    """Online input path with per-sample maxima supplied by the caller (data parallel: the all-gathered maxima of
+    the global batch): Kahan mean, scale and quantise in one launch for latency-bound tensors.
+    Returns (y, cur_max, qparams)."""
+    x = _f32(x)
+    out = torch.empty_like(x) if out is None else out
+    cur_max = torch.empty(1, dtype=torch.float32, device=x.device) if cur_max is None else cur_max
+    qparams = torch.empty(4, dtype=torch.float32, device=x.device) if qparams is None else qparams
+    a, m, o, c, q = dl(x), dl(_f32(maxima, "maxima")), dl(out), dl(cur_max), dl(qparams)
+    check_call(_lib().fq_forward_from_maxima(a.ptr, m.ptr, bits, int(bool(signed)), lo_mode, _promo(promotion), o.ptr,
+                                             None, c.ptr, q.ptr, current_stream()))
+    return out, cur_max, qparams
+
+
 def quant_weight(w, rows, bits, gamma=None, beta=None, mean=None, var=None, bias=None, out=None, bias_out=None,
                  scale_out=None, codes_dtype=None):
     """BN fold (optional) + per-row absmax + scale + quantise: two launches, nothing read back.
@@ -438,3 +453,38 @@ def qconv_dequantize(acc, s_in, s_w):
     a, si, sw, o = dl(acc), dl(s_in), dl(s_w), dl(y)
     check_call(_lib().fq_qconv_dequantize(a.ptr, si.ptr, sw.ptr, o.ptr, current_stream()))
     return y
+
+
+# ---- QConv2D on the tensor cores ---------------------------------------------------------------------
+def qconv_pack_input(x, range2, pad_h, pad_w, unsigned=False):
+    """fp32 NCHW -> spatially padded NHWC 8-bit codes + scale (1,).  nn/quantized_conv.py:108-116, 54-61."""
+    x = _f32(x)
+    n, c, h, w = x.shape
+    xq = torch.empty((n, h + 2 * pad_h, w + 2 * pad_w, c), dtype=torch.uint8 if unsigned else torch.int8, device=x.device)
+    scale = torch.empty(1, dtype=torch.float32, device=x.device)
+    a, r, q, s = dl(x), dl(_f32(range2, "range2")), dl(xq), dl(scale)
+    check_call(_lib().fq_qconv_pack_input(a.ptr, r.ptr, int(pad_h), int(pad_w), q.ptr, s.ptr, current_stream()))
+    return xq, scale
+
+
+def qconv_pack_weight(w, range2):
+    """fp32 [Cout, Cg, KH, KW] -> int8 codes [Cout, KH, KW, Cg] + scale (1,)."""
+    w = _f32(w, "w")
+    co, cg, kh, kw = w.shape
+    wq = torch.empty((co, kh, kw, cg), dtype=torch.int8, device=w.device)
+    scale = torch.empty(1, dtype=torch.float32, device=w.device)
+    a, r, q, s = dl(w), dl(_f32(range2, "range2")), dl(wq), dl(scale)
+    check_call(_lib().fq_qconv_pack_weight(a.ptr, r.ptr, q.ptr, s.ptr, current_stream()))
+    return wq, scale
+
+
+def qconv_igemm(xq, wq, bias_q, s_in, s_w, strides, groups=1, relu=False):
+    """Integer convolution on tcgen05 with the bias / ReLU / dequantise epilogue fused.  nn/quantized_conv.py:143-158."""
+    n, hp, wp, _ = xq.shape
+    co, kh, kw, _ = wq.shape
+    ho, wo = (hp - kh) // strides[0] + 1, (wp - kw) // strides[1] + 1
+    out = torch.empty((n, co, ho, wo), dtype=torch.float32, device=xq.device)
+    a, b, c, si, sw, o = dl(xq), dl(wq), dl(bias_q), dl(s_in), dl(s_w), dl(out)
+    check_call(_lib().fq_qconv_igemm(a.ptr, b.ptr, ptr(c), si.ptr, sw.ptr, int(strides[0]), int(strides[1]), int(groups),
+                                     int(bool(relu)), o.ptr, current_stream()))
+    return out

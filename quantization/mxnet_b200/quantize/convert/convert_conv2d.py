@@ -33,12 +33,13 @@ def _per_sample_buffer(m, n):
 
 def _global_range(x, m, group):
     """Data parallel, range needed NOW (online quantisation): the shard's per-sample maxima are
-    all-gathered and the Kahan mean is taken over the global batch on every rank."""
+    all-gathered; the Kahan mean over the global batch is then taken on every rank (by the quantiser itself,
+    ops.forward_from_maxima).  Returns the gathered maxima [N]."""
     from ... import dist as fqdist
     per = _per_sample_buffer(m, x.shape[0])
     ops.input_range(x, cur_max=m.current_input_max, per_sample=per)
-    ops.mean_kahan(fqdist.gather_per_sample(per, group), out=m.current_input_max)
     m._fq_range_pending = False
+    return fqdist.gather_per_sample(per, group)
 
 
 def _input_path(x, m, lo_mode):
@@ -101,9 +102,9 @@ class _InputPath(torch.autograd.Function):
         qa = m.quantize_args
         group = getattr(m, "_fq_dist_group", None)
         if group is not None and not m.quantize_input_offline:
-            _global_range(x, m, group)      # data parallel + online: range over the global batch first
-            ops.scale_from_max(m.current_input_max, qa.in_width, qa.in_signed, lo_mode, qparams=m._fq_qparams)
-            return ops.forward_scalar(x, m._fq_qparams)
+            allmax = _global_range(x, m, group)      # data parallel + online: range over the global batch first
+            return ops.forward_from_maxima(x, allmax, qa.in_width, qa.in_signed, lo_mode, cur_max=m.current_input_max,
+                                           qparams=m._fq_qparams)[0]
         # single process, or offline range: one fused launch.  Under data parallelism the per-sample maxima
         # are kept and the global mean is taken for ALL layers by one collective in update_ema().
         per = _per_sample_buffer(m, x.shape[0]) if group is not None else None

@@ -244,3 +244,109 @@ def test_two_gpu_fake_bn_statistics_equal_the_global_batch():
             assert np.allclose(got, want[key], rtol=5e-3, atol=1e-4), key
         # without the exchange the shard-local variance would be visibly off: the test has teeth
         assert np.abs(results[0]["step%d" % step]["cur_var"]).sum() > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the C ABI's own collectives (include/fq.h fq_dist_*): a host that owns an ncclComm_t, no torch.distributed
+# ---------------------------------------------------------------------------------------------------------------
+def _nccl_library_path():
+    import glob
+    cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so*"))
+    return os.path.abspath(cands[0]) if cands else "libnccl.so.2"
+
+
+def _c_abi_worker(rank, uid_queue, out):
+    try:
+        import ctypes
+        import signal
+        signal.alarm(240)           # a communicator that never forms must not outlive the test
+        torch.cuda.set_device(rank)
+        from quantization.mxnet_b200 import _ffi, ops
+        from test_channel_stats_math import mean_close
+        from oracle import build_c as C
+        from oracle import fq_oracle as O
+        path = _nccl_library_path()
+        nccl = ctypes.CDLL(path)
+
+        class UniqueId(ctypes.Structure):
+            _fields_ = [("internal", ctypes.c_char * 128)]
+        nccl.ncclGetUniqueId.argtypes = [ctypes.POINTER(UniqueId)]
+        nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UniqueId, ctypes.c_int]
+        nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+        uid = UniqueId()
+        if rank == 0:
+            assert nccl.ncclGetUniqueId(ctypes.byref(uid)) == 0
+            for _ in range(WORLD - 1):
+                uid_queue.put(ctypes.string_at(ctypes.byref(uid), 128))      # all 128 bytes (.internal stops at a NUL)
+        else:
+            ctypes.memmove(ctypes.byref(uid), uid_queue.get(timeout=120), 128)
+        comm = ctypes.c_void_p()
+        assert nccl.ncclCommInitRank(ctypes.byref(comm), WORLD, uid, rank) == 0
+        lib = _ffi.load()
+        _ffi.check_call(lib.fq_nccl_load(path.encode()))
+        st = _ffi.current_stream()
+        r = np.random.RandomState(17)
+        # (1) online input range of the global batch: all-gather of per-sample maxima + Kahan mean
+        x = np.abs(r.standard_normal((16, 8, 12, 12))).astype(np.float32)
+        shard = torch.from_numpy(x[rank * 8:(rank + 1) * 8]).cuda()
+        per = torch.empty(8, device="cuda")
+        ops.input_range(shard, per_sample=per)
+        per_all, cur = torch.empty(16, device="cuda"), torch.empty(1, device="cuda")
+        a, b, c = _ffi.dl(per), _ffi.dl(per_all), _ffi.dl(cur)
+        _ffi.check_call(lib.fq_dist_input_range(a.ptr, b.ptr, c.ptr, comm, st))
+        want_cur, want_per = O.input_range(x)
+        assert np.array_equal(per_all.cpu().numpy(), want_per) and np.float32(cur.item()) == want_cur
+        # (2) histogram counts of 2 batches: integer sum over ranks + float32 fold in batch order (32-bit wire format)
+        mx = torch.tensor([float(x.max())], device="cuda")
+        counts = torch.zeros(2, 2049, dtype=torch.int32, device="cuda")
+        for bi in range(2):
+            ops.hist_nonzero(shard * (1.0 - 0.3 * bi), mx, 2048, counts[bi], promotion="nep50")
+        hist = torch.zeros(2049, device="cuda")
+        a, b = _ffi.dl(counts), _ffi.dl(hist)
+        _ffi.check_call(lib.fq_dist_hist_fold(a.ptr, b.ptr, 1, None, comm, st))
+        want = sum(O.histogram_counts(x * np.float32(1.0 - 0.3 * bi), 2048, x.max(), "nep50").astype(np.float32)
+                   for bi in range(2))
+        assert np.array_equal(hist.cpu().numpy()[:2048], want[:2048]) and int(counts.abs().sum()) == 0
+        # (3) fake-BN statistics of the global batch from the ranks' records
+        y = (r.standard_normal((16, 6, 9, 9)) * 2 + 1).astype(np.float32)
+        rec = torch.empty(6, 4, dtype=torch.float64, device="cuda")
+        ops.channel_stats(torch.from_numpy(y[rank * 8:(rank + 1) * 8]).cuda(), parts=rec, finish=False)
+        rec_all = torch.empty(WORLD, 6, 4, dtype=torch.float64, device="cuda")
+        mean, var = torch.empty(6, device="cuda"), torch.empty(6, device="cuda")
+        a, b, c, d = _ffi.dl(rec), _ffi.dl(rec_all), _ffi.dl(mean), _ffi.dl(var)
+        _ffi.check_call(lib.fq_dist_channel_stats(a.ptr, b.ptr, c.ptr, d.ptr, comm, st))
+        wm, wv = C.channel_stats(y)
+        assert mean_close(mean.cpu().numpy(), wm, y)
+        assert np.abs(var.cpu().numpy().view(np.int32).astype(np.int64) - wv.view(np.int32).astype(np.int64)).max() <= 2
+        # (4) plain reductions: MAX of first-batch ranges, SUM of a gradient bucket
+        t = torch.tensor([1.0 + rank, 5.0 - rank], device="cuda")
+        a = _ffi.dl(t)
+        _ffi.check_call(lib.fq_dist_all_reduce(a.ptr, 1, comm, st))
+        assert t.tolist() == [2.0, 5.0]
+        gbuf = torch.full((1000,), float(rank + 1), device="cuda")
+        a = _ffi.dl(gbuf)
+        _ffi.check_call(lib.fq_dist_all_reduce(a.ptr, 0, comm, st))
+        assert bool((gbuf == 3.0).all())
+        torch.cuda.synchronize()
+        nccl.ncclCommDestroy(comm)
+        out.put((rank, "ok"))
+    except Exception as e:
+        import traceback
+        out.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_c_abi_collectives_with_a_raw_nccl_communicator():
+    ctx = mp.get_context("spawn")
+    out, uid_queue = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_c_abi_worker, args=(r, uid_queue, out), daemon=True) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    try:
+        results = sorted(out.get(timeout=300) for _ in procs)
+    finally:
+        for p in procs:
+            p.join(timeout=20)
+            if p.is_alive():
+                p.kill()
+    assert results == [(0, "ok"), (1, "ok")], results

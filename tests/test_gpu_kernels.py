@@ -864,3 +864,23 @@ def test_forward_online_every_execution_mode_is_bit_exact(mode):
     out = subprocess.run([sys.executable, "-c", _ONLINE_MODE_SNIPPET % root], capture_output=True, text=True,
                          timeout=600, env=env, cwd=root)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("shape,bits,signed", [((16, 8, 12, 12), 8, False), ((128, 16, 32, 32), 4, True),
+                                               ((6, 37), 8, False), ((256, 64, 56, 56), 8, False)])
+def test_forward_from_maxima_equals_the_online_path(ops, shape, bits, signed):
+    """Data parallel online inputs: the quantiser is handed the all-gathered per-sample maxima and derives the Kahan
+    mean and the scale itself -- same bits as the single-GPU online path (convert_conv2d.py:56-66) on the whole batch,
+    on the one-launch path (small tensors) and on the three-launch path (large or ragged ones)."""
+    x = rng(sum(shape)).standard_normal(shape).astype(F32)
+    if not signed:
+        x = np.abs(x)
+    lo_mode = ops.LO_NEG_MAX if signed else ops.LO_ZERO
+    maxima = dev(O.absmax_rows(x, shape[0]))
+    y, cur, qp = ops.forward_from_maxima(dev(x), maxima, bits, signed, lo_mode)
+    oy, _, ocur, oqp = O.fake_quant_input(x, bits, signed, None, "legacy", "conv")
+    bits_equal(host(y), oy)
+    assert F32(cur.item()) == ocur
+    bits_equal(host(qp), np.array(oqp, F32))
+    y2, cur2, qp2 = ops.forward_online(dev(x), bits, signed, lo_mode)
+    bits_equal(host(y2), host(y))

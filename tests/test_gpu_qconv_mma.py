@@ -1,0 +1,83 @@
+"""QConv2D's integer convolution on the tensor cores (tcgen05.mma kind::i8, csrc/fq_qconv_mma.cu) against the
+reference's own route -- a dot product of float32 casts of the integer codes (nn/quantized_conv.py:149-153), which
+tests/test_gpu_api.py checks against the NumPy oracle -- and against an independent float64 integer convolution.
+int32 accumulators are exact, so every comparison is bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fq_oracle as O
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+CASES = [
+    # N, C, H, W, Cout, k, stride, pad, groups, bias, act, in_dtype / preset range
+    dict(n=2, c=16, h=9, w=9, co=8, k=3, s=1, p=1, g=1, bias=True, act=None, inp="int8"),
+    dict(n=3, c=32, h=14, w=14, co=40, k=3, s=2, p=1, g=1, bias=True, act="relu", inp="int8"),
+    dict(n=2, c=64, h=12, w=10, co=48, k=3, s=1, p=1, g=2, bias=False, act=None, inp="int8"),
+    dict(n=2, c=64, h=7, w=7, co=200, k=1, s=1, p=0, g=1, bias=True, act=None, inp="int8"),        # two N tiles
+    dict(n=8, c=16, h=28, w=28, co=24, k=3, s=1, p=1, g=1, bias=True, act="relu", inp="int8"),     # 49 M tiles, K=144
+    dict(n=2, c=96, h=8, w=8, co=96, k=3, s=1, p=1, g=6, bias=True, act=None, inp="int8"),         # Cg = 16
+    dict(n=1, c=256, h=6, w=6, co=128, k=3, s=1, p=0, g=1, bias=False, act=None, inp="int8"),      # K = 2304: 18 k-blocks
+    dict(n=4, c=32, h=10, w=10, co=16, k=5, s=2, p=2, g=1, bias=True, act="relu", inp=(0.0, 6.0)),  # uint8 codes
+    dict(n=2, c=48, h=9, w=11, co=20, k=(3, 1), s=(1, 2), p=(1, 0), g=1, bias=True, act=None, inp=(-2.5, 2.5)),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "c%d_co%d_k%s_g%d" % (c["c"], c["co"], c["k"], c["g"]))
+def test_tensor_core_integer_conv_equals_the_float_code_route(case):
+    from quantization.mxnet_b200.nn import Conv2D
+    torch.manual_seed(case["c"] * 7 + case["co"])
+    preset = case["inp"] if isinstance(case["inp"], tuple) else None
+    conv = Conv2D(case["co"], case["k"], case["s"], case["p"], in_channels=case["c"], groups=case["g"],
+                  activation=case["act"], use_bias=case["bias"], quantized=True,
+                  input_dtype="int8" if preset is None else "uint8", weight_dtype="int8").cuda()
+    if case["bias"]:
+        conv.bias.data.uniform_(-0.2, 0.2)
+    x = torch.randn(case["n"], case["c"], case["h"], case["w"], device="cuda")
+    if preset is not None:
+        conv._input_range = preset
+        if preset[0] == 0.0:
+            x = x.abs() * 3
+    assert conv._tensor_core_ranges(x) is not None
+    with torch.no_grad():
+        y_tc = conv(x)
+        conv.use_tensor_cores = False
+        y_ref = conv(x)
+    assert y_tc.shape == y_ref.shape
+    assert torch.equal(y_tc.view(torch.int32), y_ref.view(torch.int32)), (y_tc - y_ref).abs().max().item()
+
+    # independent check: oracle codes, exact integer convolution in float64 on the CPU
+    ph, pw = conv._padding
+    xp = torch.nn.functional.pad(x, (pw, pw, ph, ph)).cpu().numpy()
+    if preset is None:
+        xq, s_in = O.qconv_quantize_auto(xp, "int8")
+    else:
+        xq, s_in = O.qconv_quantize(xp, preset[0], preset[1])
+    wq, s_w = O.qconv_quantize_auto(conv.weight.detach().cpu().numpy(), "int8")
+    acc = torch.nn.functional.conv2d(torch.from_numpy(xq.astype(np.float64)), torch.from_numpy(wq.astype(np.float64)),
+                                     None, conv._strides, 0, 1, case["g"]).numpy().astype(np.int64)
+    if case["bias"]:
+        bs = F32(s_in * s_w)
+        b = conv.bias.detach().cpu().numpy()
+        bq = O.roundf((O.clip(b, -bs * F32(2 ** 31), bs * F32(2 ** 31)) / bs).astype(F32)).astype(np.int64)
+        acc = acc + bq.reshape(1, -1, 1, 1)
+    if case["act"] == "relu":
+        acc = np.maximum(acc, 0)
+    want = O.qconv_dequantize(acc.astype(np.int32), F32(s_in * s_w))
+    assert np.array_equal(y_tc.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+def test_tensor_core_path_declines_what_it_cannot_represent():
+    from quantization.mxnet_b200.nn import Conv2D
+    x = torch.rand(2, 3, 8, 8, device="cuda")
+    assert Conv2D(8, 3, 1, 1, in_channels=3, quantized=True, input_dtype="int8", weight_dtype="int8").cuda() \
+        ._tensor_core_ranges(x) is None                                     # 3 input channels: not a multiple of 16
+    x = torch.rand(2, 16, 8, 8, device="cuda")
+    conv = Conv2D(8, 3, 1, 1, in_channels=16, quantized=True, input_dtype="uint8", weight_dtype="int8").cuda()
+    assert conv._tensor_core_ranges(x) is None                              # automatic uint8 range: codes may not fit
+    conv._input_range = (0.5, 4.0)
+    assert conv._tensor_core_ranges(x) is None                              # min > 0: codes start above 0 and exceed 255
+    with torch.no_grad():
+        assert conv(x).shape == (2, 8, 8, 8)                                # ... and the float-code route still runs
