@@ -194,10 +194,8 @@ def _run_config(config, cfg, dev, world, rank, steps, warmup, graph):
         if world > 1:
             fqdist.enable_data_parallel(net)
         params = [p for p in net.parameters() if p.requires_grad]
-        opt = torch.optim.Adam(params, lr=1e-6, capturable=graph)
+        opt = torch.optim.Adam(params, lr=1e-6, capturable=graph, fused=True)       # one multi-tensor kernel, like MXNet's adam_update
         bucket = fqdist.GradBucket(params, net=net if world > 1 else None)   # input ranges ride with the gradients
-        if world > 1:
-            bucket.attach()
         loss_fn = nn.CrossEntropyLoss()
 
         def step():

@@ -190,27 +190,45 @@ class GradBucket:
     step are completed right after the collective.  The step then has one rendezvous between the ranks instead
     of two (the second one, in the middle of the step, costs about 0.5 ms of rank skew per step on 2-4 GPUs)."""
 
-    def __init__(self, params, group=None, net=None):
-        self.params = [p for p in params if p.requires_grad]
+    def __init__(self, params, group=None, net=None, align=32):
+        self.all_params = [p for p in params if p.requires_grad]
+        self.params = list(self.all_params)
         self.group = group
-        self.numel = sum(p.numel() for p in self.params)
+        # every gradient view starts on a 128-byte boundary of the flat buffer (vectorised access for every kernel
+        # that touches a gradient)
+        self.align = max(1, int(align))
+        self._layout()
         self.flat = None
         self.net = net
         self._deferred_ema = []
         if net is not None:
             net._fq_grad_bucket = self
 
+    def _layout(self):
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off = (off + p.numel() + self.align - 1) // self.align * self.align
+        self.numel = off
+
     def attach(self, tail_numel=0):
+        """Make every gradient a view of the flat buffer.  Called after a backward pass (all_reduce_mean() does it
+        on first use), parameters that received no gradient stay out of the bucket: a bypassed BatchNorm still owns
+        trainable weight / bias that nothing reads, and giving them zero gradients would make the optimizer step
+        through them on every iteration (measured on MobileNetV2 with fake-BN: 104 of 317 parameters, +0.5 ms per
+        7.8 ms step)."""
+        if any(p.grad is not None for p in self.all_params):
+            used = [p for p in self.all_params if p.grad is not None]
+            if len(used) != len(self.params) or any(a is not b for a, b in zip(used, self.params)):
+                self.params = used
+                self._layout()
         dev = self.params[0].device
         self.flat = torch.zeros(self.numel + tail_numel, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            view = self.flat[off:off + n].view(p.shape)
+        for p, off in zip(self.params, self.offsets):
+            view = self.flat[off:off + p.numel()].view(p.shape)
             if p.grad is not None:
                 view.copy_(p.grad)
             p.grad = view
-            off += n
         return self
 
     def _attached(self):

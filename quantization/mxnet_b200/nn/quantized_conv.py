@@ -143,9 +143,11 @@ class Conv2D(nn.Module):
                 b_max = b_scale * float(2 ** 31)
                 _, bias_q = ops.forward_scalar(bias.detach(), torch.cat([b_scale, b_scale, -b_max, b_max]),
                                                codes_dtype=torch.int32)
-            # the reference multiplies float32 casts of the integer codes and casts the result to int32
+            # the reference multiplies float32 casts of the integer codes and casts the result to int32 (:149-153).
+            # Its F.dot is exact on integers below 2^24; cuDNN may pick a Winograd / FFT algorithm, which is not
+            # (1301.9999 would truncate to 1301), so the exact integer is restored by rounding before the cast.
             acc = nn.functional.conv2d(inputs_q.float(), weight_q.float(), None, self._strides, 0, 1, self._groups)
-            acc = acc.to(torch.int32)
+            acc = torch.round(acc).to(torch.int32)
             if bias_q is not None:
                 acc = acc + bias_q.reshape(1, -1, 1, 1)
             if self.act is not None:

@@ -46,9 +46,8 @@ def test_tensor_core_integer_conv_equals_the_float_code_route(case):
         conv.use_tensor_cores = False
         y_ref = conv(x)
     assert y_tc.shape == y_ref.shape
-    assert torch.equal(y_tc.view(torch.int32), y_ref.view(torch.int32)), (y_tc - y_ref).abs().max().item()
 
-    # independent check: oracle codes, exact integer convolution in float64 on the CPU
+    # the authority: oracle codes, exact integer convolution in float64 on the CPU
     ph, pw = conv._padding
     xp = torch.nn.functional.pad(x, (pw, pw, ph, ph)).cpu().numpy()
     if preset is None:
@@ -67,6 +66,12 @@ def test_tensor_core_integer_conv_equals_the_float_code_route(case):
         acc = np.maximum(acc, 0)
     want = O.qconv_dequantize(acc.astype(np.int32), F32(s_in * s_w))
     assert np.array_equal(y_tc.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    # ... and the reference's own route (framework convolution on float codes) lands on the same integers
+    assert torch.equal(y_tc.view(torch.int32), y_ref.view(torch.int32)), (y_tc - y_ref).abs().max().item()
+    # deterministic: a second launch gives the same bits (no race between the loader and the tensor core)
+    conv.use_tensor_cores = True
+    with torch.no_grad():
+        assert torch.equal(conv(x).view(torch.int32), y_tc.view(torch.int32))
 
 
 def test_tensor_core_path_declines_what_it_cannot_represent():

@@ -48,10 +48,9 @@ def main():
     if world > 1:
         fqdist.enable_data_parallel(net)
     params = [p for p in net.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, lr=1e-6, capturable=True)
-    bucket = fqdist.GradBucket(params, net=net if world > 1 else None)
-    if world > 1:
-        bucket.attach()
+    opt = torch.optim.Adam(params, lr=1e-6, capturable=True, fused=True)
+    align = int(os.environ.get("FQ_BUCKET_ALIGN", "32"))
+    bucket = fqdist.GradBucket(params, net=net if world > 1 else None, align=align)
     loss_fn = nn.CrossEntropyLoss()
 
     def step():
@@ -90,11 +89,11 @@ def main():
             d[1] += e.time_range.end - e.time_range.start
         out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
         os.makedirs(out_dir, exist_ok=True)
-        with open(os.path.join(out_dir, "r2_qat_kernels_n%d.json" % world), "w") as f:
+        with open(os.path.join(out_dir, "r2_qat_kernels_n%d_align%d.json" % (world, align)), "w") as f:
             json.dump({k: [v[0] / 3, round(v[1] / 3, 2)] for k, v in sorted(full.items(), key=lambda kv: -kv[1][0])}, f, indent=0)
         gaps = sorted(((evs[i + 1].time_range.start - evs[i].time_range.end, evs[i].name[:40], evs[i + 1].name[:40])
                        for i in range(len(evs) - 1)), reverse=True)[:8]
-        print(json.dumps({"n_gpus": world, "graph_ms_per_step": t, "profiled_replays": 3,
+        print(json.dumps({"n_gpus": world, "bucket_align": align, "graph_ms_per_step": t, "profiled_replays": 3,
                           "span_us_per_replay": (t1 - t0) / 3, "kernel_busy_us_per_replay": busy / 3,
                           "kernels_per_replay": len(evs) / 3,
                           "nccl_us_per_replay": sum(e.time_range.end - e.time_range.start for e in nccl) / 3,
