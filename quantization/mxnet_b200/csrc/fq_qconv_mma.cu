@@ -244,33 +244,41 @@ __global__ void __launch_bounds__(kMmaThreads, 1) qconv_igemm_kernel(const QConv
 }
 
 // ---- fp32 NCHW -> zero-padded NHWC 8-bit codes (pad, clip, divide, round: nn/quantized_conv.py:108-109, 54-61) ----
-// One block per (n, padded row).  Codes of the padding are the code of 0.0 under the same clip, as in the reference,
-// which pads first and quantises the padded tensor.
+// One block per (n, padded row): a warp per channel reads that channel's row of W floats (coalesced), quantises with
+// the guarded reciprocal (exactly roundf(clip(x) / scale), fq_common.cuh) and writes the byte into a shared-memory tile
+// [Wp][C + 4] (the +4 keeps the 32 lanes of a warp on 32 different banks); the tile is then written out as whole
+// 32-bit words, coalesced.  Codes of the padding are the code of 0.0 under the same clip, as in the reference, which
+// pads first and quantises the padded tensor.
 __global__ void __launch_bounds__(kThreads) qconv_pack_input_kernel(const float* __restrict__ x, const float* __restrict__ range2,
                                                                     signed char* __restrict__ xq, float* __restrict__ scale_out,
                                                                     int N, int C, int H, int W, int ph, int pw) {
-  extern __shared__ signed char tile[];       // [Wp][C]
-  const int Hp = H + 2 * ph, Wp = W + 2 * pw;
+  extern __shared__ __align__(16) signed char tile[];       // [Wp][C + 4]
+  const int Hp = H + 2 * ph, Wp = W + 2 * pw, Cs = C + 4;
   const int n = blockIdx.x / Hp, hp = blockIdx.x % Hp;
   const float lo = __ldg(range2), hi = __ldg(range2 + 1);
   const float scale = (hi == -lo) ? __fdiv_rn(hi, 127.0f) : __fdiv_rn(__fsub_rn(hi, lo), 255.0f);
+  const QDiv qd = QDiv::make(scale);
+  // (int) -> low 8 bits: int8 codes [-127, 127] and uint8 codes [0, 255] alike
   const signed char pad_code = (signed char)(unsigned char)(int)quant_code(clipf(0.f, lo, hi), scale);
   const int h = hp - ph;
-  if (h < 0 || h >= H) {
-    for (int i = threadIdx.x; i < Wp * C; i += blockDim.x) tile[i] = pad_code;
-  } else {
-    for (int i = threadIdx.x; i < Wp * C; i += blockDim.x) {
-      const int w = i % Wp, c = i / Wp;       // consecutive threads walk W: coalesced reads of one (n, c, h) row
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = warp; c < C; c += nw) {
+    const float* row = (h >= 0 && h < H) ? x + (((int64_t)n * C + c) * H + h) * W : nullptr;
+    for (int w = lane; w < Wp; w += 32) {
       const int ws = w - pw;
       signed char code = pad_code;
-      if (ws >= 0 && ws < W)     // (int) -> low 8 bits: int8 codes [-127, 127] and uint8 codes [0, 255] alike
-        code = (signed char)(unsigned char)(int)quant_code(clipf(__ldg(x + (((int64_t)n * C + c) * H + h) * W + ws), lo, hi), scale);
-      tile[w * C + c] = code;
+      if (row != nullptr && ws >= 0 && ws < W) code = (signed char)(unsigned char)(int)qd.code(clipf(__ldg(row + ws), lo, hi));
+      tile[w * Cs + c] = code;
     }
   }
   __syncthreads();
-  signed char* dst = xq + ((int64_t)n * Hp + hp) * Wp * C;
-  for (int i = threadIdx.x; i < Wp * C; i += blockDim.x) dst[i] = tile[i];
+  const int cw = C >> 2;                                     // C % 16 == 0 (host check): whole words
+  const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tile);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(xq + ((int64_t)n * Hp + hp) * Wp * C);
+  for (int i = threadIdx.x; i < Wp * cw; i += blockDim.x) {
+    const int w = i / cw, j = i - w * cw;
+    dst[i] = t32[w * (cw + 1) + j];
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0 && scale_out != nullptr) scale_out[0] = scale;
 }
 
@@ -310,10 +318,12 @@ int fq_qconv_pack_input(const DLTensor* x_, const DLTensor* range2_, int pad_h, 
   FQ_REQUIRE(xq.bits == 8 && (xq.code == kDLInt || xq.code == kDLUInt) && xq.numel == N * Hp * Wp * C,
              "%s: xq must be (u)int8 [N, H+2ph, W+2pw, C]", who);
   FQ_REQUIRE(so.null || (so.is_f32() && so.numel >= 1), "%s: scale_out must be float32", who);
-  FQ_REQUIRE(Wp * C <= 200 * 1024, "%s: one padded row of %lld x %lld codes does not fit in shared memory", who,
+  FQ_REQUIRE(C % 4 == 0, "%s: C=%lld must be a multiple of 4", who, (long long)C);
+  FQ_REQUIRE(Wp * (C + 4) <= 200 * 1024, "%s: one padded row of %lld x %lld codes does not fit in shared memory", who,
              (long long)Wp, (long long)C);
+  FQ_REQUIRE((reinterpret_cast<uintptr_t>(xq.data) & 3u) == 0, "%s: xq must be 4-byte aligned", who);
   if (x.numel == 0) return 0;
-  const size_t smem = (size_t)(Wp * C);
+  const size_t smem = (size_t)(Wp * (C + 4));
   FQ_CUDA(cudaFuncSetAttribute(qconv_pack_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   qconv_pack_input_kernel<<<(unsigned)(N * Hp), kThreads, smem, (cudaStream_t)stream>>>(
       x.as<const float>(), rg.as<const float>(), xq.as<signed char>(), so.null ? nullptr : so.as<float>(), (int)N, (int)C,

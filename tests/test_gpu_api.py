@@ -505,3 +505,100 @@ def test_winograd_domain_weight_quantisation_through_the_converter(Q, fake_bn):
         y2 = net(x)
         y3 = net(x)
     assert torch.equal(y2, y3) and all(m.fixed_params == 1 for m in net if isinstance(m, nn.Conv2d))
+
+
+def _two_conv_net(Q):
+    torch.manual_seed(0)
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = nn.Conv2d(3, 8, 3, padding=1)
+            self.b = nn.Conv2d(8, 8, 3, padding=1)
+            self.use_b = True
+
+        def forward(self, x):
+            y = torch.relu(self.a(x))
+            return self.b(y) if self.use_b else y
+    net = Net().cuda()
+    Q.convert.convert_model(net)
+    for i, m in enumerate(net.collect_quantized_blocks()):
+        m.name = "conv%d" % i
+    Q.init.qparams_init(net)
+    net.disable_quantize()
+    return net
+
+
+def test_collect_feature_maps_checks_every_batch_like_the_reference(Q):
+    """distribution_calibrate.py:35-36 asserts on EVERY batch; round 1 only looked at batch 0.  The histogram kernel
+    now raises a device flag for a negative value or a NaN in any batch."""
+    net = _two_conv_net(Q)
+    g = torch.Generator().manual_seed(1)
+    good = [torch.rand(4, 3, 16, 16, generator=g) for _ in range(3)]
+    dev = torch.device("cuda")
+    h, m = Q.dc.collect_feature_maps(net, 2048, [(b, None) for b in good], dev)
+    assert len(h) == 2
+    bad = [b.clone() for b in good]
+    bad[2][1, 0, 3, 3] = -0.25                       # a negative value in the LAST batch only
+    with pytest.raises(AssertionError, match="Activation should >=0"):
+        Q.dc.collect_feature_maps(net, 2048, [(b, None) for b in bad], dev)
+    bad = [b.clone() for b in good]
+    bad[1][0, 2, 5, 5] = float("nan")                # NaN in the middle batch (np.min would be NaN there)
+    with pytest.raises(AssertionError, match="Activation should >=0"):
+        Q.dc.collect_feature_maps(net, 2048, [(b, None) for b in bad], dev)
+    neg_zero = [b.clone() for b in good]
+    neg_zero[1][0, 0, 0, 0] = -0.0                   # -0.0 >= 0 is True in NumPy as well
+    h2, _ = Q.dc.collect_feature_maps(net, 2048, [(b, None) for b in neg_zero], dev)
+    assert len(h2) == 2
+
+
+def test_collect_feature_maps_with_a_block_that_is_not_called_in_every_batch(Q):
+    """a block skipped in some batches used to trip the 2048-vs-2049-bin consistency check, and a block
+    never called made kl_calibrate_all raise KeyError."""
+    net = _two_conv_net(Q)
+    g = torch.Generator().manual_seed(2)
+    batches = [torch.rand(4, 3, 16, 16, generator=g) * 300 for _ in range(4)]     # max >= 256: the 2049th bin appears
+    dev = torch.device("cuda")
+    calls = iter([True, False, True, False])
+
+    class Loader:
+        def __len__(self):
+            return len(batches)
+
+        def __iter__(self):
+            for b in batches:
+                net.use_b = next(calls)
+                yield b, None
+    h, m = Q.dc.collect_feature_maps(net, 2048, Loader(), dev)
+    blocks = net.collect_quantized_blocks()
+    assert set(h.keys()) == set(blocks)
+    # block b saw batches 0 and 2 only
+    acts = []
+    net.use_b = True
+    hook = blocks[1].register_forward_hook(lambda mod, x, y: acts.append(x[0].cpu().numpy()))
+    with torch.no_grad():
+        for i in (0, 2):
+            net(batches[i].cuda())
+    hook.remove()
+    want_max = F32(acts[0].max())                    # frozen max of the first batch this block saw
+    want = np.zeros(2049, F32)
+    for a in acts:                                   # the library's default promotion regime is "legacy"
+        c = O.histogram_counts(a, 2048, want_max, "legacy").astype(F32)
+        want[:len(c)] += c
+    got = h[blocks[1]]
+    assert m[blocks[1]] == want_max
+    assert np.array_equal(got, want[:len(got)]) and want[len(got):].sum() == 0
+    # a block that is never called: no histogram, and the all-layer search skips it
+    net.use_b = False
+
+    class Loader2:
+        def __len__(self):
+            return 2
+
+        def __iter__(self):
+            for b in batches[:2]:
+                yield b, None
+    h, m = Q.dc.collect_feature_maps(net, 2048, Loader2(), dev)
+    assert set(h.keys()) == {blocks[0]}
+    best = Q.dc.kl_calibrate_all(h, 256, 256, 2048)
+    assert best.shape == (2,) and int(best[0]) >= 256
