@@ -125,6 +125,20 @@ FQ_API int fq_forward_online(const DLTensor* x, int64_t n_samples, int bits, int
                       int promotion, const DLTensor* input_max, const DLTensor* y, const DLTensor* codes,
                       const DLTensor* cur_max, const DLTensor* qparams, const DLTensor* per_sample,
                       void* ws, void* stream);
+/* Persistent argument block ("call plan") of one converted block's input path: everything fq_forward_online takes
+ * except the addresses of the activation and of its quantised copy is captured once (the plan keeps its own copies
+ * of the descriptors; the state tensors cur_max / qparams / input_max / per_sample must stay where they are while
+ * the plan lives).  fq_input_plan_run(plan, x, y, ws, stream) is then exactly
+ * fq_forward_online(x_like with data = x, ..., y_like with data = y, ...) -- same kernels, same checks, same results --
+ * at four machine words per call.  quantize == 0: range tracking only (y ignored).  A plan is immutable after
+ * creation; it may be run concurrently with different workspaces / streams.
+ * Replaces the per-forward Python of convert_conv2d.py:55-66 / convert_dense.py:41-49. */
+typedef struct FqInputPlan FqInputPlan;
+FQ_API int fq_input_plan_create(const DLTensor* x_like, int64_t n_samples, int bits, int is_signed, int lo_mode,
+                                int promotion, const DLTensor* input_max, int quantize, const DLTensor* cur_max,
+                                const DLTensor* qparams, const DLTensor* per_sample, FqInputPlan** out);
+FQ_API int fq_input_plan_run(const FqInputPlan* plan, const void* x_data, void* y_data, void* ws, void* stream);
+FQ_API int fq_input_plan_destroy(FqInputPlan* plan);
 /* The online input path when the per-sample maxima come from outside (data parallel: the all-gathered maxima of
  * the GLOBAL batch, [N] in sample order): Kahan mean -> cur_max[0], scale math -> qparams[4], quantise -- one launch
  * for latency-bound tensors (every block derives the mean itself), three for large or ragged ones. */

@@ -78,6 +78,10 @@ SIGNATURES = {
     "fq_forward_rows": (_c.c_int, [P, _c.c_int64, P, P, P, _c.c_void_p]),
     "fq_forward_online": (_c.c_int, [P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, P, P, P, P, P, P,
                                      _c.c_void_p, _c.c_void_p]),
+    "fq_input_plan_create": (_c.c_int, [P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, P, _c.c_int, P, P, P,
+                                        _c.POINTER(_c.c_void_p)]),
+    "fq_input_plan_run": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "fq_input_plan_destroy": (_c.c_int, [_c.c_void_p]),
     "fq_forward_from_maxima": (_c.c_int, [P, P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, P, P, P, P, _c.c_void_p]),
     "fq_quant_weight": (_c.c_int, [P, _c.c_int64, _c.c_int, P, P, P, P, P, P, P, P, P, _c.c_void_p, _c.c_void_p]),
     "fq_quant_weight_multi": (_c.c_int, [_c.POINTER(FqWeightJob), _c.c_int, P, P, P, _c.c_void_p, _c.c_void_p]),
@@ -215,9 +219,21 @@ def current_stream():
 _workspaces = {}
 
 
+def workspace_for(dev, raw):
+    """Raw address (int) of the workspace of (device index, raw stream handle)."""
+    ws = _workspaces.get((dev, raw))
+    if ws is None:
+        workspace(dev)
+        ws = _workspaces[(dev, raw)]
+    return ws[2]
+
+
 def workspace(device=None):
     """Zero-initialised scratch for the fused kernels: one per (device, stream)."""
-    dev = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    if isinstance(device, int):
+        dev = device
+    else:
+        dev = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
     raw = _raw_stream(dev)
     ws = _workspaces.get((dev, raw))
     if ws is None:
@@ -226,5 +242,5 @@ def workspace(device=None):
         with torch.cuda.device(dev):
             ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
             check_call(lib.fq_workspace_init(_c.c_void_p(ws.data_ptr()), nbytes, _c.c_void_p(raw)))
-        _workspaces[(dev, raw)] = ws = (ws, _c.c_void_p(ws.data_ptr()))
+        _workspaces[(dev, raw)] = ws = (ws, _c.c_void_p(ws.data_ptr()), ws.data_ptr())
     return ws[1]

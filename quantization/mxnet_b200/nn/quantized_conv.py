@@ -144,9 +144,11 @@ class Conv2D(nn.Module):
                 _, bias_q = ops.forward_scalar(bias.detach(), torch.cat([b_scale, b_scale, -b_max, b_max]),
                                                codes_dtype=torch.int32)
             # the reference multiplies float32 casts of the integer codes and casts the result to int32 (:149-153).
-            # Its F.dot is exact on integers below 2^24; cuDNN may pick a Winograd / FFT algorithm, which is not
-            # (1301.9999 would truncate to 1301), so the exact integer is restored by rounding before the cast.
-            acc = nn.functional.conv2d(inputs_q.float(), weight_q.float(), None, self._strides, 0, 1, self._groups)
+            # Its F.dot is exact while the partial sums stay below 2^24.  A framework convolution is not: cuDNN may
+            # pick a Winograd / FFT algorithm whose float32 error on sums of ~10^6 exceeds 1 (seen at K = 2304), so
+            # this route convolves the codes in float64 -- exact below 2^53 whatever the algorithm -- and rounds
+            # before the cast.  (The tensor-core route above is exact by construction and is the fast one.)
+            acc = nn.functional.conv2d(inputs_q.double(), weight_q.double(), None, self._strides, 0, 1, self._groups)
             acc = torch.round(acc).to(torch.int32)
             if bias_q is not None:
                 acc = acc + bias_q.reshape(1, -1, 1, 1)

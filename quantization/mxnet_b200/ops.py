@@ -172,6 +172,61 @@ def forward_online(x, bits=8, signed=False, lo_mode=LO_ZERO, input_max=None, qua
     return (y, cur_max, qparams, codes) if codes_dtype is not None else (y, cur_max, qparams)
 
 
+class InputPlan:
+    """The input path of ONE converted block as a C-side call plan (fq.h fq_input_plan_*): every argument of
+    :func:`forward_online` except the activation's address is captured once; ``run`` then costs an output allocation
+    and one foreign call with five integers -- about a third of the host time of building seven DLTensor structs per
+    forward (tools/eager_profile.py).  Results are those of :func:`forward_online`: the plan calls the same entry point.
+
+    The plan borrows the block's state tensors; ``matches`` tells whether they (and the activation's shape) are
+    still the ones it was built for.
+    """
+    __slots__ = ("handle", "shape", "device", "dev_index", "cur_max", "qparams", "input_max_ptr", "input_max",
+                 "per_sample", "quantize", "sig", "_run", "_keep", "__weakref__")
+
+    def __init__(self, x, bits, signed, lo_mode, input_max=None, quantize=True, cur_max=None, qparams=None,
+                 per_sample=None, n_samples=None, promotion=None, sig=None):
+        x = _f32(x)
+        lib = _lib()
+        n_samples = x.shape[0] if n_samples is None else n_samples
+        a, im, cm, q, ps = dl(x), dl(input_max), dl(cur_max), dl(qparams), dl(per_sample)
+        h = _ffi._c.c_void_p()
+        check_call(lib.fq_input_plan_create(a.ptr, n_samples, bits, int(bool(signed)), lo_mode, _promo(promotion),
+                                            ptr(im), int(bool(quantize)), cm.ptr, ptr(q), ptr(ps), _ffi._c.byref(h)))
+        self.handle = h.value
+        self.shape = x.shape
+        self.device = x.device
+        self.dev_index = x.device.index or 0
+        self.cur_max, self.qparams, self.per_sample, self.input_max = cur_max, qparams, per_sample, input_max
+        self.input_max_ptr = None if input_max is None else input_max.data_ptr()
+        self.quantize = bool(quantize)
+        self.sig = sig
+        self._run = lib.fq_input_plan_run
+        self._keep = (cur_max, qparams, per_sample, input_max)      # the plan holds raw addresses of these
+
+    def __del__(self):
+        h, self.handle = self.handle, None
+        if h:
+            try:
+                _lib().fq_input_plan_destroy(h)
+            except Exception:       # interpreter shutdown
+                pass
+
+    def run(self, x, out=None):
+        """x: float32 CUDA tensor of the plan's shape (checked by the caller through ``shape``).  Returns y (None
+        for a range-only plan)."""
+        if not x.is_contiguous():
+            x = x.contiguous()
+        y = None
+        if self.quantize:
+            y = torch.empty_like(x) if out is None else out
+        dev = self.dev_index
+        raw = _ffi._raw_stream(dev)
+        if self._run(self.handle, x.data_ptr(), 0 if y is None else y.data_ptr(), _ffi.workspace_for(dev, raw), raw):
+            check_call(-1)
+        return y
+
+
 def forward_from_maxima(x, maxima, bits=8, signed=False, lo_mode=LO_ZERO, out=None, cur_max=None, qparams=None,
                         promotion=None):
     """Online input path with per-sample maxima supplied by the caller (data parallel: the all-gathered maxima of
@@ -296,19 +351,29 @@ class WeightPlan:
         return len(jobs) == self.n and self.pointers(jobs) == self.ptrs
 
 
-def quant_weight_multi(plan):
-    """Run every job of ``plan`` (two launches per 30 jobs).  Returns lists (w_q, bias_folded or None, scales or
-    None), views into three freshly allocated flat buffers; results equal :func:`quant_weight` per block."""
+def weight_multi_buffers(plan):
+    """(w_flat, b_flat, s_flat, [w_q views], [folded-bias views or None], [scale views or None]) for one call of
+    :func:`quant_weight_multi`; a caller that does not keep results across calls may reuse them."""
     dev = plan.device
     w_flat = torch.empty(plan.w_total, dtype=torch.float32, device=dev)
     b_flat = torch.empty(max(plan.bias_total, 1), dtype=torch.float32, device=dev)
     s_flat = torch.empty(max(plan.scale_total, 1), dtype=torch.float32, device=dev)
-    wf, bf, sf = dl(w_flat), dl(b_flat), dl(s_flat)
-    check_call(_lib().fq_quant_weight_multi(plan.table, plan.n, wf.ptr, bf.ptr, sf.ptr, workspace(dev), current_stream()))
     ws = [w_flat[o:o + n].view(shape) for o, n, shape in plan.w_slices]
     bs = [None if sl is None else b_flat[sl[0]:sl[0] + sl[1]] for sl in plan.bias_slices]
     ss = [None if sl is None else s_flat[sl[0]:sl[0] + sl[1]] for sl in plan.scale_slices]
-    return ws, bs, ss
+    return w_flat, b_flat, s_flat, ws, bs, ss, (dl(w_flat), dl(b_flat), dl(s_flat))
+
+
+def quant_weight_multi(plan, buffers=None):
+    """Run every job of ``plan`` (two launches per 30 jobs).  Returns lists (w_q, bias_folded or None, scales or
+    None), views into three flat buffers -- freshly allocated unless ``buffers`` (from :func:`weight_multi_buffers`)
+    is given; results equal :func:`quant_weight` per block."""
+    if buffers is None:
+        buffers = weight_multi_buffers(plan)
+    wf, bf, sf = buffers[6]
+    dev = plan.device.index or 0
+    check_call(_lib().fq_quant_weight_multi(plan.table, plan.n, wf.ptr, bf.ptr, sf.ptr, workspace(dev), current_stream()))
+    return buffers[3], buffers[4], buffers[5]
 
 
 def fold_backward_multi(jobs):

@@ -94,25 +94,51 @@ def _wino_path(weight, m):
     return ops.quant_weight_wino(weight, G, GI, GTI, m.quantize_args.wt_width)[0]
 
 
+def _planned_input_path(x, m, lo_mode, quantize, per):
+    """ops.forward_online for block ``m`` through a cached C-side call plan (ops.InputPlan): the block's state tensors
+    and quantiser settings are captured once per (mode, activation shape); a forward then costs one output
+    allocation and one foreign call.  The plan is rebuilt when any tensor it borrowed has been replaced (``net.to()``
+    re-packs the state arenas) -- identity checks on the block's own dicts, no Module.__getattr__."""
+    d = m.__dict__
+    bufs = m._buffers
+    offline = quantize and m.quantize_input_offline
+    cur = bufs["current_input_max"]
+    qp = bufs["_fq_qparams"] if quantize else None
+    key = (quantize, offline, lo_mode, ops.get_promotion(), x.shape)
+    plans = d.get("_fq_in_plans")
+    if plans is None:
+        plans = d["_fq_in_plans"] = {}
+    plan = plans.get(key)
+    if (plan is None or plan.cur_max is not cur or plan.qparams is not qp or plan.per_sample is not per
+            or plan.device != x.device or (offline and plan.input_max_ptr != m._parameters["input_max"].data_ptr())):
+        qa = m.quantize_args
+        if len(plans) >= 8:         # a loader with many ragged batch shapes: do not grow without bound
+            plans.clear()
+        plan = plans[key] = ops.InputPlan(x, qa.in_width, qa.in_signed, lo_mode,
+                                          input_max=m._parameters["input_max"].data if offline else None,
+                                          quantize=quantize, cur_max=cur, qparams=qp, per_sample=per)
+    if x.dtype is not torch.float32:
+        raise ops._ffi.FQError("x must be float32, got %s" % x.dtype)
+    return plan.run(x)
+
+
 class _InputPath(torch.autograd.Function):
     """convert_conv2d.py:56-66 on the device; backward = identity (ste_func.py:43-44)."""
 
     @staticmethod
     def forward(ctx, x, m, lo_mode):
-        qa = m.quantize_args
-        group = getattr(m, "_fq_dist_group", None)
+        d = m.__dict__
+        group = d.get("_fq_dist_group")
         if group is not None and not m.quantize_input_offline:
+            qa = m.quantize_args
             allmax = _global_range(x, m, group)      # data parallel + online: range over the global batch first
             return ops.forward_from_maxima(x, allmax, qa.in_width, qa.in_signed, lo_mode, cur_max=m.current_input_max,
                                            qparams=m._fq_qparams)[0]
         # single process, or offline range: one fused launch.  Under data parallelism the per-sample maxima
         # are kept and the global mean is taken for ALL layers by one collective in update_ema().
         per = _per_sample_buffer(m, x.shape[0]) if group is not None else None
-        y, _, _ = ops.forward_online(
-            x, qa.in_width, qa.in_signed, lo_mode,
-            input_max=m.input_max.data if m.quantize_input_offline else None,
-            quantize=True, cur_max=m.current_input_max, qparams=m._fq_qparams, per_sample=per)
-        m._fq_range_pending = group is not None
+        y = _planned_input_path(x, m, lo_mode, True, per)
+        d["_fq_range_pending"] = group is not None
         return y
 
     @staticmethod
@@ -122,11 +148,11 @@ class _InputPath(torch.autograd.Function):
 
 def _range_only(x, m):
     """quantize_input switched off: the range is still tracked (convert_conv2d.py:55-57)."""
-    group = getattr(m, "_fq_dist_group", None)
+    d = m.__dict__
+    group = d.get("_fq_dist_group")
     per = _per_sample_buffer(m, x.shape[0]) if group is not None else None
-    ops.forward_online(x, m.quantize_args.in_width, m.quantize_args.in_signed, ops.LO_ZERO, quantize=False,
-                       cur_max=m.current_input_max, per_sample=per)
-    m._fq_range_pending = group is not None
+    _planned_input_path(x, m, ops.LO_ZERO, False, per)
+    d["_fq_range_pending"] = group is not None
 
 
 def _as_rows(tensors):
@@ -292,9 +318,26 @@ class _MultiWeightPath(torch.autograd.Function):
         return tuple(out)
 
 
-def prequantize_weights(net, blocks):
-    """Net-level forward pre-hook body: run the weight path of every block that needs one in this forward as a
-    single multi-tensor launch and hand each block its result through ``_fq_pre``."""
+_SIG_TENSORS = ("weight", "bias", "gamma", "running_mean")
+
+
+def _weights_signature(blocks):
+    """What decides the job list of :func:`prequantize_weights` and whether its cached C job table is still valid:
+    per block the tri-state / switches and the storage addresses of the tensors a job borrows (beta and running_var
+    are created, packed and moved together with gamma / running_mean).  Reads the blocks' own dicts only."""
+    sig = []
+    for m in blocks:
+        d, p = m.__dict__, m._parameters
+        sig.append(d.get("fixed_params"))
+        sig.append(d.get("enable_quantize"))
+        sig.append(id(d.get("quantize_args")))
+        for name in _SIG_TENSORS:
+            t = p.get(name)
+            sig.append(None if t is None else t.data_ptr())
+    return sig
+
+
+def _collect_weight_jobs(blocks):
     jobs, owners = [], []
     for m in blocks:
         qa = m.quantize_args
@@ -320,34 +363,64 @@ def prequantize_weights(net, blocks):
         else:
             continue
         if not m.weight.is_cuda:
-            return
+            return [], []
         if any(t is not None and (t.dtype != torch.float32 or not t.is_contiguous()) for t in jb.values()
                if isinstance(t, torch.Tensor)):
             continue                          # e.g. a channels_last weight: the per-block path copies it afresh each call
         jobs.append(jb)
         owners.append(m)
-    if len(jobs) < 2:
+    return jobs, owners
+
+
+def prequantize_weights(net, blocks):
+    """Net-level forward pre-hook body: run the weight path of every block that needs one in this forward as a
+    single multi-tensor launch and hand each block its result through ``_fq_pre``.
+
+    Host cost matters here (an eager forward of a small network is bound by it): the job list, the C job table and
+    -- without autograd -- the output buffers are cached on the net and revalidated per forward by one flat list
+    comparison (:func:`_weights_signature`)."""
+    nd = net.__dict__
+    sig = _weights_signature(blocks)
+    cache = nd.get("_fq_weight_plan")
+    if cache is None or cache["sig"] != sig:
+        jobs, owners = _collect_weight_jobs(blocks)
+        # the plan holds raw DLTensors: it is only valid while EVERY tensor of every job is the same storage
+        cache = nd["_fq_weight_plan"] = {
+            "sig": sig, "jobs": jobs, "owners": owners, "plan": ops.WeightPlan(jobs) if len(jobs) >= 2 else None,
+            "folds": [jb.get("gamma") is not None for jb in jobs], "outs": {},
+            "grad_tensors": [t for jb in jobs for t in (jb["w"], jb.get("gamma"), jb.get("beta"), jb.get("bias"))
+                             if t is not None]}
+    plan = cache["plan"]
+    if plan is None:
         return                                # nothing to batch: the per-block path is just as good
-    # the cached plan holds raw DLTensors: it is only valid while EVERY tensor of every job is the same storage
-    key = (tuple((id(m), jb["bits"], jb["rows"]) for m, jb in zip(owners, jobs)), ops.WeightPlan.pointers(jobs))
-    plan = getattr(net, "_fq_weight_plan", None)
-    if plan is None or plan[0] != key:
-        plan = (key, ops.WeightPlan(jobs))
-        net._fq_weight_plan = plan
-    needs_grad = torch.is_grad_enabled() and any(
-        t is not None and t.requires_grad for jb in jobs for t in (jb["w"], jb.get("gamma"), jb.get("beta"), jb.get("bias")))
-    if needs_grad:
+    jobs, owners = cache["jobs"], cache["owners"]
+    if torch.is_grad_enabled() and any(t.requires_grad for t in cache["grad_tensors"]):
         flat = []
         for jb in jobs:
             flat.extend([jb["w"], jb.get("bias") if jb.get("gamma") is not None else None, jb.get("gamma"), jb.get("beta")])
-        outs = iter(_MultiWeightPath.apply(plan[1], jobs, *flat))
-        for m, jb in zip(owners, jobs):
+        outs = iter(_MultiWeightPath.apply(plan, jobs, *flat))
+        for m, fold in zip(owners, cache["folds"]):
             wq = next(outs)
-            m._fq_pre = (wq, next(outs) if jb.get("gamma") is not None else None)
-    else:
-        ws, bs, _ = ops.quant_weight_multi(plan[1])
+            m.__dict__["_fq_pre"] = (wq, next(outs) if fold else None)
+        return
+    # no autograd: nothing outlives the forward, so the quantised weights are written into buffers that persist per
+    # stream (stream order protects the previous forward's readers) -- no allocation and no 3 x len(jobs) view
+    # objects per call.  Not while a CUDA graph is being captured: a graph gets buffers of its own pool.
+    if torch.cuda.is_current_stream_capturing():
+        ws, bs, _ = ops.quant_weight_multi(plan)
         for i, m in enumerate(owners):
-            m._fq_pre = (ws[i], bs[i])
+            m.__dict__["_fq_pre"] = (ws[i], bs[i])
+        return
+    raw = ops._ffi._raw_stream(plan.device.index or 0)
+    held = cache["outs"].get(raw)
+    if held is None:
+        if len(cache["outs"]) >= 4:
+            cache["outs"].clear()
+        bufs = ops.weight_multi_buffers(plan)
+        held = cache["outs"][raw] = (bufs, [(w, b) for w, b in zip(bufs[3], bufs[4])])
+    ops.quant_weight_multi(plan, held[0])
+    for m, pre in zip(owners, held[1]):
+        m.__dict__["_fq_pre"] = pre
 
 
 def _weight_rows(m):

@@ -75,7 +75,8 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
 
     """ Add hooks to quantized blocks """
     hooks = []
-    first_batch = {}        # block index -> inputs seen in batch 0 (kept until its max is known)
+    first_batch = {}        # block index -> inputs of the first batch the block runs in (kept until its max is known)
+    have_max = set()        # blocks whose max is frozen
     called = set()
     called_rows = []        # per batch: which blocks were called (the 2049th-bin check only looks at those)
     pending = {}            # block index -> this batch's input, for the single multi-tensor launch
@@ -93,7 +94,9 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
                 state["ring"].dtype == torch.int32:
             raise RuntimeError("a layer input of %d elements is larger than any of the first batch (%d): the 32-bit "
                                "count exchange was sized for the first batch" % (x.numel(), state["max_numel"]))
-        if n_batches == 0:
+        if i not in have_max:
+            # the first batch in which THIS block runs fixes its max (fm_max_collector.get(m) is None, :97-102) --
+            # batch 0 for a plain network, a later one for a block behind a data-dependent branch
             first_batch.setdefault(i, []).append(x)
             versions[id(x)] = x._version
         elif x.data_ptr() % 16 == 0 and i not in pending:
@@ -117,8 +120,8 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
         with tqdm(total=len(loader), desc=tqdm_desc, disable=None) as pbar, torch.no_grad():
             for X in _prefetch(loader, ctx):
                 _ = net(X)
-                if n_batches == 0:
-                    # First chunk: min/max of everything the block saw, then its histogram
+                if first_batch:
+                    # First chunk of these blocks: min/max of everything the block saw, then its histogram
                     for i, xs in first_batch.items():
                         mm = state["minmax"][i]
                         ops.minmax(_unchanged(xs[0]), out=mm)
@@ -127,11 +130,13 @@ def collect_feature_maps(net, bins, loader, ctx=None, tqdm_desc="Collect FM", gr
                             mm[0:1].copy_(torch.minimum(mm[0:1], mm2[0:1]))
                             mm[1:2].copy_(torch.maximum(mm[1:2], mm2[1:2]))
                     fqdist.sync_first_batch_minmax(state["minmax"], group)
-                    _alloc_ring(max(x.numel() for xs in first_batch.values() for x in xs))
+                    if "ring" not in state:
+                        _alloc_ring(max(x.numel() for xs in first_batch.values() for x in xs))
                     for i, xs in first_batch.items():
                         for x in xs:
                             ops.hist_nonzero(x, state["minmax"][i, 1:2], bins, state["ring"].slot()[i],
                                              bad_flag=state["bad"][i:i + 1])
+                    have_max.update(first_batch)
                     first_batch.clear()
                 if pending:
                     # every layer of the batch in ONE launch, blocks shared out by tensor size

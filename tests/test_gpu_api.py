@@ -552,32 +552,34 @@ def test_collect_feature_maps_checks_every_batch_like_the_reference(Q):
     assert len(h2) == 2
 
 
-def test_collect_feature_maps_with_a_block_that_is_not_called_in_every_batch(Q):
+@pytest.mark.parametrize("schedule", [(True, False, True, False), (False, True, True, False)],
+                         ids=["from_batch0", "first_seen_in_batch1"])
+def test_collect_feature_maps_with_a_block_that_is_not_called_in_every_batch(Q, schedule):
     """a block skipped in some batches used to trip the 2048-vs-2049-bin consistency check, and a block
-    never called made kl_calibrate_all raise KeyError."""
+    never called made kl_calibrate_all raise KeyError.  A block's max is frozen by the first batch IT runs in
+    (distribution_calibrate.py:97-102), which need not be batch 0."""
     net = _two_conv_net(Q)
     g = torch.Generator().manual_seed(2)
     batches = [torch.rand(4, 3, 16, 16, generator=g) * 300 for _ in range(4)]     # max >= 256: the 2049th bin appears
     dev = torch.device("cuda")
-    calls = iter([True, False, True, False])
+    # the NET decides per forward (the loader is read one batch ahead by the prefetcher)
+    plan = iter(schedule)
+    inner = net.forward
 
-    class Loader:
-        def __len__(self):
-            return len(batches)
-
-        def __iter__(self):
-            for b in batches:
-                net.use_b = next(calls)
-                yield b, None
-    h, m = Q.dc.collect_feature_maps(net, 2048, Loader(), dev)
+    def scheduled(x):
+        net.use_b = next(plan)
+        return inner(x)
+    net.forward = scheduled
+    h, m = Q.dc.collect_feature_maps(net, 2048, [(b, None) for b in batches], dev)
+    net.forward = inner
     blocks = net.collect_quantized_blocks()
     assert set(h.keys()) == set(blocks)
-    # block b saw batches 0 and 2 only
+    ran = [i for i, on in enumerate(schedule) if on]
     acts = []
     net.use_b = True
     hook = blocks[1].register_forward_hook(lambda mod, x, y: acts.append(x[0].cpu().numpy()))
     with torch.no_grad():
-        for i in (0, 2):
+        for i in ran:
             net(batches[i].cuda())
     hook.remove()
     want_max = F32(acts[0].max())                    # frozen max of the first batch this block saw
@@ -588,17 +590,105 @@ def test_collect_feature_maps_with_a_block_that_is_not_called_in_every_batch(Q):
     got = h[blocks[1]]
     assert m[blocks[1]] == want_max
     assert np.array_equal(got, want[:len(got)]) and want[len(got):].sum() == 0
+    # block a ran in every batch
+    acts0 = [b.numpy() for b in batches]
+    want0_max = F32(acts0[0].max())
+    want0 = np.zeros(2049, F32)
+    for a in acts0:
+        c = O.histogram_counts(a, 2048, want0_max, "legacy").astype(F32)
+        want0[:len(c)] += c
+    got0 = h[blocks[0]]
+    assert m[blocks[0]] == want0_max and np.array_equal(got0, want0[:len(got0)])
     # a block that is never called: no histogram, and the all-layer search skips it
     net.use_b = False
-
-    class Loader2:
-        def __len__(self):
-            return 2
-
-        def __iter__(self):
-            for b in batches[:2]:
-                yield b, None
-    h, m = Q.dc.collect_feature_maps(net, 2048, Loader2(), dev)
+    h, m = Q.dc.collect_feature_maps(net, 2048, [(b, None) for b in batches[:2]], dev)
     assert set(h.keys()) == {blocks[0]}
     best = Q.dc.kl_calibrate_all(h, 256, 256, 2048)
     assert best.shape == (2,) and int(best[0]) >= 256
+
+
+@pytest.mark.parametrize("mode", ["online", "offline", "range_only"])
+@pytest.mark.parametrize("shape,bits_,signed", [((128, 16, 32, 32), 8, False), ((3, 5, 7, 4), 4, True),
+                                                ((64, 96, 56, 56), 8, False)])
+def test_input_plan_is_forward_online_with_a_persistent_argument_block(Q, mode, shape, bits_, signed):
+    """fq_input_plan_run(plan, x, y) == fq_forward_online(x, ..., y): same kernels, captured arguments."""
+    ops = Q.ops
+    g = torch.Generator().manual_seed(11)
+    lo = ops.LO_NEG_MAX if signed else ops.LO_ZERO
+    imax = torch.tensor([1.7], device="cuda") if mode == "offline" else None
+    quant = mode != "range_only"
+    cm_a, cm_b = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    qp_a, qp_b = torch.zeros(4, device="cuda"), torch.zeros(4, device="cuda")
+    ps_a = torch.zeros(shape[0], device="cuda")
+    ps_b = torch.zeros(shape[0], device="cuda")
+    x0 = torch.randn(*shape, generator=g).cuda()
+    plan = ops.InputPlan(x0, bits_, signed, lo, input_max=imax, quantize=quant, cur_max=cm_a,
+                         qparams=qp_a if quant else None, per_sample=ps_a)
+    for seed in range(3):                       # the plan is reused with new activations at new addresses
+        x = (torch.randn(*shape, generator=g) * (seed + 1)).cuda()
+        y_a = plan.run(x)
+        y_b, _, _ = ops.forward_online(x, bits_, signed, lo, input_max=imax, quantize=quant, cur_max=cm_b,
+                                       qparams=qp_b, per_sample=ps_b)
+        assert (y_a is None) == (y_b is None) == (not quant)
+        if quant:
+            assert torch.equal(y_a.view(torch.int32), y_b.view(torch.int32))
+            assert torch.equal(qp_a.view(torch.int32), qp_b.view(torch.int32))
+        assert torch.equal(cm_a, cm_b) and torch.equal(ps_a, ps_b) and float(cm_a) > 0
+    if quant:                                   # a quantising plan without an output is an error, not a crash
+        from quantization.mxnet_b200 import _ffi
+        raw = _ffi._raw_stream(0)
+        with pytest.raises(_ffi.FQError, match="y is required"):
+            _ffi.check_call(_ffi.load().fq_input_plan_run(plan.handle, x.data_ptr(), 0, _ffi.workspace_for(0, raw), raw))
+
+
+def test_eager_host_caches_follow_weight_updates_flag_switches_and_moves(Q):
+    """The call plans / cached weight job table / persistent no-grad output buffers must never serve stale data:
+    in-place weight updates, enable/disable, offline switch, a new bias, ragged batch shapes and net.to() round trips
+    all give what a freshly converted copy of the same network gives."""
+    def fresh_like(net):
+        twin, _ = build(Q, "cifar_resnet20_v1", 10)
+        twin.load_state_dict(net.state_dict())
+        twin.batch_weight_paths = False                     # the per-block launches, no net-level cache
+        for a, b in zip(net.collect_quantized_blocks(), twin.collect_quantized_blocks()):
+            b.enable_quantize, b.quantize_input, b.quantize_input_offline = a.enable_quantize, a.quantize_input, \
+                a.quantize_input_offline
+        return twin
+
+    net, _ = build(Q, "cifar_resnet20_v1", 10)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(16, 3, 32, 32, generator=g).cuda()
+    x_small = torch.randn(5, 3, 32, 32, generator=g).cuda()
+
+    def check(tag):
+        twin = fresh_like(net)
+        with torch.no_grad():
+            for inp in (x, x_small, x):
+                a, b = net(inp), twin(inp)
+                assert torch.equal(a, b), (tag, (a - b).abs().max().item())
+        for p, q in zip(net.collect_quantized_blocks(), twin.collect_quantized_blocks()):
+            if p.enable_quantize:       # a disabled block tracks nothing: it keeps whatever it saw last
+                assert torch.equal(p.current_input_max, q.current_input_max), tag
+
+    check("first")
+    check("second forward reuses every cache")
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() == 4:
+                p.mul_(0.75)                                # what an optimizer step does: same storage, new values
+    check("in-place weight update")
+    net.update_ema(0.5)
+    net.quantize_input(True, online=False)
+    check("offline ranges")
+    net.quantize_input(True, online=True)
+    net.disable_quantize()
+    check("disabled")
+    net.enable_quantize()
+    net.collect_quantized_blocks()[3].enable_quantize = False
+    check("one block disabled")
+    net.enable_quantize()
+    net.cpu()
+    net.cuda()                                              # state arenas re-packed at new addresses
+    check("after a round trip through the host")
+    with torch.enable_grad():                               # autograd forwards allocate fresh outputs in between
+        net(x).sum().backward()
+    check("after an autograd step")

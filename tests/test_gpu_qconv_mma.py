@@ -66,7 +66,8 @@ def test_tensor_core_integer_conv_equals_the_float_code_route(case):
         acc = np.maximum(acc, 0)
     want = O.qconv_dequantize(acc.astype(np.int32), F32(s_in * s_w))
     assert np.array_equal(y_tc.cpu().numpy().view(np.uint32), want.view(np.uint32))
-    # ... and the reference's own route (framework convolution on float codes) lands on the same integers
+    # ... and the reference's own route (a product of float casts of the codes, :149-153; here a float64 framework
+    # convolution, exact below 2^53 whatever algorithm cuDNN picks) lands on the same integers
     assert torch.equal(y_tc.view(torch.int32), y_ref.view(torch.int32)), (y_tc - y_ref).abs().max().item()
     # deterministic: a second launch gives the same bits (no race between the loader and the tensor core)
     conv.use_tensor_cores = True
