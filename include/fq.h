@@ -260,7 +260,8 @@ FQ_API int fq_qconv_dequantize(const DLTensor* acc_i32, const DLTensor* s_in, co
  * fq_qconv_pack_input: fp32 NCHW x -> spatially zero-padded NHWC 8-bit codes xq [N, H+2ph, W+2pw, C] with the
  *   arithmetic of fq_qconv_quantize (clip, divide by scale, roundf); the padding holds the code of 0.0, because the
  *   reference pads first and quantises the padded tensor (:108-116).  int8 xq for symmetric ranges, uint8 xq for
- *   [0, max] ranges (the caller guarantees that the codes fit).  scale_out[0] receives the scale.
+ *   [0, max] ranges (the caller guarantees that the codes fit).  C % 16 == 0, xq 16-byte aligned.  scale_out[0]
+ *   receives the scale.
  * fq_qconv_pack_weight: fp32 [Cout, Cg, KH, KW] -> int8 codes [Cout, KH, KW, Cg] (K-major for the GEMM).
  * fq_qconv_igemm: implicit GEMM on tcgen05 (kind::i8, int32 accumulators in tensor memory), fused epilogue
  *   out = float(max?(acc + bias_q)) * (s_in * s_w)  (:143-158).  Cg % 16 == 0; out float32 [N, Cout, Ho, Wo]. */

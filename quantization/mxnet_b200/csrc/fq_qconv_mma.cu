@@ -21,13 +21,12 @@ namespace fq {
 
 constexpr int kMmaM = 128;            // output pixels per CTA
 constexpr int kMmaK = 128;            // int8 elements per k-block = one 128 B swizzle row
-constexpr int kMmaStages = 3;
-constexpr int kMmaThreads = 256;
 
 struct QConvArgs {
   const signed char* xq;      // [N, Hp, Wp, C] codes, spatially padded
   const signed char* wq;      // [Cout, KH, KW, Cg] codes
-  const int* bias_q;          // [Cout] or NULL
+  const int* bias_q;          // [Cout] int32 codes, or NULL
+  const float* bias_f;        // [Cout] float bias to be quantised with b_scale = s_in * s_w (:122-127), or NULL
   const float* s_in;          // device scalars
   const float* s_w;
   float* out;                 // [N, Cout, Ho, Wo]
@@ -109,175 +108,308 @@ __device__ __forceinline__ uint32_t make_idesc_i8(int n, int a_unsigned) {
   return (2u << 4) | ((a_unsigned ? 0u : 1u) << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kMmaM >> 4) << 24);
 }
 
-// One CTA: 128 output pixels x BN output channels of one group.  grid = (ceil(M / 128), ceil(Cout_g / BN), groups).
-__global__ void __launch_bounds__(kMmaThreads, 1) qconv_igemm_kernel(const QConvArgs a) {
+// ---- the implicit GEMM: persistent, warp-specialised --------------------------------------------------------
+// One CTA per SM walks over tiles of 128 output pixels x BN output channels (BN <= 256: a whole 256-channel layer
+// reads its A tile once).  Three roles, connected by mbarriers only (no __syncthreads in the steady state):
+//   warps 4-7  PRODUCERS  gather A (16-byte channel runs of the padded NHWC codes, one per (pixel, kh, kw)) and
+//              copy B (K-major weight rows) into a 4-stage ring of 128-byte-swizzled tiles with cp.async; a stage is
+//              published (cp.async.wait_group -> fence.proxy.async -> arrive on full[s]) two k-blocks after it was
+//              issued, so 2-3 k-blocks of copies are always in flight;
+//   warp  8    MMA        one thread waits for full[s], issues 4 x tcgen05.mma.kind::i8 (M=128, N=BN, K=32) into
+//              one of TWO accumulator buffers in tensor memory, and commits to empty[s] (the producers may refill)
+//              and, after a tile's last k-block, to acc_full[buf];
+//   warps 0-3  EPILOGUE   wait for acc_full[buf], read the accumulators with tcgen05.ld (warp w owns TMEM lanes
+//              32w..32w+31 = tile rows), release the buffer (acc_empty[buf]) and then add the int32 bias, apply
+//              ReLU, dequantise and store NCHW floats -- while the tensor core is already busy with the next tile.
+constexpr int kEpiWarps = 4, kProdWarps = 4;
+constexpr int kMmaThreadsV2 = 32 * (kEpiWarps + kProdWarps + 1);
+constexpr int kStagesV2 = 4, kLagV2 = 2;
+constexpr int kMaxBN = 256;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_dyn(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free_dyn(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QConvArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024 B alignment is what the 128 B swizzle atom (8 rows x 128 B) needs
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* smem_a = smem;                                          // [stages][128 rows][128 B]
-  unsigned char* smem_b = smem + kMmaStages * kMmaM * kMmaK;             // [stages][128 rows][128 B] (BN rows used)
-  __shared__ uint64_t mma_done[kMmaStages];      // stage consumed by the tensor core -> may be refilled
-  __shared__ uint64_t acc_ready;
+  unsigned char* smem_b = smem + kStagesV2 * kMmaM * kMmaK;              // [stages][BN rows][128 B]
+  __shared__ uint64_t full[kStagesV2], empty[kStagesV2], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ int bias_s[2][kMaxBN];                                      // this tile's int32 bias codes
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int M = a.N * a.Ho * a.Wo;
-  const int m0 = blockIdx.x * kMmaM;
-  const int g = blockIdx.z;
+  const int M = a.N * a.Ho * a.Wo, HoWo = a.Ho * a.Wo;
   const int cout_g = a.Cout / a.groups;
-  const int co0 = blockIdx.y * a.BN;                     // within the group
+  const int m_tiles = (M + kMmaM - 1) / kMmaM, n_tiles = (cout_g + a.BN - 1) / a.BN;
+  const int tiles = m_tiles * n_tiles * a.groups;
   const int nkb = (a.K + kMmaK - 1) / kMmaK;
+  const uint32_t b_stage_bytes = (uint32_t)a.BN * kMmaK;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * (uint32_t)a.BN) tmem_cols <<= 1;               // two accumulator buffers of BN columns
 
   if (tid == 0) {
-    for (int s = 0; s < kMmaStages; ++s) mbar_init(&mma_done[s], 1);
-    mbar_init(&acc_ready, 1);
+    for (int s = 0; s < kStagesV2; ++s) {
+      mbar_init(&full[s], 32 * kProdWarps);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 32 * kEpiWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc<128>(&tmem_slot);
+  if (warp == 0) tmem_alloc_dyn(&tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = tmem_slot;
+  const uint32_t tmem_base = tmem_slot;
 
-  // ---- loader: each thread owns 4 (row, 16 B chunk) slots of A and of B per k-block -----------------------
-  // slot s = tid + 256 * i: row = s >> 3 (0..127), chunk = s & 7; stored at row * 128 + ((chunk ^ (row & 7)) << 4)
-  int a_row[4], a_chunk[4];
-  const signed char* a_base[4];        // &xq[n, oh*sh, ow*sw, g*Cg] of the row's output pixel, or NULL beyond M
+  if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
+    // =========================== PRODUCERS ===========================
+    const int p = tid - 32 * kEpiWarps;                  // 0..127
+    const int chunk = p & 7, row0 = p >> 3;              // slot i: row = row0 + 16 i, same chunk, same row & 7
+    const uint32_t soff = (uint32_t)row0 * 128u + (uint32_t)((chunk ^ (row0 & 7)) << 4);
+    const int b_slots = a.BN >> 4;                       // BN rows x 8 chunks / 128 threads
+    int it = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int mt = t % m_tiles, rest = t / m_tiles;
+      const int nt = rest % n_tiles, g = rest / n_tiles;
+      const int m0 = mt * kMmaM, co0 = nt * a.BN;
+      const signed char* a_base[8];      // &xq[n, oh*sh, ow*sw, g*Cg] of the row's output pixel, or NULL beyond M
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int s = tid + kMmaThreads * i;
-    a_row[i] = s >> 3;
-    a_chunk[i] = s & 7;
-    const int m = m0 + a_row[i];
-    if (m < M) {
-      const int n = m / (a.Ho * a.Wo), r = m % (a.Ho * a.Wo);
-      const int oh = r / a.Wo, ow = r % a.Wo;
-      a_base[i] = a.xq + (((int64_t)n * a.Hp + (int64_t)oh * a.sh) * a.Wp + (int64_t)ow * a.sw) * a.C + (int64_t)g * a.Cg;
-    } else {
-      a_base[i] = nullptr;
-    }
-  }
-  auto load_stage = [&](int kb, int stage) {
-    const uint32_t sa = smem_u32(smem_a + stage * kMmaM * kMmaK), sb = smem_u32(smem_b + stage * kMmaM * kMmaK);
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + row0 + 16 * i;
+        if (m < M) {
+          const int n = m / HoWo, r = m - n * HoWo;
+          const int oh = r / a.Wo, ow = r - oh * a.Wo;
+          a_base[i] = a.xq + (((int64_t)n * a.Hp + (int64_t)oh * a.sh) * a.Wp + (int64_t)ow * a.sw) * a.C + (int64_t)g * a.Cg;
+        } else {
+          a_base[i] = nullptr;
+        }
+      }
+      // weight row of slot i: b_row0 + i * 16 K; rows at or beyond b_valid_rows are zero-filled
+      const signed char* b_row0 = a.wq + ((int64_t)g * cout_g + co0 + row0) * a.K;
+      const int b_valid_rows = cout_g - co0;
+      // (kh, kw, ci) of this thread's chunk, advanced by 128 per k-block without a division
+      int ld_k = chunk * 16, ld_ci = ld_k % a.Cg, ld_kh, ld_kw;
+      {
+        const int khw = ld_k / a.Cg;
+        ld_kh = khw / a.KW;
+        ld_kw = khw - ld_kh * a.KW;
+      }
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int stage = it % kStagesV2;
+        if (it >= kStagesV2) mbar_wait(&empty[stage], (uint32_t)((it / kStagesV2) - 1) & 1u);
+        const uint32_t sa = smem_u32(smem_a + stage * kMmaM * kMmaK) + soff;
+        const uint32_t sb = smem_u32(smem_b) + (uint32_t)stage * b_stage_bytes + soff;
+        const bool vk = ld_k < a.K;
+        const int64_t a_off = ((int64_t)ld_kh * a.Wp + ld_kw) * a.C + ld_ci;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = a_row[i], chunk = a_chunk[i];
-      const int k = kb * kMmaK + chunk * 16;                 // first of 16 consecutive k = (kh, kw, ci..ci+15)
-      const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-      // A: gather from the padded NHWC codes
-      const int khw = k / a.Cg, ci = k % a.Cg;
-      const int kh = khw / a.KW, kw = khw % a.KW;
-      const bool va = a_base[i] != nullptr && k < a.K;
-      const signed char* src_a = va ? a_base[i] + ((int64_t)kh * a.Wp + kw) * a.C + ci : a.xq;
-      cp_async16(sa + off, src_a, va);
-      // B: weight rows are K-major already
-      const int co = co0 + row;
-      const bool vb = row < a.BN && co < cout_g && k < a.K;
-      const signed char* src_b = vb ? a.wq + ((int64_t)g * cout_g + co) * a.K + k : a.wq;
-      if (row < a.BN) cp_async16(sb + off, src_b, vb);
+        for (int i = 0; i < 8; ++i) {
+          const bool va = vk && a_base[i] != nullptr;
+          cp_async16(sa + i * (16 * 128), va ? a_base[i] + a_off : a.xq, va);
+        }
+#pragma unroll 4
+        for (int i = 0; i < b_slots; ++i) {
+          const bool vb = vk && row0 + 16 * i < b_valid_rows;
+          cp_async16(sb + i * (16 * 128), vb ? b_row0 + (int64_t)i * 16 * a.K + ld_k : a.wq, vb);
+        }
+        cp_async_commit();
+        if (it >= kLagV2) {                    // the copies of k-block it - LAG have landed: publish that stage
+          cp_async_wait<kLagV2>();
+          fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          mbar_arrive(&full[(it - kLagV2) % kStagesV2]);
+        }
+        ld_k += kMmaK;
+        ld_ci += kMmaK;
+        while (ld_ci >= a.Cg) {                // at most 128 / Cg <= 8 steps
+          ld_ci -= a.Cg;
+          if (++ld_kw == a.KW) {
+            ld_kw = 0;
+            ++ld_kh;
+          }
+        }
+      }
     }
-    cp_async_commit();
-  };
-
-  const uint32_t idesc = make_idesc_i8(a.BN, a.a_unsigned);
-  // prologue
-  for (int s = 0; s < kMmaStages - 1; ++s) {
-    if (s < nkb) load_stage(s, s);
-    else cp_async_commit();
-  }
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int stage = kb % kMmaStages;
-    cp_async_wait<kMmaStages - 2>();         // this thread's copies of k-block kb have landed
-    fence_proxy_async();                     // ... and are visible to the tensor core's (async proxy) reads
-    __syncthreads();
-    if (tid == 0) {
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int j = (it > kLagV2 ? it - kLagV2 : 0); j < it; ++j) mbar_arrive(&full[j % kStagesV2]);
+  } else if (warp == kEpiWarps + kProdWarps) {
+    // =========================== MMA ISSUER ===========================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_i8(a.BN, a.a_unsigned);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        if (lt >= 2) {                         // the epilogue has drained this accumulator buffer
+          mbar_wait(&acc_empty[buf], (uint32_t)((lt >> 1) - 1) & 1u);
+          tc_fence_after();
+        }
+        const uint32_t tmem_acc = tmem_base + (uint32_t)buf * (tmem_cols >> 1);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int stage = it % kStagesV2;
+          mbar_wait(&full[stage], (uint32_t)(it / kStagesV2) & 1u);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * kMmaM * kMmaK);
+          const uint32_t sb = smem_u32(smem_b) + (uint32_t)stage * b_stage_bytes;
+#pragma unroll
+          for (int k = 0; k < kMmaK / 32; ++k)   // UMMA K = 32 int8 = 32 B: advance the start address inside the swizzle row
+            umma_i8(tmem_acc, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, (kb | k) != 0);
+          umma_commit(&empty[stage]);            // arrives when the MMAs above have finished reading this stage
+          if (kb == nkb - 1) umma_commit(&acc_full[buf]);
+        }
+      }
+    }
+  } else {
+    // =========================== EPILOGUE ===========================
+    const float scale = __fmul_rn(__ldg(a.s_in), __ldg(a.s_w));         // nn/quantized_conv.py:158  in_scale * w_scale
+    const float b_max = __fmul_rn(scale, 2147483648.0f);                // :123  b_scale * 2^31
+    int lt = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++lt) {
+      const int mt = t % m_tiles, rest = t / m_tiles;
+      const int nt = rest % n_tiles, g = rest / n_tiles;
+      const int m0 = mt * kMmaM, co0 = nt * a.BN;
+      const int buf = lt & 1;
+      // this tile's bias as int32 codes: given, or quantised here from the float bias (:122-127)
+      for (int c = tid; c < a.BN; c += 32 * kEpiWarps) {
+        const int co = co0 + c;
+        int bq = 0;
+        if (co < cout_g) {
+          if (a.bias_q != nullptr) bq = __ldg(a.bias_q + g * cout_g + co);
+          else if (a.bias_f != nullptr) bq = (int)quant_code(clipf(__ldg(a.bias_f + g * cout_g + co), -b_max, b_max), scale);
+        }
+        bias_s[buf][c] = bq;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");   // epilogue warps only
+      const int row = warp * 32 + lane;                                  // TMEM lane == tile row
+      const int m = m0 + row;
+      int64_t out_base = 0;
+      if (m < M) {
+        const int n = m / HoWo, r = m - n * HoWo;
+        out_base = ((int64_t)n * a.Cout + (int64_t)g * cout_g + co0) * HoWo + r;
+      }
+      mbar_wait(&acc_full[buf], (uint32_t)(lt >> 1) & 1u);
       tc_fence_after();
-      const uint32_t sa = smem_u32(smem_a + stage * kMmaM * kMmaK), sb = smem_u32(smem_b + stage * kMmaM * kMmaK);
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * (tmem_cols >> 1);
+      const int ncols = min(a.BN, cout_g - co0);
+      for (int c0 = 0; c0 < a.BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld16_nowait(tmem_acc + (uint32_t)c0, v);
+        if (c0 + 16 < a.BN) tmem_ld16_nowait(tmem_acc + (uint32_t)(c0 + 16), v + 16);
+        tmem_ld_wait();
+        if (c0 + 32 >= a.BN) {                 // last read of this buffer: hand it back before the stores
+          tc_fence_before();
+          mbar_arrive(&acc_empty[buf]);
+        }
+        if (m < M) {
 #pragma unroll
-      for (int k = 0; k < kMmaK / 32; ++k) {     // UMMA K = 32 int8 = 32 B: advance the start address inside the swizzle row
-        umma_i8(tmem_acc, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, (kb | k) != 0);
-      }
-      umma_commit(&mma_done[stage]);             // arrives when the MMAs above have finished reading this stage
-      if (kb == nkb - 1) umma_commit(&acc_ready);
-    }
-    // refill the stage consumed by k-block kb - 1 with k-block kb + stages - 1
-    const int nxt = kb + kMmaStages - 1;
-    if (nxt < nkb) {
-      if (kb >= 1) mbar_wait(&mma_done[(kb - 1) % kMmaStages], ((kb - 1) / kMmaStages) & 1);
-      load_stage(nxt, nxt % kMmaStages);
-    } else {
-      cp_async_commit();
-    }
-  }
-
-  // ---- epilogue: TMEM -> registers -> (+ bias, ReLU, dequantise) -> NCHW float ------------------------------
-  mbar_wait(&acc_ready, 0);
-  tc_fence_after();
-  const float scale = __fmul_rn(__ldg(a.s_in), __ldg(a.s_w));         // nn/quantized_conv.py:158  in_scale * w_scale
-  const int row = (warp & 3) * 32 + lane;                             // TMEM lane == tile row; a warp owns its lane quarter
-  const int m = m0 + row;
-  const int half = warp >> 2;                                         // warps 0-3: columns [0, BN/2), warps 4-7: the rest
-  const int ncol = a.BN / 2;
-  int64_t out_base = 0;
-  if (m < M) {
-    const int n = m / (a.Ho * a.Wo), r = m % (a.Ho * a.Wo);
-    out_base = ((int64_t)n * a.Cout + (int64_t)g * cout_g) * (a.Ho * a.Wo) + r;
-  }
-  for (int c0 = half * ncol; c0 < (half + 1) * ncol; c0 += 16) {
-    uint32_t v[16];
-    tmem_ld16(tmem_acc + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
-    // BN / 2 may be 8, 24, ...: columns beyond this half belong to the other warps (or are padding)
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int c = c0 + j, co = co0 + c;
-      if (m < M && c < (half + 1) * ncol && co < cout_g) {
-        int acc = (int)v[j];
-        if (a.bias_q != nullptr) acc += __ldg(a.bias_q + g * cout_g + co);
-        if (a.relu) acc = max(acc, 0);
-        a.out[out_base + (int64_t)co * (a.Ho * a.Wo)] = __fmul_rn((float)acc, scale);
+          for (int j = 0; j < 32; ++j) {
+            const int c = c0 + j;
+            if (c < ncols) {
+              int acc = (int)v[j] + bias_s[buf][c];
+              if (a.relu) acc = max(acc, 0);
+              a.out[out_base + (int64_t)c * HoWo] = __fmul_rn((float)acc, scale);
+            }
+          }
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_free<128>(tmem_acc);
+  if (warp == 0) tmem_free_dyn(tmem_base, tmem_cols);
 }
 
 // ---- fp32 NCHW -> zero-padded NHWC 8-bit codes (pad, clip, divide, round: nn/quantized_conv.py:108-109, 54-61) ----
-// One block per (n, padded row): a warp per channel reads that channel's row of W floats (coalesced), quantises with
-// the guarded reciprocal (exactly roundf(clip(x) / scale), fq_common.cuh) and writes the byte into a shared-memory tile
-// [Wp][C + 4] (the +4 keeps the 32 lanes of a warp on 32 different banks); the tile is then written out as whole
-// 32-bit words, coalesced.  Codes of the padding are the code of 0.0 under the same clip, as in the reference, which
-// pads first and quantises the padded tensor.
+// HBM-bound: 4 B read + 1 B written per element.  One block per (n, padded row).  A work item is (16 channels, one
+// pixel): its thread issues the 16 scalar loads up front (lanes run along W, so each load instruction of a warp is one
+// coalesced 128 B line of one channel row), quantises with the guarded reciprocal (exactly roundf(clip(x) / scale),
+// fq_common.cuh), packs the 16 codes into one 128-bit shared-memory store into a tile [W][C + 16] (row stride 4 banks
+// mod 32: the 8 lanes of a store phase cover the 32 banks exactly once), and the tile leaves as whole 16-byte vectors,
+// coalesced.  Codes of the padding are the code of 0.0 under the same clip, as in the reference, which pads first and
+// quantises the padded tensor; padding rows and columns never touch shared memory.
+__device__ __forceinline__ uint32_t pack4_codes(float c0, float c1, float c2, float c3) {
+  // (int) -> low 8 bits: int8 codes [-127, 127] and uint8 codes [0, 255] alike; three byte permutes
+  const uint32_t lo = __byte_perm((uint32_t)(int)c0, (uint32_t)(int)c1, 0x0040);
+  const uint32_t hi = __byte_perm((uint32_t)(int)c2, (uint32_t)(int)c3, 0x0040);
+  return __byte_perm(lo, hi, 0x5410);
+}
+// the by-the-book code of one element, out of line: taken by a few elements per million (QDiv's guard band)
+__device__ __noinline__ float slow_code(float v, float d) { return quant_code(v, d); }
+
 __global__ void __launch_bounds__(kThreads) qconv_pack_input_kernel(const float* __restrict__ x, const float* __restrict__ range2,
                                                                     signed char* __restrict__ xq, float* __restrict__ scale_out,
                                                                     int N, int C, int H, int W, int ph, int pw) {
-  extern __shared__ __align__(16) signed char tile[];       // [Wp][C + 4]
-  const int Hp = H + 2 * ph, Wp = W + 2 * pw, Cs = C + 4;
+  extern __shared__ __align__(16) unsigned char tile[];       // [W][C + 16]
+  const int Hp = H + 2 * ph, Wp = W + 2 * pw, Cs = C + 16, c16n = C >> 4;
   const int n = blockIdx.x / Hp, hp = blockIdx.x % Hp;
   const float lo = __ldg(range2), hi = __ldg(range2 + 1);
   const float scale = (hi == -lo) ? __fdiv_rn(hi, 127.0f) : __fdiv_rn(__fsub_rn(hi, lo), 255.0f);
   const QDiv qd = QDiv::make(scale);
-  // (int) -> low 8 bits: int8 codes [-127, 127] and uint8 codes [0, 255] alike
-  const signed char pad_code = (signed char)(unsigned char)(int)quant_code(clipf(0.f, lo, hi), scale);
+  const uint32_t pad1 = (uint32_t)(int)quant_code(clipf(0.f, lo, hi), scale) & 0xffu;
+  const uint32_t pad4 = pad1 * 0x01010101u;
   const int h = hp - ph;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int c = warp; c < C; c += nw) {
-    const float* row = (h >= 0 && h < H) ? x + (((int64_t)n * C + c) * H + h) * W : nullptr;
-    for (int w = lane; w < Wp; w += 32) {
-      const int ws = w - pw;
-      signed char code = pad_code;
-      if (row != nullptr && ws >= 0 && ws < W) code = (signed char)(unsigned char)(int)qd.code(clipf(__ldg(row + ws), lo, hi));
-      tile[w * Cs + c] = code;
+  const bool interior = h >= 0 && h < H;
+  if (interior) {
+    const float* plane = x + ((int64_t)n * C * H + h) * W;      // channel c of this row: plane + c * H * W
+    const uint32_t cstride = (uint32_t)(H * W);                 // H * W < 2^27 (host check): 32-bit offsets
+    const uint64_t magic_w = 0xffffffffull / (uint32_t)W + 1ull;   // exact quotients for item < 2^16 (host check)
+#pragma unroll 1
+    for (int item = threadIdx.x; item < c16n * W; item += blockDim.x) {
+      const int c16 = (int)(((uint64_t)(uint32_t)item * magic_w) >> 32), w = item - c16 * W;
+      const char* src = reinterpret_cast<const char*>(plane + (int64_t)(c16 * 16) * cstride + w);
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)       // base + u32 * u32 in one wide multiply-add per load
+        v[j] = __ldg(reinterpret_cast<const float*>(src + (uint64_t)(uint32_t)j * (uint64_t)(cstride * 4u)));
+      float t[16];
+      float worst = 0.f;                 // NaN-propagating max of QDiv::near_tie's left-hand side over the 16 elements
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[j] = clipf(v[j], lo, hi);
+        const float q0 = __fmul_rn(v[j], qd.r);
+        t[j] = rintf(q0);
+        const float m = __fmaf_rn(fabsf(q0), qd.guard, fabsf(__fsub_rn(q0, t[j])));
+        asm("max.NaN.f32 %0, %0, %1;" : "+f"(worst) : "f"(m));
+      }
+      if (!(worst < 0.5f)) {             // some element sits in the guard band (or is NaN): by the book for those
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (qd.near_tie(__fmul_rn(v[j], qd.r), t[j])) t[j] = slow_code(v[j], qd.d);
+      }
+      *reinterpret_cast<uint4*>(tile + (size_t)w * Cs + c16 * 16) =
+          make_uint4(pack4_codes(t[0], t[1], t[2], t[3]), pack4_codes(t[4], t[5], t[6], t[7]),
+                     pack4_codes(t[8], t[9], t[10], t[11]), pack4_codes(t[12], t[13], t[14], t[15]));
     }
   }
   __syncthreads();
-  const int cw = C >> 2;                                     // C % 16 == 0 (host check): whole words
-  const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tile);
-  uint32_t* dst = reinterpret_cast<uint32_t*>(xq + ((int64_t)n * Hp + hp) * Wp * C);
-  for (int i = threadIdx.x; i < Wp * cw; i += blockDim.x) {
-    const int w = i / cw, j = i - w * cw;
-    dst[i] = t32[w * (cw + 1) + j];
+  uint4* dst = reinterpret_cast<uint4*>(xq + ((int64_t)n * Hp + hp) * Wp * C);
+  const uint4 padv = make_uint4(pad4, pad4, pad4, pad4);
+  const uint64_t magic_c = 0xffffffffull / (uint32_t)c16n + 1ull;   // 2^32 when c16n == 1
+#pragma unroll 2
+  for (int i = threadIdx.x; i < Wp * c16n; i += blockDim.x) {
+    const int wp_ = (int)(((uint64_t)(uint32_t)i * magic_c) >> 32), j = i - wp_ * c16n;
+    const int w = wp_ - pw;
+    dst[i] = (interior && w >= 0 && w < W) ? *reinterpret_cast<const uint4*>(tile + (size_t)w * Cs + j * 16) : padv;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && scale_out != nullptr) scale_out[0] = scale;
 }
@@ -318,12 +450,14 @@ int fq_qconv_pack_input(const DLTensor* x_, const DLTensor* range2_, int pad_h, 
   FQ_REQUIRE(xq.bits == 8 && (xq.code == kDLInt || xq.code == kDLUInt) && xq.numel == N * Hp * Wp * C,
              "%s: xq must be (u)int8 [N, H+2ph, W+2pw, C]", who);
   FQ_REQUIRE(so.null || (so.is_f32() && so.numel >= 1), "%s: scale_out must be float32", who);
-  FQ_REQUIRE(C % 4 == 0, "%s: C=%lld must be a multiple of 4", who, (long long)C);
-  FQ_REQUIRE(Wp * (C + 4) <= 200 * 1024, "%s: one padded row of %lld x %lld codes does not fit in shared memory", who,
-             (long long)Wp, (long long)C);
-  FQ_REQUIRE((reinterpret_cast<uintptr_t>(xq.data) & 3u) == 0, "%s: xq must be 4-byte aligned", who);
+  FQ_REQUIRE(C % 16 == 0, "%s: C=%lld must be a multiple of 16 (the tensor-core loader moves 16-byte runs of channels)",
+             who, (long long)C);
+  FQ_REQUIRE(W * (C + 16) <= 200 * 1024 && Wp * (C / 16) < 65536,
+             "%s: one row of %lld x %lld codes does not fit in shared memory", who, (long long)W, (long long)C);
+  FQ_REQUIRE((reinterpret_cast<uintptr_t>(xq.data) & 15u) == 0, "%s: xq must be 16-byte aligned", who);
+  FQ_REQUIRE(H * W < (1LL << 27), "%s: one channel plane of %lld x %lld is too large", who, (long long)H, (long long)W);
   if (x.numel == 0) return 0;
-  const size_t smem = (size_t)(Wp * (C + 4));
+  const size_t smem = (size_t)(W * (C + 16));
   FQ_CUDA(cudaFuncSetAttribute(qconv_pack_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   qconv_pack_input_kernel<<<(unsigned)(N * Hp), kThreads, smem, (cudaStream_t)stream>>>(
       x.as<const float>(), rg.as<const float>(), xq.as<signed char>(), so.null ? nullptr : so.as<float>(), (int)N, (int)C,
@@ -389,14 +523,16 @@ int fq_qconv_igemm(const DLTensor* xq_, const DLTensor* wq_, const DLTensor* bia
   a.Wo = (a.Wp - a.KW) / stride_w + 1;
   FQ_REQUIRE(out_->shape[0] == a.N && out_->shape[1] == a.Cout && out_->shape[2] == a.Ho && out_->shape[3] == a.Wo,
              "%s: out must be [%d, %d, %d, %d]", who, a.N, a.Cout, a.Ho, a.Wo);
-  FQ_REQUIRE(bq.null || (bq.code == kDLInt && bq.bits == 32 && bq.numel == a.Cout), "%s: bias_q must be int32 [Cout]", who);
+  FQ_REQUIRE(bq.null || (((bq.code == kDLInt && bq.bits == 32) || bq.is_f32()) && bq.numel == a.Cout),
+             "%s: bias must be int32 codes or float32 [Cout]", who);
   FQ_REQUIRE((int64_t)a.N * a.Ho * a.Wo < (1LL << 31) && xq.numel < (1LL << 40), "%s: problem too large", who);
   FQ_REQUIRE((reinterpret_cast<uintptr_t>(xq.data) & 15u) == 0 && (reinterpret_cast<uintptr_t>(wq.data) & 15u) == 0,
              "%s: xq and wq must be 16-byte aligned", who);
   a.K = a.KH * a.KW * a.Cg;
   a.xq = xq.as<const signed char>();
   a.wq = wq.as<const signed char>();
-  a.bias_q = bq.null ? nullptr : bq.as<const int>();
+  a.bias_q = (bq.null || bq.is_f32()) ? nullptr : bq.as<const int>();
+  a.bias_f = (!bq.null && bq.is_f32()) ? bq.as<const float>() : nullptr;
   a.s_in = si.as<const float>();
   a.s_w = sw.as<const float>();
   a.out = out.as<float>();
@@ -404,15 +540,17 @@ int fq_qconv_igemm(const DLTensor* xq_, const DLTensor* wq_, const DLTensor* bia
   a.a_unsigned = xq.code == kDLUInt;
   const int cout_g = a.Cout / groups;
   int bn = (cout_g + 15) / 16 * 16;
-  if (bn > 128) bn = 128;
-  if (bn < 32) bn = 32;              // the two epilogue halves read 16 columns at a time
+  if (bn > kMaxBN) bn = kMaxBN;
   a.BN = bn;
   const int64_t M = (int64_t)a.N * a.Ho * a.Wo;
   if (M == 0) return 0;
-  const size_t smem = (size_t)2 * kMmaStages * kMmaM * kMmaK + 1024;
+  const int64_t tiles = ((M + kMmaM - 1) / kMmaM) * ((cout_g + bn - 1) / bn) * groups;
+  FQ_REQUIRE(tiles < (1LL << 31), "%s: problem too large", who);
+  const size_t smem = (size_t)kStagesV2 * (kMmaM * kMmaK + (size_t)bn * kMmaK) + 1024;
   FQ_CUDA(cudaFuncSetAttribute(qconv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)((M + kMmaM - 1) / kMmaM), (unsigned)((cout_g + bn - 1) / bn), (unsigned)groups);
-  qconv_igemm_kernel<<<grid, kMmaThreads, smem, (cudaStream_t)stream>>>(a);
+  const int64_t sms = sm_count();
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);            // persistent: one CTA per SM
+  qconv_igemm_kernel<<<grid, kMmaThreadsV2, smem, (cudaStream_t)stream>>>(a);
   FQ_LAUNCH_CHECK("qconv_igemm_kernel");
   return 0;
 }

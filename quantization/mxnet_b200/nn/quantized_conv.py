@@ -74,6 +74,7 @@ class Conv2D(nn.Module):
         self._input_range = None
         self._weight_range = None
         self.use_tensor_cores = True       # set to False to force the framework convolution on float codes
+        self.cache_weight_codes = False    # True: keep the int8 weight codes while the weight is unchanged
 
         self.weight = nn.Parameter(torch.empty(channels, in_channels // groups, *self._kernel_size))
         nn.init.uniform_(self.weight, -0.07, 0.07)          # mxnet's default Uniform(0.07)
@@ -90,13 +91,12 @@ class Conv2D(nn.Module):
         if self._weight_range is None:
             if self._weight_dtype != 'int8':
                 return None
-            mx = ops.absmax_rows(self.weight.detach(), 1)
-            w_rng = torch.cat([-mx, mx])
+            w_rng = None                          # max |w|, taken when the weight codes are (re)built
         else:
             lo, hi = (float(v) for v in self._weight_range)
             if hi != -lo:
                 return None
-            w_rng = torch.tensor([lo, hi], dtype=torch.float32, device=dev)
+            w_rng = (lo, hi)
         if self._input_range is None:
             if self._input_dtype != 'int8':
                 return None             # an automatic uint8 range has no zero point: its codes need not fit 8 bits
@@ -109,6 +109,25 @@ class Conv2D(nn.Module):
             return torch.tensor([lo, hi], dtype=torch.float32, device=dev), True, w_rng       # codes in [0, 255]
         return None
 
+    def _weight_codes(self, w_rng):
+        """K-major int8 weight codes + scale for the tensor-core route.  Rebuilt on every forward, as the reference
+        quantises its weight on every forward (:118-121); with ``cache_weight_codes = True`` (inference) only when the
+        weight's address or autograd version changed -- which in-place edits through ``weight.data`` do not show."""
+        w = self.weight
+        key = (w.data_ptr(), w._version, w_rng, w.device)
+        hit = self.__dict__.get("_fq_wcodes") if self.cache_weight_codes else None
+        if hit is None or hit[0] != key:
+            wd = w.detach()
+            if w_rng is None:
+                mx = ops.absmax_rows(wd, 1)
+                rng = torch.cat([-mx, mx])
+            else:
+                rng = torch.tensor(w_rng, dtype=torch.float32, device=w.device)
+            hit = (key, ops.qconv_pack_weight(wd, rng))
+            if self.cache_weight_codes:
+                self.__dict__["_fq_wcodes"] = hit
+        return hit[1]
+
     def forward(self, inputs):
         weight, bias = self.weight, self.bias
         ph, pw = self._padding
@@ -117,15 +136,11 @@ class Conv2D(nn.Module):
             if tc is not None:
                 in_rng, unsigned, w_rng = tc
                 xq, in_scale = ops.qconv_pack_input(inputs, in_rng, ph, pw, unsigned=unsigned)
-                wq, w_scale = ops.qconv_pack_weight(weight.detach(), w_rng)
-                bias_q = None
-                if bias is not None:
-                    b_scale = in_scale * w_scale
-                    b_max = b_scale * float(2 ** 31)
-                    _, bias_q = ops.forward_scalar(bias.detach(), torch.cat([b_scale, b_scale, -b_max, b_max]),
-                                                   codes_dtype=torch.int32)
-                return ops.qconv_igemm(xq, wq, bias_q, in_scale, w_scale, self._strides, self._groups,
-                                       relu=self.act is not None)
+                wq, w_scale = self._weight_codes(w_rng)
+                # the float bias goes in as it is: the kernel's epilogue quantises it with b_scale = s_in * s_w,
+                # clipped to +- b_scale * 2^31 (:122-127) -- in_scale only exists on the device
+                return ops.qconv_igemm(xq, wq, None if bias is None else bias.detach(), in_scale, w_scale, self._strides,
+                                       self._groups, relu=self.act is not None)
         inputs = nn.functional.pad(inputs, (pw, pw, ph, ph))
         if self._quantized:
             if self._input_range is None:

@@ -544,7 +544,8 @@ def qconv_pack_weight(w, range2):
 
 
 def qconv_igemm(xq, wq, bias_q, s_in, s_w, strides, groups=1, relu=False):
-    """Integer convolution on tcgen05 with the bias / ReLU / dequantise epilogue fused.  nn/quantized_conv.py:143-158."""
+    """Integer convolution on tcgen05 with the bias / ReLU / dequantise epilogue fused.  nn/quantized_conv.py:143-158.
+    ``bias_q``: int32 codes, or the float32 bias itself (quantised in the epilogue with b_scale = s_in * s_w, :122-127)."""
     n, hp, wp, _ = xq.shape
     co, kh, kw, _ = wq.shape
     ho, wo = (hp - kh) // strides[0] + 1, (wp - kw) // strides[1] + 1

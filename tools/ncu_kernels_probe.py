@@ -52,7 +52,7 @@ with torch.no_grad():
     t_tc = timeit(lambda: conv(xi))
     in_rng, unsigned, w_rng = conv._tensor_core_ranges(xi)
     xq, s_in = ops.qconv_pack_input(xi, in_rng, 1, 1)
-    wq, s_w = ops.qconv_pack_weight(conv.weight.detach(), w_rng)
+    wq, s_w = conv._weight_codes(w_rng)
     t_mma = timeit(lambda: ops.qconv_igemm(xq, wq, None, s_in, s_w, (1, 1), 1))
     conv.use_tensor_cores = False
     t_ref = timeit(lambda: conv(xi))
