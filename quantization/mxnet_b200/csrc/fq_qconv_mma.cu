@@ -15,6 +15,8 @@
 // Operands are staged with cp.async (LDGSTS, 16 B) rather than TMA: the A operand is an im2col GATHER whose rows
 // change with (kh, kw) and with the image border, which a tiled tensor map cannot express without the im2col mode;
 // generic-proxy writes are ordered before the tensor core's async-proxy reads with fence.proxy.async.
+#include <cuda.h>      // CUtensorMap (types only: the encoder is resolved through cudaGetDriverEntryPoint)
+
 #include "fq_fused.cuh"
 
 namespace fq {
@@ -32,7 +34,7 @@ struct QConvArgs {
   float* out;                 // [N, Cout, Ho, Wo]
   int N, C, Hp, Wp, Cout, KH, KW, Cg, groups, Ho, Wo, sh, sw, relu, a_unsigned;
   int K;                      // KH * KW * Cg
-  int BN;                     // padded output channels per group handled by one CTA (16..128, multiple of 16)
+  int BN;                     // padded output channels per group handled by one CTA (16..256, multiple of 16)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -42,6 +44,18 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef FQ_MBAR_TEST_WAIT
+  uint32_t done = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
@@ -50,6 +64,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;          // src-size 0: the 16 bytes are zero-filled, nothing is read
@@ -111,20 +126,30 @@ __device__ __forceinline__ uint32_t make_idesc_i8(int n, int a_unsigned) {
 // ---- the implicit GEMM: persistent, warp-specialised --------------------------------------------------------
 // One CTA per SM walks over tiles of 128 output pixels x BN output channels (BN <= 256: a whole 256-channel layer
 // reads its A tile once).  Three roles, connected by mbarriers only (no __syncthreads in the steady state):
-//   warps 4-7  PRODUCERS  gather A (16-byte channel runs of the padded NHWC codes, one per (pixel, kh, kw)) and
-//              copy B (K-major weight rows) into a 4-stage ring of 128-byte-swizzled tiles with cp.async; a stage is
-//              published (cp.async.wait_group -> fence.proxy.async -> arrive on full[s]) two k-blocks after it was
-//              issued, so 2-3 k-blocks of copies are always in flight;
-//   warp  8    MMA        one thread waits for full[s], issues 4 x tcgen05.mma.kind::i8 (M=128, N=BN, K=32) into
-//              one of TWO accumulator buffers in tensor memory, and commits to empty[s] (the producers may refill)
+//   warps 4-11 PRODUCERS  k-block `it` of the CTA's stream goes to stage it % 4 and is loaded by ONE PAIR of warps
+//              (warps 4+2s, 5+2s for stage s; 64 tile rows each): wait for empty[s], gather A with cp.async -- a
+//              16-byte run of input channels per (pixel, kh, kw), straight from the padded NHWC codes into the
+//              128-byte-swizzled K-major layout -- then cp.async.wait_group 0 -> fence.proxy.async -> one arrival per
+//              warp on full[s].  A pair has four k-blocks of time for this chain (issue ~100 instructions, the L2
+//              round trip, the proxy fence), and the four pairs keep four k-blocks in flight.  Lane 0 of the pair's
+//              first warp also launches B: BN weight rows x 128 bytes of K as ONE bulk tensor copy (TMA,
+//              128 B swizzle), completing on the same barrier.
+//   warp  12   MMA        one thread waits for full[s], issues 4 x tcgen05.mma.kind::i8 (M=128, N=BN, K=32) into
+//              one of TWO accumulator buffers in tensor memory, and commits to empty[s] (the pair may refill it)
 //              and, after a tile's last k-block, to acc_full[buf];
 //   warps 0-3  EPILOGUE   wait for acc_full[buf], read the accumulators with tcgen05.ld (warp w owns TMEM lanes
 //              32w..32w+31 = tile rows), release the buffer (acc_empty[buf]) and then add the int32 bias, apply
 //              ReLU, dequantise and store NCHW floats -- while the tensor core is already busy with the next tile.
-constexpr int kEpiWarps = 4, kProdWarps = 4;
+// Measured on the way here (3x3, 256 -> 256 channels, 56 x 56, batch 32; profiles/r2_qconv_*): one CTA per tile with
+// __syncthreads per k-block 133 us; two CTAs per SM 111 us; this organisation with every producer warp taking part in
+// every k-block 99 us (each warp's serial chain -- constant loads, address math, MEMBAR + proxy fence, barrier -- was
+// ~900 clocks per k-block against 512 clocks of tensor-core work) and a per-element branchy epilogue; branch-free
+// epilogue 70 us.
+constexpr int kEpiWarps = 4, kProdWarps = 8;
 constexpr int kMmaThreadsV2 = 32 * (kEpiWarps + kProdWarps + 1);
-constexpr int kStagesV2 = 4, kLagV2 = 2;
+constexpr int kStagesV2 = 4;
 constexpr int kMaxBN = 256;
+static_assert(kProdWarps == 2 * kStagesV2, "one pair of producer warps per stage");
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
@@ -145,8 +170,20 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// one arrival + `bytes` of expected TMA traffic on a barrier
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// TMA: one box of a 2-D tensor map -> shared memory (128 B-swizzled as the map says); completion on `bar`
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
 
-__global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QConvArgs a) {
+__global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QConvArgs a, const __grid_constant__ CUtensorMap tmap_b) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024 B alignment is what the 128 B swizzle atom (8 rows x 128 B) needs
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -154,7 +191,7 @@ __global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QCo
   unsigned char* smem_b = smem + kStagesV2 * kMmaM * kMmaK;              // [stages][BN rows][128 B]
   __shared__ uint64_t full[kStagesV2], empty[kStagesV2], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ int bias_s[2][kMaxBN];                                      // this tile's int32 bias codes
+  __shared__ __align__(16) int bias_s[2][kMaxBN];                        // this tile's int32 bias codes
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = a.N * a.Ho * a.Wo, HoWo = a.Ho * a.Wo;
@@ -162,18 +199,19 @@ __global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QCo
   const int m_tiles = (M + kMmaM - 1) / kMmaM, n_tiles = (cout_g + a.BN - 1) / a.BN;
   const int tiles = m_tiles * n_tiles * a.groups;
   const int nkb = (a.K + kMmaK - 1) / kMmaK;
+  const int my_tiles = blockIdx.x < tiles ? (tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const uint32_t b_stage_bytes = (uint32_t)a.BN * kMmaK;
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * (uint32_t)a.BN) tmem_cols <<= 1;               // two accumulator buffers of BN columns
 
   if (tid == 0) {
     for (int s = 0; s < kStagesV2; ++s) {
-      mbar_init(&full[s], 32 * kProdWarps);
+      mbar_init(&full[s], 3);            // the two gathering warps of the stage + the thread that launches B's TMA
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 32 * kEpiWarps);
+      mbar_init(&acc_empty[b], kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -185,80 +223,74 @@ __global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QCo
 
   if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
     // =========================== PRODUCERS ===========================
-    const int p = tid - 32 * kEpiWarps;                  // 0..127
-    const int chunk = p & 7, row0 = p >> 3;              // slot i: row = row0 + 16 i, same chunk, same row & 7
-    const uint32_t soff = (uint32_t)row0 * 128u + (uint32_t)((chunk ^ (row0 & 7)) << 4);
-    const int b_slots = a.BN >> 4;                       // BN rows x 8 chunks / 128 threads
-    int it = 0;
-    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-      const int mt = t % m_tiles, rest = t / m_tiles;
-      const int nt = rest % n_tiles, g = rest / n_tiles;
-      const int m0 = mt * kMmaM, co0 = nt * a.BN;
-      const signed char* a_base[8];      // &xq[n, oh*sh, ow*sw, g*Cg] of the row's output pixel, or NULL beyond M
+    const int pw = warp - kEpiWarps;                     // 0..7
+    const int stage = pw >> 1, half = pw & 1;            // this warp: k-blocks it = stage (mod 4), tile rows [64 half, +64)
+    const int chunk = lane & 7, rsub = lane >> 3;        // copy i of a k-block: row = 64 half + 4 i + rsub, this chunk
+    const uint32_t sa0 = smem_u32(smem_a + stage * kMmaM * kMmaK);
+    const uint32_t sb0 = smem_u32(smem_b) + (uint32_t)stage * b_stage_bytes;
+    const int total = my_tiles * nkb;                    // k-blocks in this CTA's stream
+    int cur_tile = -1, kb = 0, b_row = 0;
+    const signed char* a_base[16];       // &xq[n, oh*sh, ow*sw, g*Cg] of each row's output pixel, or NULL beyond M
+    for (int it = stage; it < total; it += kStagesV2) {
+      const int lt = it / nkb;
+      kb = it - lt * nkb;
+      if (lt != cur_tile) {              // new tile: the 16 pixels of this lane (rows 4 apart: walk (n, oh, ow))
+        cur_tile = lt;
+        const int t = (int)blockIdx.x + lt * (int)gridDim.x;
+        const int mt = t % m_tiles, rest = t / m_tiles;
+        const int nt = rest % n_tiles, g = rest / n_tiles;
+        b_row = g * cout_g + nt * a.BN;
+        int m = mt * kMmaM + 64 * half + rsub;
+        int n = m / HoWo, r = m - n * HoWo;
+        int oh = r / a.Wo, ow = r - oh * a.Wo;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + row0 + 16 * i;
-        if (m < M) {
-          const int n = m / HoWo, r = m - n * HoWo;
-          const int oh = r / a.Wo, ow = r - oh * a.Wo;
-          a_base[i] = a.xq + (((int64_t)n * a.Hp + (int64_t)oh * a.sh) * a.Wp + (int64_t)ow * a.sw) * a.C + (int64_t)g * a.Cg;
-        } else {
-          a_base[i] = nullptr;
-        }
-      }
-      // weight row of slot i: b_row0 + i * 16 K; rows at or beyond b_valid_rows are zero-filled
-      const signed char* b_row0 = a.wq + ((int64_t)g * cout_g + co0 + row0) * a.K;
-      const int b_valid_rows = cout_g - co0;
-      // (kh, kw, ci) of this thread's chunk, advanced by 128 per k-block without a division
-      int ld_k = chunk * 16, ld_ci = ld_k % a.Cg, ld_kh, ld_kw;
-      {
-        const int khw = ld_k / a.Cg;
-        ld_kh = khw / a.KW;
-        ld_kw = khw - ld_kh * a.KW;
-      }
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int stage = it % kStagesV2;
-        if (it >= kStagesV2) mbar_wait(&empty[stage], (uint32_t)((it / kStagesV2) - 1) & 1u);
-        const uint32_t sa = smem_u32(smem_a + stage * kMmaM * kMmaK) + soff;
-        const uint32_t sb = smem_u32(smem_b) + (uint32_t)stage * b_stage_bytes + soff;
-        const bool vk = ld_k < a.K;
-        const int64_t a_off = ((int64_t)ld_kh * a.Wp + ld_kw) * a.C + ld_ci;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const bool va = vk && a_base[i] != nullptr;
-          cp_async16(sa + i * (16 * 128), va ? a_base[i] + a_off : a.xq, va);
-        }
-#pragma unroll 4
-        for (int i = 0; i < b_slots; ++i) {
-          const bool vb = vk && row0 + 16 * i < b_valid_rows;
-          cp_async16(sb + i * (16 * 128), vb ? b_row0 + (int64_t)i * 16 * a.K + ld_k : a.wq, vb);
-        }
-        cp_async_commit();
-        if (it >= kLagV2) {                    // the copies of k-block it - LAG have landed: publish that stage
-          cp_async_wait<kLagV2>();
-          fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async-proxy reads
-          mbar_arrive(&full[(it - kLagV2) % kStagesV2]);
-        }
-        ld_k += kMmaK;
-        ld_ci += kMmaK;
-        while (ld_ci >= a.Cg) {                // at most 128 / Cg <= 8 steps
-          ld_ci -= a.Cg;
-          if (++ld_kw == a.KW) {
-            ld_kw = 0;
-            ++ld_kh;
+        for (int i = 0; i < 16; ++i) {
+          a_base[i] = m < M ? a.xq + (((int64_t)n * a.Hp + (int64_t)oh * a.sh) * a.Wp + (int64_t)ow * a.sw) * a.C + (int64_t)g * a.Cg
+                            : nullptr;
+          m += 4;
+          ow += 4;
+          while (ow >= a.Wo) {
+            ow -= a.Wo;
+            if (++oh == a.Ho) {
+              oh = 0;
+              ++n;
+            }
           }
         }
       }
+      const int use = it / kStagesV2;                    // how often this stage has been filled before
+      if (use > 0) mbar_wait(&empty[stage], (uint32_t)(use - 1) & 1u);
+      if (half == 0 && lane == 0) {
+        // B: BN weight rows x 128 B of K in ONE bulk tensor copy (rows beyond Cout and bytes beyond K arrive as
+        // zeros; rows of the next group, if the tile overhangs its group, feed columns the epilogue drops)
+        mbar_arrive_expect_tx(&full[stage], b_stage_bytes);
+        tma_load_2d(sb0, &tmap_b, &full[stage], kb * kMmaK, b_row);
+      }
+      // A: this lane's chunk is k = (kh, kw, ci .. ci + 15)
+      const int k = kb * kMmaK + chunk * 16;
+      const bool vk = k < a.K;
+      const int khw = k / a.Cg, ci = k - khw * a.Cg;
+      const int kh = khw / a.KW, kw = khw - kh * a.KW;
+      const int64_t a_off = ((int64_t)kh * a.Wp + kw) * a.C + ci;
+      const uint32_t dst0 = sa0 + (uint32_t)(64 * half + rsub) * 128u;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int row = 64 * half + 4 * i + rsub;        // row & 7 = (4 i + rsub) & 7
+        const bool va = vk && a_base[i] != nullptr;
+        cp_async16(dst0 + (uint32_t)i * 512u + (uint32_t)((chunk ^ (row & 7)) << 4), va ? a_base[i] + a_off : a.xq, va);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      fence_proxy_async();               // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();                      // every lane's copies are in and fenced: ONE arrival per warp
+      if (lane == 0) mbar_arrive(&full[stage]);
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int j = (it > kLagV2 ? it - kLagV2 : 0); j < it; ++j) mbar_arrive(&full[j % kStagesV2]);
   } else if (warp == kEpiWarps + kProdWarps) {
     // =========================== MMA ISSUER ===========================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_i8(a.BN, a.a_unsigned);
-      int it = 0, lt = 0;
-      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++lt) {
+      int it = 0;
+      for (int lt = 0; lt < my_tiles; ++lt) {
         const int buf = lt & 1;
         if (lt >= 2) {                         // the epilogue has drained this accumulator buffer
           mbar_wait(&acc_empty[buf], (uint32_t)((lt >> 1) - 1) & 1u);
@@ -283,8 +315,8 @@ __global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QCo
     // =========================== EPILOGUE ===========================
     const float scale = __fmul_rn(__ldg(a.s_in), __ldg(a.s_w));         // nn/quantized_conv.py:158  in_scale * w_scale
     const float b_max = __fmul_rn(scale, 2147483648.0f);                // :123  b_scale * 2^31
-    int lt = 0;
-    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++lt) {
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int t = (int)blockIdx.x + lt * (int)gridDim.x;
       const int mt = t % m_tiles, rest = t / m_tiles;
       const int nt = rest % n_tiles, g = rest / n_tiles;
       const int m0 = mt * kMmaM, co0 = nt * a.BN;
@@ -311,6 +343,8 @@ __global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QCo
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * (tmem_cols >> 1);
       const int ncols = min(a.BN, cout_g - co0);
+      float* out_row = a.out + out_base;                              // + c * HoWo per output channel
+      const uint32_t cstride = (uint32_t)HoWo * 4u;                   // bytes between channels (HoWo < 2^29: host check)
       for (int c0 = 0; c0 < a.BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld16_nowait(tmem_acc + (uint32_t)c0, v);
@@ -318,16 +352,32 @@ __global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QCo
         tmem_ld_wait();
         if (c0 + 32 >= a.BN) {                 // last read of this buffer: hand it back before the stores
           tc_fence_before();
-          mbar_arrive(&acc_empty[buf]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        if (m < M) {
+        if (m >= M) continue;
+        char* o = reinterpret_cast<char*>(out_row) + (uint64_t)(uint32_t)c0 * cstride;
+        if (c0 + 32 <= ncols) {
+          // whole chunk inside the layer: straight-line code, the 32 bias codes as 8 broadcast 128-bit loads
+          int b[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int4 t4 = *reinterpret_cast<const int4*>(&bias_s[buf][c0 + 4 * q]);
+            b[4 * q] = t4.x; b[4 * q + 1] = t4.y; b[4 * q + 2] = t4.z; b[4 * q + 3] = t4.w;
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j;
-            if (c < ncols) {
-              int acc = (int)v[j] + bias_s[buf][c];
+            int acc = (int)v[j] + b[j];
+            if (a.relu) acc = max(acc, 0);
+            *reinterpret_cast<float*>(o + (uint64_t)(uint32_t)j * cstride) = __fmul_rn((float)acc, scale);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (c0 + j < ncols) {
+              int acc = (int)v[j] + bias_s[buf][c0 + j];
               if (a.relu) acc = max(acc, 0);
-              a.out[out_base + (int64_t)c * HoWo] = __fmul_rn((float)acc, scale);
+              *reinterpret_cast<float*>(o + (uint64_t)(uint32_t)j * cstride) = __fmul_rn((float)acc, scale);
             }
           }
         }
@@ -433,6 +483,22 @@ __global__ void __launch_bounds__(kThreads) qconv_pack_weight_kernel(const float
 
 using namespace fq;
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: no link-time dependency on libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
 extern "C" {
 
 int fq_qconv_pack_input(const DLTensor* x_, const DLTensor* range2_, int pad_h, int pad_w, const DLTensor* xq_,
@@ -525,7 +591,8 @@ int fq_qconv_igemm(const DLTensor* xq_, const DLTensor* wq_, const DLTensor* bia
              "%s: out must be [%d, %d, %d, %d]", who, a.N, a.Cout, a.Ho, a.Wo);
   FQ_REQUIRE(bq.null || (((bq.code == kDLInt && bq.bits == 32) || bq.is_f32()) && bq.numel == a.Cout),
              "%s: bias must be int32 codes or float32 [Cout]", who);
-  FQ_REQUIRE((int64_t)a.N * a.Ho * a.Wo < (1LL << 31) && xq.numel < (1LL << 40), "%s: problem too large", who);
+  FQ_REQUIRE((int64_t)a.N * a.Ho * a.Wo < (1LL << 31) && (int64_t)a.Ho * a.Wo < (1LL << 29) && xq.numel < (1LL << 40),
+             "%s: problem too large", who);
   FQ_REQUIRE((reinterpret_cast<uintptr_t>(xq.data) & 15u) == 0 && (reinterpret_cast<uintptr_t>(wq.data) & 15u) == 0,
              "%s: xq and wq must be 16-byte aligned", who);
   a.K = a.KH * a.KW * a.Cg;
@@ -548,9 +615,21 @@ int fq_qconv_igemm(const DLTensor* xq_, const DLTensor* wq_, const DLTensor* bia
   FQ_REQUIRE(tiles < (1LL << 31), "%s: problem too large", who);
   const size_t smem = (size_t)kStagesV2 * (kMmaM * kMmaK + (size_t)bn * kMmaK) + 1024;
   FQ_CUDA(cudaFuncSetAttribute(qconv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // B = the [Cout, K] int8 code matrix, fetched by TMA in boxes of bn rows x 128 bytes of K, 128 B-swizzled
+  EncodeTiledFn encode = encode_tiled_fn();
+  FQ_REQUIRE(encode != nullptr, "%s: the driver does not export cuTensorMapEncodeTiled", who);
+  CUtensorMap tmap_b;
+  const cuuint64_t gdim[2] = {(cuuint64_t)a.K, (cuuint64_t)a.Cout};
+  const cuuint64_t gstride[1] = {(cuuint64_t)a.K};                        // bytes between rows (K % 16 == 0)
+  const cuuint32_t box[2] = {(cuuint32_t)kMmaK, (cuuint32_t)bn};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult er = encode(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<signed char*>(a.wq), gdim, gstride, box,
+                             estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FQ_REQUIRE(er == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed with %d", who, (int)er);
   const int64_t sms = sm_count();
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);            // persistent: one CTA per SM
-  qconv_igemm_kernel<<<grid, kMmaThreadsV2, smem, (cudaStream_t)stream>>>(a);
+  qconv_igemm_kernel<<<grid, kMmaThreadsV2, smem, (cudaStream_t)stream>>>(a, tmap_b);
   FQ_LAUNCH_CHECK("qconv_igemm_kernel");
   return 0;
 }

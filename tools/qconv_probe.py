@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel times of the tensor-core QConv2D route on ResNet-like layers (batch 32):
 pack_input (HBM-bound: 4 B read + 1 B written per element), pack_weight, igemm (tensor-bound), whole layer,
-beside the float-code route and a plain cuDNN fp32 convolution.  CUDA events, 20 repetitions after warm-up."""
+beside the float-code route and a plain cuDNN fp32 convolution.  CUDA events around a graph replay of 20 calls."""
 import os
 import sys
 
@@ -14,13 +14,24 @@ from quantization.mxnet_b200.nn import Conv2D  # noqa: E402
 
 
 def timeit(fn, reps=20):
-    for _ in range(3):
-        fn()
+    """GPU time per call in ms: the calls are captured into a CUDA graph and replayed, so that host time per call
+    (tens of microseconds through Python) does not hide kernels that are shorter than that."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(reps):
-        fn()
+    g.replay()
     b.record()
     b.synchronize()
     return a.elapsed_time(b) / reps
