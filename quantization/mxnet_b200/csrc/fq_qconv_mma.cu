@@ -406,12 +406,15 @@ __device__ __forceinline__ uint32_t pack4_codes(float c0, float c1, float c2, fl
 // the by-the-book code of one element, out of line: taken by a few elements per million (QDiv's guard band)
 __device__ __noinline__ float slow_code(float v, float d) { return quant_code(v, d); }
 
-__global__ void __launch_bounds__(kThreads) qconv_pack_input_kernel(const float* __restrict__ x, const float* __restrict__ range2,
+__global__ void __launch_bounds__(kThreads, 4) qconv_pack_input_kernel(const float* __restrict__ x, const float* __restrict__ range2,
                                                                     signed char* __restrict__ xq, float* __restrict__ scale_out,
                                                                     int N, int C, int H, int W, int ph, int pw) {
   extern __shared__ __align__(16) unsigned char tile[];       // [W][C + 16]
   const int Hp = H + 2 * ph, Wp = W + 2 * pw, Cs = C + 16, c16n = C >> 4;
-  const int n = blockIdx.x / Hp, hp = blockIdx.x % Hp;
+  // rows are taken from the END of the tensor backwards: the range pass that precedes this kernel (max |x|) read x
+  // front to back, so its tail is what still sits in L2
+  const int bid = (int)(gridDim.x - 1 - blockIdx.x);
+  const int n = bid / Hp, hp = bid % Hp;
   const float lo = __ldg(range2), hi = __ldg(range2 + 1);
   const float scale = (hi == -lo) ? __fdiv_rn(hi, 127.0f) : __fdiv_rn(__fsub_rn(hi, lo), 255.0f);
   const QDiv qd = QDiv::make(scale);
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(kThreads) qconv_pack_input_kernel(const float*
     const int w = wp_ - pw;
     dst[i] = (interior && w >= 0 && w < W) ? *reinterpret_cast<const uint4*>(tile + (size_t)w * Cs + j * 16) : padv;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && scale_out != nullptr) scale_out[0] = scale;
+  if (bid == 0 && threadIdx.x == 0 && scale_out != nullptr) scale_out[0] = scale;
 }
 
 // weights: fp32 [Cout, Cg, KH, KW] -> int8 codes [Cout, KH, KW, Cg]

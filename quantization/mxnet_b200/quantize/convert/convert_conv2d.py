@@ -288,6 +288,7 @@ class _MultiWeightPath(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, jobs, *tensors):
         ws, bs, _ = ops.quant_weight_multi(plan)
+        ctx.plan = plan
         ctx.jobs = jobs
         ctx.tensors = tensors
         outs = []
@@ -313,18 +314,29 @@ class _MultiWeightPath(torch.autograd.Function):
             slots.append(len(out))
             out.extend([None, None, None, None])
         # the fold backward of every block in ONE launch (the op-by-op formula is 6-8 launches per block)
-        for pos, jb, (dweight, dgamma, dbias, dbeta) in zip(slots, fold_jobs, _fold_backward(fold_jobs) if fold_jobs else []):
+        results = []
+        if fold_jobs:
+            if all(jb["dwq"] is not None and jb["dwq"].is_cuda for jb in fold_jobs):
+                # the persistent tensors of these jobs are those of ctx.plan (rebuilt whenever one of them moves), so
+                # their descriptors are built once and only the gradients' addresses change from step to step
+                fplan = ctx.plan.__dict__.get("fold_plan")
+                if fplan is None:
+                    fplan = ctx.plan.__dict__["fold_plan"] = ops.FoldBackwardPlan(fold_jobs)
+                results = fplan.run([jb["dwq"] for jb in fold_jobs], [jb["dbq"] for jb in fold_jobs])
+            else:
+                results = _fold_backward(fold_jobs)
+        for pos, jb, (dweight, dgamma, dbias, dbeta) in zip(slots, fold_jobs, results):
             out[pos:pos + 4] = [dweight, dbias if jb["bias"] is not None else None, dgamma, dbeta]
         return tuple(out)
 
 
-_SIG_TENSORS = ("weight", "bias", "gamma", "running_mean")
+_SIG_TENSORS = ("weight", "bias", "gamma", "beta", "running_mean", "running_var")
 
 
 def _weights_signature(blocks):
     """What decides the job list of :func:`prequantize_weights` and whether its cached C job table is still valid:
-    per block the tri-state / switches and the storage addresses of the tensors a job borrows (beta and running_var
-    are created, packed and moved together with gamma / running_mean).  Reads the blocks' own dicts only."""
+    per block the tri-state / switches and the storage address of EVERY tensor a job borrows (a cached table holds raw
+    pointers: it is stale as soon as one of them is replaced).  Reads the blocks' own dicts only."""
     sig = []
     for m in blocks:
         d, p = m.__dict__, m._parameters

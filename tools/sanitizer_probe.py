@@ -50,5 +50,16 @@ best2, _ = ops.kl_search(h, 1024, 2000, 2048, promotion="legacy")               
 ops.kl_threshold(best, torch.ones(2, device="cuda"), 2048)
 ops.quantize_int8_export(w, torch.tensor([-1.0, 1.0], device="cuda"))
 c, s = ops.qconv_quantize(x, ops.minmax(x)); ops.qconv_dequantize(c, s, s)
+# tensor-core QConv2D route: pack (16 channels per thread), TMA + cp.async producers, tcgen05 MMA, TMEM epilogue;
+# ragged M (162 rows), two groups, K tail (144 = 128 + 16), float bias quantised in the epilogue, call plan
+from quantization.mxnet_b200.nn import Conv2D  # noqa: E402
+for cin, cout, k, g_, n_ in ((16, 8, 3, 1, 2), (64, 48, 3, 2, 2), (32, 300, 1, 1, 3)):
+    conv = Conv2D(cout, k, 1, k // 2, in_channels=cin, groups=g_, activation="relu", use_bias=True, quantized=True,
+                  input_dtype="int8", weight_dtype="int8").cuda()
+    with torch.no_grad():
+        conv(dev(r.standard_normal((n_, cin, 9, 9)).astype(np.float32)))
+cm, qp2 = torch.zeros(1, device="cuda"), torch.zeros(4, device="cuda")
+ip = ops.InputPlan(x, 8, False, ops.LO_ZERO, cur_max=cm, qparams=qp2)
+ip.run(x); ip.run(x.clone())
 torch.cuda.synchronize()
 print("sanitizer probe done", int(best[0]), int(best2[0]))
