@@ -215,6 +215,68 @@ __global__ void __launch_bounds__(kThreads, 5) offline_track_tiles_kernel(InputA
   if (t0 < t1) flush(row, m_cur);
 }
 
+// Variant (FQ_TRACK_MODE=1): ONE tile per block like the plain quantiser (no loop, loads issued before anything
+// else) and NO block-wide reduction: each warp reduces its maxima with shuffles, folds them into two shared-memory
+// slots with shared atomics and takes a ticket; the LAST warp of the block to do so owns the block's maxima and
+// touches the global row slot -- and only if the block's maximum beats what the slot already holds (a plain L2 read
+// first: same-address global atomics serialise at ~170 ns each, measured).  No warp ever waits for another one.
+__global__ void __launch_bounds__(kThreads, 5) offline_track_warp_kernel(InputArgs a) {
+  __shared__ float qp[4];
+  __shared__ int64_t row_s;
+  __shared__ unsigned int blk_max[2], ticket;
+  const int64_t nvec = a.n >> 2;
+  const float4* p4 = reinterpret_cast<const float4*>(a.x);
+  const int64_t tile = blockIdx.x;
+  const int64_t v0 = tile * (kTileElems / 4) + threadIdx.x;
+  float4 v[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const int64_t j = v0 + u * kThreads;
+    v[u] = j < nvec ? ld_stream(p4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (threadIdx.x == 0) {
+    compute_qparams(a.fin.input_max[0], a.fin.bits, a.fin.is_signed, a.fin.lo_mode, a.fin.promotion, qp);
+    row_s = (tile * kTileElems) / a.L;               // one 64-bit division per block
+    blk_max[0] = blk_max[1] = 0u;
+    ticket = 0u;
+  }
+  __syncthreads();
+  const float s = qp[1], lo = qp[2], hi = qp[3];
+  const QDiv qd = QDiv::make(qp[0]);
+  const int64_t row = row_s;
+  const int64_t rel64 = (row + 1) * a.L - tile * kTileElems;         // row boundary relative to the tile start
+  const int rel = rel64 > (int64_t)kTileElems ? (int)kTileElems + 8 : (int)rel64;
+  float m_cur = 0.f, m_nxt = 0.f;
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const int64_t j = v0 + u * kThreads;
+    const int ir = 4 * ((int)threadIdx.x + u * kThreads);
+    const float m = absmax4(0.f, v[u]);
+    if (ir < rel) m_cur = fmaxf(m_cur, m);
+    else m_nxt = fmaxf(m_nxt, m);
+    if (j < nvec) {
+      const float4 c = qd.code4(make_float4(clipf(v[u].x, lo, hi), clipf(v[u].y, lo, hi), clipf(v[u].z, lo, hi),
+                                            clipf(v[u].w, lo, hi)));
+      st_stream(reinterpret_cast<float4*>(a.y) + j,
+                make_float4(__fmul_rn(c.x, s), __fmul_rn(c.y, s), __fmul_rn(c.z, s), __fmul_rn(c.w, s)));
+      if (a.code_kind) put_code4(a.codes, a.code_kind, 4 * j, c);
+    }
+  }
+  const bool two = rel < (int)kTileElems;            // block-uniform: this tile holds the start of the next row
+  m_cur = warp_max(m_cur);
+  if (two) m_nxt = warp_max(m_nxt);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&blk_max[0], __float_as_uint(m_cur));
+    if (two) atomicMax(&blk_max[1], __float_as_uint(m_nxt));
+    __threadfence_block();
+    if (atomicAdd(&ticket, 1u) == kThreads / 32 - 1) {           // the last warp: every warp's maxima are in
+      const unsigned int b0 = atomicMax(&blk_max[0], 0u), b1 = atomicMax(&blk_max[1], 0u);
+      if (row < a.rows && b0 > __ldcg(&a.ws->rowmax[row])) atomicMax(&a.ws->rowmax[row], b0);
+      if (two && row + 1 < a.rows && b1 > __ldcg(&a.ws->rowmax[row + 1])) atomicMax(&a.ws->rowmax[row + 1], b1);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Online input path of a latency-bound tensor (<= 1024 tiles): quantiser that finishes the range itself.
 // ---------------------------------------------------------------------------------------------
@@ -634,8 +696,18 @@ int fq_forward_online(const DLTensor* x_, int64_t n_samples, int bits, int is_si
     const int64_t ntiles = (a.n + kTileElems - 1) / kTileElems;
     int64_t tpb = ntiles / ((int64_t)sm_count() * 6 * 4);
     tpb = tpb < 1 ? 1 : (tpb > kTrackTilesMax ? kTrackTilesMax : tpb);
-    offline_track_tiles_kernel<<<(unsigned)((ntiles + tpb - 1) / tpb), kThreads, 0, st>>>(a, (int)tpb);
-    FQ_LAUNCH_CHECK("offline_track_tiles_kernel");
+    static int track_mode = -1;
+    if (track_mode < 0) {
+      const char* env = getenv("FQ_TRACK_MODE");
+      track_mode = env != nullptr ? atoi(env) : 0;
+    }
+    if (track_mode == 1 && ntiles < (1LL << 31)) {
+      offline_track_warp_kernel<<<(unsigned)ntiles, kThreads, 0, st>>>(a);
+      FQ_LAUNCH_CHECK("offline_track_warp_kernel");
+    } else {
+      offline_track_tiles_kernel<<<(unsigned)((ntiles + tpb - 1) / tpb), kThreads, 0, st>>>(a, (int)tpb);
+      FQ_LAUNCH_CHECK("offline_track_tiles_kernel");
+    }
     finish_rows_kernel<<<1, kThreads, 0, st>>>(a.ws, a.rows, a.fin);
     FQ_LAUNCH_CHECK("finish_rows_kernel");
     return 0;
