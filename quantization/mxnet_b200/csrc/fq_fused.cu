@@ -145,82 +145,16 @@ __global__ void __launch_bounds__(kThreads, 6) input_path_kernel(InputArgs a) {
   if (threadIdx.x == 0) a.ws->ticket = 0;
 }
 
-// Offline range + tracking for long rows (L >= one tile, so a tile meets at most two rows).  A block streams
-// `tiles_per_block` CONSECUTIVE tiles like the plain quantiser and keeps the running |x| maximum of the row it is in
-// in registers; only when the row changes (or the block ends) does it reduce over the block and issue ONE atomicMax.
-// The first version took one tile per block and reduced + touched its row slot once per tile: 5.9 TB/s at 2^30
-// elements in its branch-free form; consecutive tiles per block: 6.4 TB/s (0.97 of what a plain device copy
-// reaches on this GPU).  Prefetching the next tile into a second register set (64 registers, 4 blocks per SM)
-// measured the same (profiles/README.md, round 2).
-constexpr int kTrackTilesMax = 8;
-
-__global__ void __launch_bounds__(kThreads, 5) offline_track_tiles_kernel(InputArgs a, int tiles_per_block) {
-  __shared__ float red[32];
-  __shared__ float qp[4];
-  if (threadIdx.x == 0)
-    compute_qparams(a.fin.input_max[0], a.fin.bits, a.fin.is_signed, a.fin.lo_mode, a.fin.promotion, qp);
-  __syncthreads();
-  const float s = qp[1], lo = qp[2], hi = qp[3];
-  const QDiv qd = QDiv::make(qp[0]);
-  const int64_t nvec = a.n >> 2;
-  const int64_t ntiles = (nvec + kTileElems / 4 - 1) / (kTileElems / 4);
-  const float4* p4 = reinterpret_cast<const float4*>(a.x);
-  const int64_t t0 = (int64_t)blockIdx.x * tiles_per_block;
-  const int64_t t1 = min(ntiles, t0 + tiles_per_block);
-  int64_t row = (t0 * kTileElems) / a.L;             // one 64-bit division per block
-  int64_t boundary = (row + 1) * a.L;                // first element of the next row (L % 4 == 0: never inside a float4)
-  float m_cur = 0.f, m_nxt = 0.f;
-  auto flush = [&](int64_t r, float m) {             // block-uniform: depends on tile indices and L only
-    m = block_max(m, red);
-    if (threadIdx.x == 0 && r < a.rows) atomicMax(&a.ws->rowmax[r], __float_as_uint(m));
-  };
-  auto load_tile = [&](int64_t tile, float4* v) {
-    const int64_t v0 = tile * (kTileElems / 4) + threadIdx.x;
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int64_t j = v0 + u * kThreads;
-      v[u] = j < nvec ? ld_stream(p4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  float4 v[kUnroll];
-  for (int64_t tile = t0; tile < t1; ++tile) {
-    load_tile(tile, v);
-    const int64_t v0 = tile * (kTileElems / 4) + threadIdx.x;
-    // the row boundary relative to the tile start, in elements (32-bit: anything beyond the tile is "far")
-    const int64_t rel64 = boundary - tile * kTileElems;
-    const int rel = rel64 > (int64_t)kTileElems ? (int)kTileElems + 8 : (int)rel64;
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int64_t j = v0 + u * kThreads;
-      const int ir = 4 * ((int)threadIdx.x + u * kThreads);        // element offset inside the tile
-      const float m = absmax4(0.f, v[u]);                          // zeros beyond the end of the tensor
-      if (ir < rel) m_cur = fmaxf(m_cur, m);                       // selects, not branches
-      else m_nxt = fmaxf(m_nxt, m);
-      if (j < nvec) {
-        const float4 c = qd.code4(make_float4(clipf(v[u].x, lo, hi), clipf(v[u].y, lo, hi), clipf(v[u].z, lo, hi),
-                                              clipf(v[u].w, lo, hi)));
-        st_stream(reinterpret_cast<float4*>(a.y) + j,
-                  make_float4(__fmul_rn(c.x, s), __fmul_rn(c.y, s), __fmul_rn(c.z, s), __fmul_rn(c.w, s)));
-        if (a.code_kind) put_code4(a.codes, a.code_kind, 4 * j, c);
-      }
-    }
-    if ((tile + 1) * kTileElems >= boundary) {       // the next tile starts in the next row (L >= one tile)
-      flush(row, m_cur);
-      ++row;
-      boundary += a.L;
-      m_cur = m_nxt;
-      m_nxt = 0.f;
-    }
-  }
-  if (t0 < t1) flush(row, m_cur);
-}
-
-// Variant (FQ_TRACK_MODE=1): ONE tile per block like the plain quantiser (no loop, loads issued before anything
-// else) and NO block-wide reduction: each warp reduces its maxima with shuffles, folds them into two shared-memory
-// slots with shared atomics and takes a ticket; the LAST warp of the block to do so owns the block's maxima and
-// touches the global row slot -- and only if the block's maximum beats what the slot already holds (a plain L2 read
-// first: same-address global atomics serialise at ~170 ns each, measured).  No warp ever waits for another one.
-__global__ void __launch_bounds__(kThreads, 5) offline_track_warp_kernel(InputArgs a) {
+// Offline range + tracking for long rows (L >= one tile, so a tile meets at most two rows).  ONE tile per block like
+// the plain quantiser (no loop, loads issued before anything else) and NO block-wide reduction: each warp reduces
+// its maxima with shuffles, folds them into two shared-memory slots with shared atomics and takes a ticket; the LAST
+// warp of the block to do so owns the block's maxima and touches the global row slot -- and only if the block's
+// maximum beats what the slot already holds (a plain L2 read first).  No warp ever waits for another one.
+// History (2^30 elements; profiles/README.md): one tile per block with a block-wide reduce (two __syncthreads) and an
+// atomicMax per tile 5.9 TB/s; up to 8 consecutive tiles per block with the running row maximum in registers and one
+// block reduce per row change 6.4 (prefetching the next tile: the same); one RED.MAX per WARP straight to the row
+// slot 2.1 -- two million same-address global atomics serialise at ~170 ns each; this version 6.76 (6.57 at 2^28).
+__global__ void __launch_bounds__(kThreads, 5) offline_track_tiles_kernel(InputArgs a) {
   __shared__ float qp[4];
   __shared__ int64_t row_s;
   __shared__ unsigned int blk_max[2], ticket;
@@ -692,22 +626,10 @@ int fq_forward_online(const DLTensor* x_, int64_t n_samples, int bits, int is_si
   FQ_TRY(code_kind_of(who, codes, x.numel, &a.code_kind) == 0);
 
   if (!imax.null && a.L >= kTileElems && a.L % 4 == 0) {   // offline range + tracking, long rows: streaming tile kernel
-    // enough blocks to fill the machine first (6 resident per SM), then up to kTrackTilesMax tiles per block
     const int64_t ntiles = (a.n + kTileElems - 1) / kTileElems;
-    int64_t tpb = ntiles / ((int64_t)sm_count() * 6 * 4);
-    tpb = tpb < 1 ? 1 : (tpb > kTrackTilesMax ? kTrackTilesMax : tpb);
-    static int track_mode = -1;
-    if (track_mode < 0) {
-      const char* env = getenv("FQ_TRACK_MODE");
-      track_mode = env != nullptr ? atoi(env) : 0;
-    }
-    if (track_mode == 1 && ntiles < (1LL << 31)) {
-      offline_track_warp_kernel<<<(unsigned)ntiles, kThreads, 0, st>>>(a);
-      FQ_LAUNCH_CHECK("offline_track_warp_kernel");
-    } else {
-      offline_track_tiles_kernel<<<(unsigned)((ntiles + tpb - 1) / tpb), kThreads, 0, st>>>(a, (int)tpb);
-      FQ_LAUNCH_CHECK("offline_track_tiles_kernel");
-    }
+    FQ_REQUIRE(ntiles < (1LL << 31), "%s: tensor too large", who);
+    offline_track_tiles_kernel<<<(unsigned)ntiles, kThreads, 0, st>>>(a);
+    FQ_LAUNCH_CHECK("offline_track_tiles_kernel");
     finish_rows_kernel<<<1, kThreads, 0, st>>>(a.ws, a.rows, a.fin);
     FQ_LAUNCH_CHECK("finish_rows_kernel");
     return 0;
