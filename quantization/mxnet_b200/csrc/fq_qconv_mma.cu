@@ -35,6 +35,7 @@ struct QConvArgs {
   int N, C, Hp, Wp, Cout, KH, KW, Cg, groups, Ho, Wo, sh, sw, relu, a_unsigned;
   int K;                      // KH * KW * Cg
   int BN;                     // padded output channels per group handled by one CTA (16..256, multiple of 16)
+  int tma_a;                  // 1: A arrives by TMA in im2col mode (Cg % 128 == 0), 0: gathered with cp.async
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -183,7 +184,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
-__global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QConvArgs a, const __grid_constant__ CUtensorMap tmap_b) {
+// TMA in im2col mode: 128 consecutive output pixels (walking W, then H, then N inside the map's bounding box, with the
+// convolution stride as traversal stride) x 128 channels of ONE filter tap {kw, kh} -> one 128 B-swizzled A stage
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h,
+                                                   int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], "
+      "{%7, %8};" ::"r"(dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QConvArgs a, const __grid_constant__ CUtensorMap tmap_b,
+                                                                       const __grid_constant__ CUtensorMap tmap_a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024 B alignment is what the 128 B swizzle atom (8 rows x 128 B) needs
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -206,7 +219,8 @@ __global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QCo
 
   if (tid == 0) {
     for (int s = 0; s < kStagesV2; ++s) {
-      mbar_init(&full[s], 3);            // the two gathering warps of the stage + the thread that launches B's TMA
+      // gathered A: the two gathering warps of the stage + the thread that launches B's TMA; A by TMA: that thread only
+      mbar_init(&full[s], a.tma_a ? 1 : 3);
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -221,8 +235,35 @@ __global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QCo
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
-    // =========================== PRODUCERS ===========================
+  if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps && a.tma_a) {
+    // =========================== PRODUCER, both operands by TMA ===========================
+    // Cg % 128 == 0: a k-block is 128 channels of one filter tap, which is exactly what the im2col mode of the tensor
+    // map delivers -- no gather, no address arithmetic, no generic->async proxy fence.  ONE thread keeps the ring full.
+    if (warp == kEpiWarps && lane == 0) {
+      const int cblocks = a.Cg / kMmaK;                  // k-blocks per filter tap
+      int it = 0;
+      for (int lt = 0; lt < my_tiles; ++lt) {
+        const int t = (int)blockIdx.x + lt * (int)gridDim.x;
+        const int mt = t % m_tiles, rest = t / m_tiles;
+        const int nt = rest % n_tiles, g = rest / n_tiles;
+        const int b_row = g * cout_g + nt * a.BN;
+        const int m0 = mt * kMmaM;
+        const int n = m0 / HoWo, r = m0 - n * HoWo;
+        const int oh = r / a.Wo, ow = r - oh * a.Wo;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int stage = it % kStagesV2, use = it / kStagesV2;
+          if (use > 0) mbar_wait(&empty[stage], (uint32_t)(use - 1) & 1u);
+          const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * kMmaK;
+          const int kh = tap / a.KW, kw = tap - kh * a.KW;
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)(kMmaM * kMmaK) + b_stage_bytes);
+          tma_load_im2col_4d(smem_u32(smem_a + stage * kMmaM * kMmaK), &tmap_a, &full[stage], g * a.Cg + c0, ow * a.sw,
+                             oh * a.sh, n, (uint16_t)kw, (uint16_t)kh);
+          tma_load_2d(smem_u32(smem_b) + (uint32_t)stage * b_stage_bytes, &tmap_b, &full[stage], kb * kMmaK, b_row);
+        }
+      }
+    }
+  } else if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
+    // =========================== PRODUCERS, A gathered with cp.async ===========================
     const int pw = warp - kEpiWarps;                     // 0..7
     const int stage = pw >> 1, half = pw & 1;            // this warp: k-blocks it = stage (mod 4), tile rows [64 half, +64)
     const int chunk = lane & 7, rsub = lane >> 3;        // copy i of a k-block: row = 64 half + 4 i + rsub, this chunk
@@ -502,6 +543,30 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeIm2colFn encode_im2col_fn() {
+  static EncodeIm2colFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(p);
+  }
+  return fn;
+}
+// FQ_QCONV_TMA_A=0 (environment, read once) keeps the cp.async gather for A on every shape (A/B measurements)
+static bool tma_a_disabled() {
+  static int off = -1;
+  if (off < 0) {
+    const char* env = getenv("FQ_QCONV_TMA_A");
+    off = (env != nullptr && env[0] == '0') ? 1 : 0;
+  }
+  return off == 1;
+}
+
 extern "C" {
 
 int fq_qconv_pack_input(const DLTensor* x_, const DLTensor* range2_, int pad_h, int pad_w, const DLTensor* xq_,
@@ -630,9 +695,36 @@ int fq_qconv_igemm(const DLTensor* xq_, const DLTensor* wq_, const DLTensor* bia
                              estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FQ_REQUIRE(er == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed with %d", who, (int)er);
+  // A = the padded NHWC codes [N, Hp, Wp, C] read through an im2col tensor map when a k-block is 128 channels of one
+  // filter tap (Cg % 128 == 0).  The padding is materialised, so the bounding box of the window origins starts at 0 and
+  // ends KW-1 / KH-1 short of the far edges; the convolution stride is the traversal stride.
+  CUtensorMap tmap_a = tmap_b;
+  a.tma_a = 0;
+  EncodeIm2colFn encode_im2col = encode_im2col_fn();
+  if (a.Cg % kMmaK == 0 && encode_im2col != nullptr && a.KW <= 128 && a.KH <= 128 && a.sw <= 8 && a.sh <= 8 && !tma_a_disabled()) {
+    const cuuint64_t adim[4] = {(cuuint64_t)a.C, (cuuint64_t)a.Wp, (cuuint64_t)a.Hp, (cuuint64_t)a.N};
+    const cuuint64_t astride[3] = {(cuuint64_t)a.C, (cuuint64_t)a.Wp * a.C, (cuuint64_t)a.Hp * a.Wp * a.C};
+    const int lower[2] = {0, 0};
+    const int upper[2] = {-(a.KW - 1), -(a.KH - 1)};
+    const cuuint32_t astep[4] = {1, (cuuint32_t)a.sw, (cuuint32_t)a.sh, 1};
+    const CUresult ar = encode_im2col(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<signed char*>(a.xq), adim, astride,
+                                      lower, upper, (cuuint32_t)kMmaK, (cuuint32_t)kMmaM, astep, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (ar == CUDA_SUCCESS) {
+      // drivers up to CUDA 13.1 set a descriptor bit for tensors below 128 KB that the im2col mode must not carry
+      // (the same fix-up CUTLASS applies in make_im2col_tma_copy_desc)
+      int drv = 0;
+      if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 && xq.numel < 131072)
+        reinterpret_cast<uint64_t*>(&tmap_a)[1] &= ~(1ull << 21);
+      a.tma_a = 1;
+    } else {
+      tmap_a = tmap_b;                                   // not representable: keep the cp.async gather
+    }
+  }
   const int64_t sms = sm_count();
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);            // persistent: one CTA per SM
-  qconv_igemm_kernel<<<grid, kMmaThreadsV2, smem, (cudaStream_t)stream>>>(a, tmap_b);
+  qconv_igemm_kernel<<<grid, kMmaThreadsV2, smem, (cudaStream_t)stream>>>(a, tmap_b, tmap_a);
   FQ_LAUNCH_CHECK("qconv_igemm_kernel");
   return 0;
 }

@@ -22,10 +22,16 @@ CASES = [
     dict(n=1, c=256, h=6, w=6, co=128, k=3, s=1, p=0, g=1, bias=False, act=None, inp="int8"),      # K = 2304: 18 k-blocks
     dict(n=4, c=32, h=10, w=10, co=16, k=5, s=2, p=2, g=1, bias=True, act="relu", inp=(0.0, 6.0)),  # uint8 codes
     dict(n=2, c=48, h=9, w=11, co=20, k=(3, 1), s=(1, 2), p=(1, 0), g=1, bias=True, act=None, inp=(-2.5, 2.5)),
+    # Cin/groups a multiple of 128: the A operand arrives by TMA in im2col mode (the cases above gather it with cp.async)
+    dict(n=3, c=128, h=14, w=14, co=64, k=3, s=2, p=1, g=1, bias=True, act="relu", inp="int8"),    # stride 2, ragged M
+    dict(n=2, c=256, h=9, w=11, co=96, k=(3, 1), s=(1, 2), p=(1, 0), g=2, bias=True, act=None, inp="int8"),
+    dict(n=5, c=128, h=8, w=8, co=300, k=1, s=1, p=0, g=1, bias=True, act=None, inp=(0.0, 6.0)),   # uint8, two N tiles
+    dict(n=8, c=128, h=28, w=28, co=32, k=3, s=1, p=1, g=1, bias=False, act=None, inp="int8"),     # 49 M tiles, tiles span images
+    dict(n=1, c=384, h=5, w=7, co=48, k=5, s=1, p=2, g=3, bias=True, act="relu", inp="int8"),      # 5x5 taps, three groups
 ]
 
 
-@pytest.mark.parametrize("case", CASES, ids=lambda c: "c%d_co%d_k%s_g%d" % (c["c"], c["co"], c["k"], c["g"]))
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "c%d_co%d_k%s_g%d_n%d" % (c["c"], c["co"], c["k"], c["g"], c["n"]))
 def test_tensor_core_integer_conv_equals_the_float_code_route(case):
     from quantization.mxnet_b200.nn import Conv2D
     torch.manual_seed(case["c"] * 7 + case["co"])
