@@ -430,6 +430,286 @@ __global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QCo
   if (warp == 0) tmem_free_dyn(tmem_base, tmem_cols);
 }
 
+// ---- the same GEMM on SM PAIRS: tcgen05 cta_group::2 --------------------------------------------------------------
+// With one SM per tile every MMA reads 12 KB of operands from shared memory for 128 clocks of math while TMA writes
+// 48 KB per k-block into it: ~190 B/clock against the 128 B/clock a shared memory delivers, so the tensor pipe stalls
+// (53 % busy, measured).  A 2-CTA cluster (the two SMs of a TPC) computes a 256-pixel x BN tile instead: each CTA
+// holds ITS 128 rows of A and HALF of B's rows, the leader CTA's single MMA thread issues M = 256 instructions that
+// read both shared memories, and each tensor core accumulates its own 128 rows in its own tensor memory.  Per SM and
+// k-block that is 32 KB written + 32 KB read -- and 32 KB stages make room for a 6-deep ring.
+//   producer (1 thread per CTA): waits for ITS empty[s], launches its im2col TMA for A and its tiled TMA for half of B;
+//     both complete on the LEADER's full[s] (mbarrier address with the peer bit cleared), for which the leader's
+//     producer has announced the bytes of both CTAs;
+//   MMA (leader only): waits for full[s], issues 4 x tcgen05.mma.cta_group::2, commits with a 2-CTA multicast to
+//     empty[s] -- and to acc_full[buf] after a tile's last k-block -- in BOTH CTAs;
+//   epilogue (4 warps per CTA): as above on the CTA's own 128 rows; the buffer is handed back by arriving on the
+//     LEADER's acc_empty[buf] (8 warp arrivals).
+// Used when both operands come by TMA (Cin/groups % 128 == 0) and BN is a multiple of 32.
+constexpr int kStages2 = 6;
+constexpr int kThreads2 = 32 * (kEpiWarps + 2);
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;        // shared::cluster address of the same word in the pair's even CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on this barrier's twin in the even CTA
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cluster.b64 _, [%0];\n\t}" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void umma2_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          dst),
+      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h,
+                                                    int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], "
+      "[%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+    qconv_igemm2_kernel(const QConvArgs a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* smem_a = smem;                                          // [stages][128 rows][128 B]
+  unsigned char* smem_b = smem + kStages2 * kMmaM * kMmaK;               // [stages][BN / 2 rows][128 B]
+  __shared__ uint64_t full[kStages2], empty[kStages2], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) int bias_s[2][kMaxBN];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cluster_id = (int)blockIdx.x >> 1, n_clusters = (int)gridDim.x >> 1;
+  const int M = a.N * a.Ho * a.Wo, HoWo = a.Ho * a.Wo;
+  const int cout_g = a.Cout / a.groups;
+  const int m_tiles = (M + 2 * kMmaM - 1) / (2 * kMmaM), n_tiles = (cout_g + a.BN - 1) / a.BN;
+  const int tiles = m_tiles * n_tiles * a.groups;
+  const int nkb = (a.K + kMmaK - 1) / kMmaK;
+  const int my_tiles = cluster_id < tiles ? (tiles - 1 - cluster_id) / n_clusters + 1 : 0;
+  const uint32_t b_stage_bytes = (uint32_t)(a.BN >> 1) * kMmaK;          // this CTA's half of B
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * (uint32_t)a.BN) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(&full[s], 1);            // the leader's producer (which announces both CTAs' bytes)
+      mbar_init(&empty[s], 1);           // one multicast commit per use
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 2 * kEpiWarps);   // the epilogue warps of both CTAs (leader's copy is the one in use)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                    // both CTAs' barriers exist before anything is signalled across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == kEpiWarps) {
+    // =========================== PRODUCER (one thread per CTA) ===========================
+    if (lane == 0) {
+      const int cblocks = a.Cg / kMmaK;
+      const uint32_t stage_tx = 2u * ((uint32_t)(kMmaM * kMmaK) + b_stage_bytes);
+      int it = 0;
+#ifdef FQ_QCONV_PROFILE
+      long long prof_wait_empty = 0;
+      const long long prof_t0 = clock64();
+#endif
+      for (int lt = 0; lt < my_tiles; ++lt) {
+        const int t = cluster_id + lt * n_clusters;
+        const int mt = t % m_tiles, rest = t / m_tiles;
+        const int nt = rest % n_tiles, g = rest / n_tiles;
+        const int b_row = g * cout_g + nt * a.BN + rank * (a.BN >> 1);
+        int m0 = mt * 2 * kMmaM + rank * kMmaM;
+        if (m0 >= M) m0 = 0;             // a half tile entirely beyond M: load something valid, the epilogue drops it
+        const int n = m0 / HoWo, r = m0 - n * HoWo;
+        const int oh = r / a.Wo, ow = r - oh * a.Wo;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int stage = it % kStages2, use = it / kStages2;
+#ifdef FQ_QCONV_PROFILE
+          const long long tp0 = clock64();
+#endif
+          if (use > 0) mbar_wait(&empty[stage], (uint32_t)(use - 1) & 1u);
+#ifdef FQ_QCONV_PROFILE
+          prof_wait_empty += clock64() - tp0;
+#endif
+          const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * kMmaK;
+          const int kh = tap / a.KW, kw = tap - kh * a.KW;
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], stage_tx);
+          tma2_load_im2col_4d(smem_u32(smem_a + stage * kMmaM * kMmaK), &tmap_a, &full[stage], g * a.Cg + c0, ow * a.sw,
+                              oh * a.sh, n, (uint16_t)kw, (uint16_t)kh);
+          tma2_load_2d(smem_u32(smem_b) + (uint32_t)stage * b_stage_bytes, &tmap_b, &full[stage], kb * kMmaK, b_row);
+        }
+      }
+#ifdef FQ_QCONV_PROFILE
+      if (blockIdx.x < 2) printf("cta %d producer: total %lld, waiting for empty %lld, k-blocks %d\n", (int)blockIdx.x, clock64() - prof_t0, prof_wait_empty, it);
+#endif
+    }
+  } else if (warp == kEpiWarps + 1) {
+    // =========================== MMA ISSUER (leader CTA only) ===========================
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = (2u << 4) | ((a.a_unsigned ? 0u : 1u) << 7) | (1u << 10) | ((uint32_t)(a.BN >> 3) << 17) |
+                             ((uint32_t)((2 * kMmaM) >> 4) << 24);
+      int it = 0;
+#ifdef FQ_QCONV_PROFILE
+      long long prof_full = 0, prof_acc = 0;
+      const long long prof_t0 = clock64();
+#endif
+      for (int lt = 0; lt < my_tiles; ++lt) {
+        const int buf = lt & 1;
+        if (lt >= 2) {
+#ifdef FQ_QCONV_PROFILE
+          const long long tp0 = clock64();
+#endif
+          mbar_wait(&acc_empty[buf], (uint32_t)((lt >> 1) - 1) & 1u);
+#ifdef FQ_QCONV_PROFILE
+          prof_acc += clock64() - tp0;
+#endif
+          tc_fence_after();
+        }
+        const uint32_t tmem_acc = tmem_base + (uint32_t)buf * (tmem_cols >> 1);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int stage = it % kStages2;
+#ifdef FQ_QCONV_PROFILE
+          const long long tp0 = clock64();
+#endif
+          mbar_wait(&full[stage], (uint32_t)(it / kStages2) & 1u);
+#ifdef FQ_QCONV_PROFILE
+          prof_full += clock64() - tp0;
+#endif
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * kMmaM * kMmaK);
+          const uint32_t sb = smem_u32(smem_b) + (uint32_t)stage * b_stage_bytes;
+#pragma unroll
+          for (int k = 0; k < kMmaK / 32; ++k)
+            umma2_i8(tmem_acc, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, (kb | k) != 0);
+          umma2_commit_both(&empty[stage]);
+          if (kb == nkb - 1) umma2_commit_both(&acc_full[buf]);
+        }
+      }
+#ifdef FQ_QCONV_PROFILE
+      if (blockIdx.x == 0) printf("cta 0 mma: total %lld, waiting for full %lld, for acc_empty %lld, tiles %d\n", clock64() - prof_t0, prof_full, prof_acc, my_tiles);
+#endif
+    }
+  } else {
+    // =========================== EPILOGUE (this CTA's 128 rows) ===========================
+    const float scale = __fmul_rn(__ldg(a.s_in), __ldg(a.s_w));
+    const float b_max = __fmul_rn(scale, 2147483648.0f);
+#ifdef FQ_QCONV_PROFILE
+    long long prof_wait = 0;
+    const long long prof_t0 = clock64();
+#endif
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int t = cluster_id + lt * n_clusters;
+      const int mt = t % m_tiles, rest = t / m_tiles;
+      const int nt = rest % n_tiles, g = rest / n_tiles;
+      const int m0 = mt * 2 * kMmaM + rank * kMmaM, co0 = nt * a.BN;
+      const int buf = lt & 1;
+      for (int c = tid; c < a.BN; c += 32 * kEpiWarps) {
+        const int co = co0 + c;
+        int bq = 0;
+        if (co < cout_g) {
+          if (a.bias_q != nullptr) bq = __ldg(a.bias_q + g * cout_g + co);
+          else if (a.bias_f != nullptr) bq = (int)quant_code(clipf(__ldg(a.bias_f + g * cout_g + co), -b_max, b_max), scale);
+        }
+        bias_s[buf][c] = bq;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      const int m = m0 + warp * 32 + lane;
+      int64_t out_base = 0;
+      if (m < M) {
+        const int n = m / HoWo, r = m - n * HoWo;
+        out_base = ((int64_t)n * a.Cout + (int64_t)g * cout_g + co0) * HoWo + r;
+      }
+#ifdef FQ_QCONV_PROFILE
+      const long long tp0 = clock64();
+#endif
+      mbar_wait(&acc_full[buf], (uint32_t)(lt >> 1) & 1u);
+#ifdef FQ_QCONV_PROFILE
+      prof_wait += clock64() - tp0;
+#endif
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * (tmem_cols >> 1);
+      const int ncols = min(a.BN, cout_g - co0);
+      float* out_row = a.out + out_base;
+      const uint32_t cstride = (uint32_t)HoWo * 4u;
+      for (int c0 = 0; c0 < a.BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld16_nowait(tmem_acc + (uint32_t)c0, v);
+        tmem_ld16_nowait(tmem_acc + (uint32_t)(c0 + 16), v + 16);      // BN % 32 == 0 on this path
+        tmem_ld_wait();
+        if (c0 + 32 >= a.BN) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&acc_empty[buf]);
+        }
+        if (m >= M) continue;
+        char* o = reinterpret_cast<char*>(out_row) + (uint64_t)(uint32_t)c0 * cstride;
+        if (c0 + 32 <= ncols) {
+          int b[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int4 t4 = *reinterpret_cast<const int4*>(&bias_s[buf][c0 + 4 * q]);
+            b[4 * q] = t4.x; b[4 * q + 1] = t4.y; b[4 * q + 2] = t4.z; b[4 * q + 3] = t4.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            int acc = (int)v[j] + b[j];
+            if (a.relu) acc = max(acc, 0);
+            *reinterpret_cast<float*>(o + (uint64_t)(uint32_t)j * cstride) = __fmul_rn((float)acc, scale);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (c0 + j < ncols) {
+              int acc = (int)v[j] + bias_s[buf][c0 + j];
+              if (a.relu) acc = max(acc, 0);
+              *reinterpret_cast<float*>(o + (uint64_t)(uint32_t)j * cstride) = __fmul_rn((float)acc, scale);
+            }
+          }
+        }
+      }
+    }
+#ifdef FQ_QCONV_PROFILE
+    if (blockIdx.x == 0 && tid == 0) printf("cta 0 epilogue warp 0: total %lld, waiting for acc_full %lld\n", clock64() - prof_t0, prof_wait);
+#endif
+  }
+  tc_fence_before();
+  cluster_sync_all();                    // nobody signals the peer or reads tensor memory after this point
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+}
+
 // ---- fp32 NCHW -> zero-padded NHWC 8-bit codes (pad, clip, divide, round: nn/quantized_conv.py:108-109, 54-61) ----
 // HBM-bound: 4 B read + 1 B written per element.  One block per (n, padded row).  A work item is (16 channels, one
 // pixel): its thread issues the 16 scalar loads up front (lanes run along W, so each load instruction of a warp is one
@@ -557,14 +837,16 @@ static EncodeIm2colFn encode_im2col_fn() {
   }
   return fn;
 }
-// FQ_QCONV_TMA_A=0 (environment, read once) keeps the cp.async gather for A on every shape (A/B measurements)
+// FQ_QCONV_TMA_A=0 (environment, read per call) keeps the cp.async gather for A on every shape (A/B measurements, tests)
 static bool tma_a_disabled() {
-  static int off = -1;
-  if (off < 0) {
-    const char* env = getenv("FQ_QCONV_TMA_A");
-    off = (env != nullptr && env[0] == '0') ? 1 : 0;
-  }
-  return off == 1;
+  const char* env = getenv("FQ_QCONV_TMA_A");
+  return env != nullptr && env[0] == '0';
+}
+// FQ_QCONV_2CTA (environment, read per call so that tests can switch it): "0" one SM per tile, "1" SM pairs whenever
+// the shape allows, unset: SM pairs when there are at least two waves of 256-pixel tiles
+static int two_cta_mode() {
+  const char* env = getenv("FQ_QCONV_2CTA");
+  return env == nullptr ? -1 : (env[0] == '0' ? 0 : 1);
 }
 
 extern "C" {
@@ -723,6 +1005,25 @@ int fq_qconv_igemm(const DLTensor* xq_, const DLTensor* wq_, const DLTensor* bia
     }
   }
   const int64_t sms = sm_count();
+  const int64_t tiles2 = ((M + 2 * kMmaM - 1) / (2 * kMmaM)) * ((cout_g + bn - 1) / bn) * groups;
+  const int mode2 = two_cta_mode();
+  // pairs pay a cluster launch and two cluster-wide barriers: worth it from two waves of tiles on (measured)
+  if (a.tma_a && bn % 32 == 0 && (mode2 == 1 || (mode2 < 0 && tiles2 >= 2 * (sms / 2)))) {
+    // SM pairs (cta_group::2): 256 pixels x bn channels per cluster, each CTA fetches half of B's rows
+    CUtensorMap tmap_b2;
+    const cuuint32_t box2[2] = {(cuuint32_t)kMmaK, (cuuint32_t)(bn / 2)};
+    const CUresult er2 = encode(&tmap_b2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<signed char*>(a.wq), gdim, gstride, box2,
+                                estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FQ_REQUIRE(er2 == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed with %d", who, (int)er2);
+    const size_t smem2 = (size_t)kStages2 * (kMmaM * kMmaK + (size_t)(bn / 2) * kMmaK) + 1024;
+    FQ_CUDA(cudaFuncSetAttribute(qconv_igemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    const int64_t pairs = sms / 2;
+    const unsigned grid2 = 2u * (unsigned)(tiles2 < pairs ? tiles2 : pairs);
+    qconv_igemm2_kernel<<<grid2, kThreads2, smem2, (cudaStream_t)stream>>>(a, tmap_b2, tmap_a);
+    FQ_LAUNCH_CHECK("qconv_igemm2_kernel");
+    return 0;
+  }
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);            // persistent: one CTA per SM
   qconv_igemm_kernel<<<grid, kMmaThreadsV2, smem, (cudaStream_t)stream>>>(a, tmap_b, tmap_a);
   FQ_LAUNCH_CHECK("qconv_igemm_kernel");

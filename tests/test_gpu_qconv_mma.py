@@ -31,9 +31,21 @@ CASES = [
 ]
 
 
+# how the tensor-core kernel is organised (csrc/fq_qconv_mma.cu): A gathered with cp.async or fetched by TMA in im2col
+# mode, one SM per tile or SM pairs (tcgen05 cta_group::2).  The library picks by shape; the tests force each.
+MODES = {"auto": {}, "gather": {"FQ_QCONV_TMA_A": "0"}, "tma_1sm": {"FQ_QCONV_2CTA": "0"}, "tma_2sm": {"FQ_QCONV_2CTA": "1"}}
+
+
+@pytest.mark.parametrize("mode", list(MODES))
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "c%d_co%d_k%s_g%d_n%d" % (c["c"], c["co"], c["k"], c["g"], c["n"]))
-def test_tensor_core_integer_conv_equals_the_float_code_route(case):
+def test_tensor_core_integer_conv_equals_the_float_code_route(case, mode, monkeypatch):
     from quantization.mxnet_b200.nn import Conv2D
+    if mode != "auto" and mode != "gather" and (case["c"] // case["g"]) % 128 != 0:
+        pytest.skip("TMA modes need Cin/groups % 128 == 0")
+    for k in ("FQ_QCONV_TMA_A", "FQ_QCONV_2CTA"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in MODES[mode].items():
+        monkeypatch.setenv(k, v)
     torch.manual_seed(case["c"] * 7 + case["co"])
     preset = case["inp"] if isinstance(case["inp"], tuple) else None
     conv = Conv2D(case["co"], case["k"], case["s"], case["p"], in_channels=case["c"], groups=case["g"],

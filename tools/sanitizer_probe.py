@@ -58,6 +58,15 @@ for cin, cout, k, g_, n_ in ((16, 8, 3, 1, 2), (64, 48, 3, 2, 2), (32, 300, 1, 1
                   input_dtype="int8", weight_dtype="int8").cuda()
     with torch.no_grad():
         conv(dev(r.standard_normal((n_, cin, 9, 9)).astype(np.float32)))
+# ... and both operands by TMA (Cin/groups % 128 == 0): one SM per tile, then SM pairs (tcgen05 cta_group::2)
+for two_cta in ("0", "1"):
+    os.environ["FQ_QCONV_2CTA"] = two_cta
+    for cin, cout, k, g_, n_ in ((128, 64, 3, 1, 3), (256, 96, 1, 2, 2)):
+        conv = Conv2D(cout, k, 1, k // 2, in_channels=cin, groups=g_, activation="relu", use_bias=True, quantized=True,
+                      input_dtype="int8", weight_dtype="int8").cuda()
+        with torch.no_grad():
+            conv(dev(r.standard_normal((n_, cin, 9, 9)).astype(np.float32)))
+os.environ.pop("FQ_QCONV_2CTA")
 cm, qp2 = torch.zeros(1, device="cuda"), torch.zeros(4, device="cuda")
 ip = ops.InputPlan(x, 8, False, ops.LO_ZERO, cur_max=cm, qparams=qp2)
 ip.run(x); ip.run(x.clone())
