@@ -52,8 +52,16 @@ def main():
         mix = "  ".join("%s=%d" % (k, counts[k]) for k in KEYS if counts[k])
         print("%-70s %6d | %s" % (short[:70], len(ins), mix))
     print()
-    print("No tensor-core (UTC*MMA / HMMA / IMMA) or TMA (UTMALDG) instruction appears: the path has no dense contraction")
-    print("(north_star) and streams with 128-bit LDG/STG; ACQBULK is the griddepcontrol.wait of the dependent launches.")
+    print("Outside the two qconv_igemm kernels no tensor-core (UTC*MMA / HMMA / IMMA) or TMA (UTMALDG) instruction appears: the")
+    print("north-star path has no dense contraction and streams with 128-bit LDG/STG; ACQBULK is the griddepcontrol.wait of")
+    print("the dependent launches.  QConv2D's integer convolution: UTCIMMA (tcgen05.mma kind::i8; .2CTA = cta_group::2),")
+    print("UTMALDG.2D (weights) and UTMALDG.4D.IM2COL (activations) by TMA, UTCBAR(.2CTA.MULTICAST) = tcgen05.commit, LDTM =")
+    print("tcgen05.ld from tensor memory:")
+    for f, ins in funcs.items():
+        if "qconv_igemm" in f:
+            c = collections.Counter(re.match(r"(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", i).group(1) for i in ins
+                                    if re.match(r"(?:@!?U?P\d+\s+)?(UTMALDG|UTCIMMA|UTCBAR|LDTM|LDGSTS|SYNCS|UCGABAR)", i))
+            print("  %s: %s" % (re.sub(r"\(.*", "", pretty.get(f, f)), "  ".join("%s=%d" % kv for kv in sorted(c.items()))))
     # hot loops: from the first 128-bit load to the last store / shared atomic of the unrolled body
     for want, title in (("hist_multi_kernel<true>", "hist_multi_kernel<CHECK=true>: the unrolled tile body (first 120 instructions after the first 128-bit load)"),
                         ("forward_scalar_kernel<true, fq::NoCode, false>", "forward_scalar_kernel<clip, no codes>: tile body"),
