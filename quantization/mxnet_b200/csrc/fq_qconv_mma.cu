@@ -35,7 +35,8 @@ struct QConvArgs {
   int N, C, Hp, Wp, Cout, KH, KW, Cg, groups, Ho, Wo, sh, sw, relu, a_unsigned;
   int K;                      // KH * KW * Cg
   int BN;                     // padded output channels per group handled by one CTA (16..256, multiple of 16)
-  int tma_a;                  // 1: A arrives by TMA in im2col mode (Cg % 128 == 0), 0: gathered with cp.async
+  int tma_a;                  // 1: A arrives by TMA in im2col mode (Cg % 64 == 0), 0: gathered with cp.async
+  int kb_bytes;               // bytes of K per k-block = swizzle span: 128, or 64 when Cg is an odd multiple of 64 (TMA only)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -118,6 +119,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// the same for rows 64 B apart, 64 B-swizzled: stride byte offset 8 x 64 B = 512, layout type SWIZZLE_64B = 4
+__device__ __forceinline__ uint64_t make_smem_desc64(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(512u >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 at [4,6), a/b format (1 = signed 8 bit,
 // 0 = unsigned) at [7,10) / [10,13), both operands K-major, N >> 3 at [17,23), M >> 4 at [24,29).
 __device__ __forceinline__ uint32_t make_idesc_i8(int n, int a_unsigned) {
@@ -195,6 +200,7 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorM
       : "memory");
 }
 
+template <int KB>      // bytes of K per k-block: 128, or 64 (TMA path with taps of an odd multiple of 64 channels)
 __global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QConvArgs a, const __grid_constant__ CUtensorMap tmap_b,
                                                                        const __grid_constant__ CUtensorMap tmap_a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QCo
   const int cout_g = a.Cout / a.groups;
   const int m_tiles = (M + kMmaM - 1) / kMmaM, n_tiles = (cout_g + a.BN - 1) / a.BN;
   const int tiles = m_tiles * n_tiles * a.groups;
-  const int nkb = (a.K + kMmaK - 1) / kMmaK;
+  const int nkb = (a.K + KB - 1) / KB;
   const int my_tiles = blockIdx.x < tiles ? (tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const uint32_t b_stage_bytes = (uint32_t)a.BN * kMmaK;
   uint32_t tmem_cols = 32;
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QCo
     // Cg % 128 == 0: a k-block is 128 channels of one filter tap, which is exactly what the im2col mode of the tensor
     // map delivers -- no gather, no address arithmetic, no generic->async proxy fence.  ONE thread keeps the ring full.
     if (warp == kEpiWarps && lane == 0) {
-      const int cblocks = a.Cg / kMmaK;                  // k-blocks per filter tap
+      const int cblocks = a.Cg / KB;                     // k-blocks per filter tap
       int it = 0;
       for (int lt = 0; lt < my_tiles; ++lt) {
         const int t = (int)blockIdx.x + lt * (int)gridDim.x;
@@ -253,12 +259,13 @@ __global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QCo
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int stage = it % kStagesV2, use = it / kStagesV2;
           if (use > 0) mbar_wait(&empty[stage], (uint32_t)(use - 1) & 1u);
-          const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * kMmaK;
+          const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * KB;
           const int kh = tap / a.KW, kw = tap - kh * a.KW;
-          mbar_arrive_expect_tx(&full[stage], (uint32_t)(kMmaM * kMmaK) + b_stage_bytes);
+          // stages keep their 128-byte-row strides; with 64-byte k-blocks a stage is simply half full
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)(kMmaM * KB) + (uint32_t)(a.BN * KB));
           tma_load_im2col_4d(smem_u32(smem_a + stage * kMmaM * kMmaK), &tmap_a, &full[stage], g * a.Cg + c0, ow * a.sw,
                              oh * a.sh, n, (uint16_t)kw, (uint16_t)kh);
-          tma_load_2d(smem_u32(smem_b) + (uint32_t)stage * b_stage_bytes, &tmap_b, &full[stage], kb * kMmaK, b_row);
+          tma_load_2d(smem_u32(smem_b) + (uint32_t)stage * b_stage_bytes, &tmap_b, &full[stage], kb * KB, b_row);
         }
       }
     }
@@ -345,8 +352,10 @@ __global__ void __launch_bounds__(kMmaThreadsV2, 1) qconv_igemm_kernel(const QCo
           const uint32_t sa = smem_u32(smem_a + stage * kMmaM * kMmaK);
           const uint32_t sb = smem_u32(smem_b) + (uint32_t)stage * b_stage_bytes;
 #pragma unroll
-          for (int k = 0; k < kMmaK / 32; ++k)   // UMMA K = 32 int8 = 32 B: advance the start address inside the swizzle row
-            umma_i8(tmem_acc, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, (kb | k) != 0);
+          for (int k = 0; k < KB / 32; ++k) {    // UMMA K = 32 int8 = 32 B: advance the start address inside the swizzle row
+            if (KB == kMmaK) umma_i8(tmem_acc, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, (kb | k) != 0);
+            else umma_i8(tmem_acc, make_smem_desc64(sa + k * 32), make_smem_desc64(sb + k * 32), idesc, (kb | k) != 0);
+          }
           umma_commit(&empty[stage]);            // arrives when the MMAs above have finished reading this stage
           if (kb == nkb - 1) umma_commit(&acc_full[buf]);
         }
@@ -964,35 +973,40 @@ int fq_qconv_igemm(const DLTensor* xq_, const DLTensor* wq_, const DLTensor* bia
   const int64_t tiles = ((M + kMmaM - 1) / kMmaM) * ((cout_g + bn - 1) / bn) * groups;
   FQ_REQUIRE(tiles < (1LL << 31), "%s: problem too large", who);
   const size_t smem = (size_t)kStagesV2 * (kMmaM * kMmaK + (size_t)bn * kMmaK) + 1024;
-  FQ_CUDA(cudaFuncSetAttribute(qconv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // B = the [Cout, K] int8 code matrix, fetched by TMA in boxes of bn rows x 128 bytes of K, 128 B-swizzled
+
+  // A by TMA needs a k-block to be channels of ONE filter tap: 128-byte k-blocks when Cg % 128 == 0, 64-byte
+  // k-blocks (64 B swizzle, two MMAs per k-block) when Cg is an odd multiple of 64; otherwise A is gathered
+  EncodeIm2colFn encode_im2col = encode_im2col_fn();
+  const bool tma_a_ok = a.Cg % 64 == 0 && encode_im2col != nullptr && a.KW <= 128 && a.KH <= 128 && a.sw <= 8 && a.sh <= 8 &&
+                        !tma_a_disabled();
+  a.kb_bytes = (tma_a_ok && a.Cg % kMmaK != 0) ? 64 : kMmaK;
+  const CUtensorMapSwizzle swz = a.kb_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  // B = the [Cout, K] int8 code matrix, fetched by TMA in boxes of bn rows x one k-block of K, swizzled like A
   EncodeTiledFn encode = encode_tiled_fn();
   FQ_REQUIRE(encode != nullptr, "%s: the driver does not export cuTensorMapEncodeTiled", who);
   CUtensorMap tmap_b;
   const cuuint64_t gdim[2] = {(cuuint64_t)a.K, (cuuint64_t)a.Cout};
   const cuuint64_t gstride[1] = {(cuuint64_t)a.K};                        // bytes between rows (K % 16 == 0)
-  const cuuint32_t box[2] = {(cuuint32_t)kMmaK, (cuuint32_t)bn};
+  const cuuint32_t box[2] = {(cuuint32_t)a.kb_bytes, (cuuint32_t)bn};
   const cuuint32_t estride[2] = {1, 1};
   const CUresult er = encode(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<signed char*>(a.wq), gdim, gstride, box,
-                             estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                             estride, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FQ_REQUIRE(er == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed with %d", who, (int)er);
   // A = the padded NHWC codes [N, Hp, Wp, C] read through an im2col tensor map when a k-block is 128 channels of one
   // filter tap (Cg % 128 == 0).  The padding is materialised, so the bounding box of the window origins starts at 0 and
   // ends KW-1 / KH-1 short of the far edges; the convolution stride is the traversal stride.
   CUtensorMap tmap_a = tmap_b;
   a.tma_a = 0;
-  EncodeIm2colFn encode_im2col = encode_im2col_fn();
-  if (a.Cg % kMmaK == 0 && encode_im2col != nullptr && a.KW <= 128 && a.KH <= 128 && a.sw <= 8 && a.sh <= 8 && !tma_a_disabled()) {
+  if (tma_a_ok) {
     const cuuint64_t adim[4] = {(cuuint64_t)a.C, (cuuint64_t)a.Wp, (cuuint64_t)a.Hp, (cuuint64_t)a.N};
     const cuuint64_t astride[3] = {(cuuint64_t)a.C, (cuuint64_t)a.Wp * a.C, (cuuint64_t)a.Hp * a.Wp * a.C};
     const int lower[2] = {0, 0};
     const int upper[2] = {-(a.KW - 1), -(a.KH - 1)};
     const cuuint32_t astep[4] = {1, (cuuint32_t)a.sw, (cuuint32_t)a.sh, 1};
     const CUresult ar = encode_im2col(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<signed char*>(a.xq), adim, astride,
-                                      lower, upper, (cuuint32_t)kMmaK, (cuuint32_t)kMmaM, astep, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                      lower, upper, (cuuint32_t)a.kb_bytes, (cuuint32_t)kMmaM, astep, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (ar == CUDA_SUCCESS) {
       // drivers up to CUDA 13.1 set a descriptor bit for tensors below 128 KB that the im2col mode must not carry
       // (the same fix-up CUTLASS applies in make_im2col_tma_copy_desc)
@@ -1001,14 +1015,17 @@ int fq_qconv_igemm(const DLTensor* xq_, const DLTensor* wq_, const DLTensor* bia
         reinterpret_cast<uint64_t*>(&tmap_a)[1] &= ~(1ull << 21);
       a.tma_a = 1;
     } else {
+      FQ_REQUIRE(a.kb_bytes == kMmaK, "%s: cuTensorMapEncodeIm2col failed with %d", who, (int)ar);
       tmap_a = tmap_b;                                   // not representable: keep the cp.async gather
     }
+  } else {
+    FQ_REQUIRE(a.kb_bytes == kMmaK, "%s: internal: 64-byte k-blocks without TMA", who);
   }
   const int64_t sms = sm_count();
   const int64_t tiles2 = ((M + 2 * kMmaM - 1) / (2 * kMmaM)) * ((cout_g + bn - 1) / bn) * groups;
   const int mode2 = two_cta_mode();
   // pairs pay a cluster launch and two cluster-wide barriers: worth it from two waves of tiles on (measured)
-  if (a.tma_a && bn % 32 == 0 && (mode2 == 1 || (mode2 < 0 && tiles2 >= 2 * (sms / 2)))) {
+  if (a.tma_a && a.kb_bytes == kMmaK && bn % 32 == 0 && (mode2 == 1 || (mode2 < 0 && tiles2 >= 2 * (sms / 2)))) {
     // SM pairs (cta_group::2): 256 pixels x bn channels per cluster, each CTA fetches half of B's rows
     CUtensorMap tmap_b2;
     const cuuint32_t box2[2] = {(cuuint32_t)kMmaK, (cuuint32_t)(bn / 2)};
@@ -1025,7 +1042,9 @@ int fq_qconv_igemm(const DLTensor* xq_, const DLTensor* wq_, const DLTensor* bia
     return 0;
   }
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);            // persistent: one CTA per SM
-  qconv_igemm_kernel<<<grid, kMmaThreadsV2, smem, (cudaStream_t)stream>>>(a, tmap_b, tmap_a);
+  auto kern1 = a.kb_bytes == 64 ? qconv_igemm_kernel<64> : qconv_igemm_kernel<kMmaK>;
+  FQ_CUDA(cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern1<<<grid, kMmaThreadsV2, smem, (cudaStream_t)stream>>>(a, tmap_b, tmap_a);
   FQ_LAUNCH_CHECK("qconv_igemm_kernel");
   return 0;
 }

@@ -28,6 +28,10 @@ CASES = [
     dict(n=5, c=128, h=8, w=8, co=300, k=1, s=1, p=0, g=1, bias=True, act=None, inp=(0.0, 6.0)),   # uint8, two N tiles
     dict(n=8, c=128, h=28, w=28, co=32, k=3, s=1, p=1, g=1, bias=False, act=None, inp="int8"),     # 49 M tiles, tiles span images
     dict(n=1, c=384, h=5, w=7, co=48, k=5, s=1, p=2, g=3, bias=True, act="relu", inp="int8"),      # 5x5 taps, three groups
+    # Cin/groups an odd multiple of 64: TMA with 64-byte k-blocks (64 B swizzle, two MMAs per k-block)
+    dict(n=2, c=64, h=12, w=10, co=40, k=3, s=1, p=1, g=1, bias=True, act=None, inp="int8"),
+    dict(n=2, c=192, h=7, w=9, co=64, k=3, s=2, p=1, g=1, bias=True, act="relu", inp=(0.0, 6.0)),
+    dict(n=3, c=128, h=8, w=8, co=272, k=1, s=1, p=0, g=2, bias=False, act=None, inp="int8"),      # Cg = 64, two N tiles per group
 ]
 
 
@@ -40,8 +44,9 @@ MODES = {"auto": {}, "gather": {"FQ_QCONV_TMA_A": "0"}, "tma_1sm": {"FQ_QCONV_2C
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "c%d_co%d_k%s_g%d_n%d" % (c["c"], c["co"], c["k"], c["g"], c["n"]))
 def test_tensor_core_integer_conv_equals_the_float_code_route(case, mode, monkeypatch):
     from quantization.mxnet_b200.nn import Conv2D
-    if mode != "auto" and mode != "gather" and (case["c"] // case["g"]) % 128 != 0:
-        pytest.skip("TMA modes need Cin/groups % 128 == 0")
+    cg = case["c"] // case["g"]
+    if (mode == "tma_1sm" and cg % 64 != 0) or (mode == "tma_2sm" and cg % 128 != 0):
+        pytest.skip("A by TMA needs Cin/groups % 64 == 0, SM pairs % 128 == 0")
     for k in ("FQ_QCONV_TMA_A", "FQ_QCONV_2CTA"):
         monkeypatch.delenv(k, raising=False)
     for k, v in MODES[mode].items():
