@@ -110,3 +110,74 @@ def test_tensor_core_path_declines_what_it_cannot_represent():
     assert conv._tensor_core_ranges(x) is None                              # min > 0: codes start above 0 and exceed 255
     with torch.no_grad():
         assert conv(x).shape == (2, 8, 8, 8)                                # ... and the float-code route still runs
+
+
+def _random_cases(seed, count):
+    rng = np.random.RandomState(seed)
+    cases = []
+    while len(cases) < count:
+        cg = int(rng.choice([16, 32, 48, 64, 128, 192, 256]))
+        g = int(rng.choice([1, 1, 1, 2, 3]))
+        kh, kw = int(rng.choice([1, 2, 3, 5])), int(rng.choice([1, 2, 3, 5]))
+        sh, sw = int(rng.choice([1, 1, 2, 3])), int(rng.choice([1, 1, 2, 3]))
+        ph, pw = int(rng.randint(0, kh)), int(rng.randint(0, kw))
+        h, w = int(rng.randint(kh, 20)), int(rng.randint(kw, 20))
+        if h + 2 * ph < kh or w + 2 * pw < kw:
+            continue
+        n = int(rng.randint(1, 5))
+        co_g = int(rng.choice([8, 16, 24, 40, 64, 136, 264]))
+        if cg * g * h * w * n > 400000:
+            continue
+        cases.append(dict(n=n, c=cg * g, h=h, w=w, co=co_g * g, k=(kh, kw), s=(sh, sw), p=(ph, pw), g=g,
+                          bias=bool(rng.randint(2)), act="relu" if rng.randint(2) else None,
+                          inp="int8" if rng.randint(3) else (0.0, float(rng.uniform(2, 8)))))
+    return cases
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_tensor_core_integer_conv_random_shapes(mode, monkeypatch):
+    """48 seeded random layers (kernel / stride / padding / groups / channel counts on every loader path, output rows
+    shorter than a tile, tiles that wrap rows and images, N tiles that overhang a group) under each kernel
+    organisation: bit-exact against a float64 integer convolution of the oracle's codes."""
+    from quantization.mxnet_b200.nn import Conv2D
+    for k in ("FQ_QCONV_TMA_A", "FQ_QCONV_2CTA"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in MODES[mode].items():
+        monkeypatch.setenv(k, v)
+    ran = 0
+    for idx, case in enumerate(_random_cases(20261017, 48)):
+        cg = case["c"] // case["g"]
+        if (mode == "tma_1sm" and cg % 64 != 0) or (mode == "tma_2sm" and cg % 128 != 0):
+            continue
+        torch.manual_seed(1000 + idx)
+        preset = case["inp"] if isinstance(case["inp"], tuple) else None
+        conv = Conv2D(case["co"], case["k"], case["s"], case["p"], in_channels=case["c"], groups=case["g"],
+                      activation=case["act"], use_bias=case["bias"], quantized=True,
+                      input_dtype="int8" if preset is None else "uint8", weight_dtype="int8").cuda()
+        if case["bias"]:
+            conv.bias.data.uniform_(-0.2, 0.2)
+        x = torch.randn(case["n"], case["c"], case["h"], case["w"], device="cuda")
+        if preset is not None:
+            conv._input_range = preset
+            x = x.abs() * 3
+        assert conv._tensor_core_ranges(x) is not None, case
+        with torch.no_grad():
+            y_tc = conv(x)
+        ph, pw = conv._padding
+        xp = torch.nn.functional.pad(x, (pw, pw, ph, ph)).cpu().numpy()
+        xq, s_in = O.qconv_quantize_auto(xp, "int8") if preset is None else O.qconv_quantize(xp, preset[0], preset[1])
+        wq, s_w = O.qconv_quantize_auto(conv.weight.detach().cpu().numpy(), "int8")
+        acc = torch.nn.functional.conv2d(torch.from_numpy(xq.astype(np.float64)), torch.from_numpy(wq.astype(np.float64)),
+                                         None, conv._strides, 0, 1, case["g"]).numpy().astype(np.int64)
+        if case["bias"]:
+            bs = F32(s_in * s_w)
+            b = conv.bias.detach().cpu().numpy()
+            acc = acc + O.roundf((O.clip(b, -bs * F32(2 ** 31), bs * F32(2 ** 31)) / bs).astype(F32)).astype(np.int64).reshape(1, -1, 1, 1)
+        if case["act"] == "relu":
+            acc = np.maximum(acc, 0)
+        want = O.qconv_dequantize(acc.astype(np.int32), F32(s_in * s_w))
+        got = y_tc.cpu().numpy()
+        assert got.shape == want.shape, (case, got.shape, want.shape)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (mode, idx, case, float(np.abs(got - want).max()))
+        ran += 1
+    assert ran >= 10
