@@ -131,3 +131,45 @@ def test_model_zoo_quantised_block_counts(name, n_conv, n_dense):
     for b in blocks:
         if isinstance(b, nn.Conv2d):
             assert b.name.replace("conv", "batchnorm") + "_gamma" in params, b.name
+
+
+def test_weight_job_cache_signature_follows_every_switch_and_every_job_tensor():
+    """The net-level weight launch is served from a cached job table (convert_conv2d.prequantize_weights); the table
+    is only reused while _weights_signature is unchanged.  Everything that decides the job list or that the table
+    holds a raw pointer of must therefore show in the signature (in-place optimizer updates keep the
+    storage, so they must NOT invalidate; a new bias, a moved tensor or a flipped switch must)."""
+    from quantization.mxnet_b200.quantize.convert import convert_conv2d as C
+    net = small_net()
+    fn = {nn.Conv2d: convert.gen_conv2d_converter(fake_bn=True, quant_type="channel"),
+          nn.Linear: convert.gen_dense_converter(), nn.ReLU: None, nn.BatchNorm2d: convert.bypass_bn}
+    convert.convert_model(net, convert_fn=fn)
+    qparams_init(net)
+    blocks = net.collect_quantized_blocks()
+    conv = blocks[0]
+    s0 = C._weights_signature(blocks)
+    assert C._weights_signature(blocks) == s0                               # stable from call to call
+    with torch.no_grad():
+        conv.weight.mul_(0.5)                                               # optimizer-style update: same storage
+        conv.gamma.add_(1.0)
+    assert C._weights_signature(blocks) == s0
+    for change, undo in (
+            (lambda: setattr(conv, "enable_quantize", False), lambda: setattr(conv, "enable_quantize", True)),
+            (lambda: setattr(conv, "fixed_params", 0), lambda: setattr(conv, "fixed_params", -1)),
+            (lambda: setattr(blocks[-1], "enable_quantize", False), lambda: setattr(blocks[-1], "enable_quantize", True))):
+        change()
+        assert C._weights_signature(blocks) != s0
+        undo()
+        assert C._weights_signature(blocks) == s0
+    for name in ("weight", "bias", "gamma", "beta", "running_mean", "running_var"):
+        p = getattr(conv, name)
+        assert p is not None, name                                          # qparams_init gave the conv a zero bias
+        old = p.data
+        p.data = old.clone()                                                # what net.to() / a re-pack does
+        assert C._weights_signature(blocks) != s0, name
+        p.data = old
+        assert C._weights_signature(blocks) == s0
+    conv.quantize_args = conv.quantize_args._replace(wt_width=4)
+    assert C._weights_signature(blocks) != s0
+    # the job list itself: CPU weights cannot be batched (no CPU path) -> nothing to launch, per-block path decides
+    jobs, owners = C._collect_weight_jobs(blocks)
+    assert jobs == [] and owners == []
