@@ -340,6 +340,87 @@ static int with_code_sink(const char* who, const View& codes, int64_t n, F f) {
   return -1;
 }
 
+// ---- A/B variant (FQ_FORWARD_BULK=1): the same quantiser fed by the bulk-async copy engine ------------------------
+// Persistent blocks; a ring of 3 input tiles is filled with cp.async.bulk (global -> shared, mbarrier complete_tx), the
+// threads read their float4s from shared memory, quantise, write the result tile to one of two output buffers
+// (fence.proxy.async) and one thread sends it off with cp.async.bulk (shared -> global, bulk_group).  One barrier per
+// tile.  Measured against the LDG.128 / STG.128 kernel above (profiles/README.md): kept only as the A/B it is.
+constexpr int kBulkStages = 3;
+__device__ __forceinline__ uint32_t bulk_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(kThreads, 2) forward_scalar_bulk_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                          int64_t ntiles, const float* __restrict__ qp_dev,
+                                                                          float d, float s, float lo, float hi) {
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  float4* in = reinterpret_cast<float4*>(bulk_smem);                                    // [stages][kTileElems / 4]
+  float4* out = in + kBulkStages * (kTileElems / 4);                                    // [2][kTileElems / 4]
+  __shared__ uint64_t full[kBulkStages];
+  constexpr uint32_t kTileBytes = kTileElems * 4;
+  if (qp_dev != nullptr) {
+    d = __ldg(qp_dev + FQ_QP_D);
+    s = __ldg(qp_dev + FQ_QP_S);
+    lo = __ldg(qp_dev + FQ_QP_LO);
+    hi = __ldg(qp_dev + FQ_QP_HI);
+  }
+  const QDiv qd = QDiv::make(d);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBulkStages; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bulk_smem_u32(&full[i])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto load_tile = [&](int64_t tile, int stage) {       // thread 0 only
+    const uint32_t bar = bulk_smem_u32(&full[stage]);
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(kTileBytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     bulk_smem_u32(in + (size_t)stage * (kTileElems / 4))),
+                 "l"(x + tile * kTileElems), "r"(kTileBytes), "r"(bar)
+                 : "memory");
+  };
+  const int64_t first = blockIdx.x, step = gridDim.x;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < kBulkStages; ++i)
+      if (first + i * step < ntiles) load_tile(first + i * step, i);
+  int64_t it = 0;
+  for (int64_t tile = first; tile < ntiles; tile += step, ++it) {
+    const int stage = (int)(it % kBulkStages);
+    const uint32_t parity = (uint32_t)(it / kBulkStages) & 1u;
+    {
+      const uint32_t bar = bulk_smem_u32(&full[stage]);
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}" ::"r"(
+              bar),
+          "r"(parity)
+          : "memory");
+    }
+    const float4* src = in + (size_t)stage * (kTileElems / 4);
+    float4* dst = out + (size_t)(it & 1) * (kTileElems / 4);
+    float4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) v[u] = src[threadIdx.x + u * kThreads];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const float4 c = qd.code4(make_float4(clipf(v[u].x, lo, hi), clipf(v[u].y, lo, hi), clipf(v[u].z, lo, hi),
+                                            clipf(v[u].w, lo, hi)));
+      dst[threadIdx.x + u * kThreads] = make_float4(__fmul_rn(c.x, s), __fmul_rn(c.y, s), __fmul_rn(c.z, s), __fmul_rn(c.w, s));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // the previous tile's store must have finished READING its output buffer before anyone passes the barrier: the
+    // next tile's results go into that buffer
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(y + tile * kTileElems),
+                   "r"(bulk_smem_u32(dst)), "r"(kTileBytes)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      const int64_t nxt = tile + kBulkStages * step;
+      if (nxt < ntiles) load_tile(nxt, stage);
+    }
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 static int forward_scalar_impl(const char* who, const DLTensor* x_, const float* qp_dev, float d, float s, float lo,
                                float hi, bool clip, const DLTensor* y_, const DLTensor* codes_, void* stream,
                                bool reverse = false, bool dependent = false) {
@@ -355,6 +436,23 @@ static int forward_scalar_impl(const char* who, const DLTensor* x_, const float*
   int64_t per_block = 0;
   const int grid = vec ? tile_grid(n, 1 << 30) : ew_grid(n);      // one tile per block
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    static int bulk = -1;
+    if (bulk < 0) {
+      const char* env = getenv("FQ_FORWARD_BULK");
+      bulk = (env != nullptr && env[0] == '1') ? 1 : 0;
+    }
+    if (bulk == 1 && clip && !dependent && !reverse && codes.null && vec && n % kTileElems == 0) {
+      const size_t smem = (size_t)(kBulkStages + 2) * kTileElems * 4;
+      FQ_CUDA(cudaFuncSetAttribute(forward_scalar_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int64_t ntiles = n / kTileElems;
+      const int64_t cap = (int64_t)sm_count() * 2;
+      forward_scalar_bulk_kernel<<<(unsigned)(ntiles < cap ? ntiles : cap), kThreads, smem, st>>>(
+          x.as<const float>(), y.as<float>(), ntiles, qp_dev, d, s, lo, hi);
+      FQ_LAUNCH_CHECK("forward_scalar_bulk_kernel");
+      return 0;
+    }
+  }
   return with_code_sink(who, codes, n, [&](auto sink) -> int {
     using Code = decltype(sink);
     if (clip && dependent) {
