@@ -35,6 +35,35 @@ def _f32(x, name="x"):
     return x.contiguous()
 
 
+def _act(x, name="x"):
+    """An activation as the kernels may read it: float32 and dense.  A ``channels_last`` tensor is dense memory in
+    N, H, W, C order; for everything that is elementwise, or a reduction over whole samples, or over the whole tensor
+    (quantisers, per-sample / global ranges, histograms) the order inside a sample does not matter, so its memory is
+    handed over as it lies -- as the contiguous NHWC view -- instead of through an NCHW copy (two extra passes)."""
+    if x.dtype != torch.float32:
+        raise _ffi.FQError("%s must be float32, got %s" % (name, x.dtype))
+    if x.is_contiguous():
+        return x
+    if x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last):
+        return x.permute(0, 2, 3, 1)
+    return x.contiguous()
+
+
+def _ew(x, out, codes_dtype=None):
+    """(input as the kernel reads it, output to return, output as the kernel writes it) for an elementwise kernel: a
+    channels_last activation is read and written in place of its memory order (the result is channels_last too);
+    with a codes output, or any other non-contiguous layout, the input is copied to NCHW first as before."""
+    xa = _act(x)
+    aliased = xa is not x and xa.data_ptr() == x.data_ptr()
+    if aliased and codes_dtype is None and (out is None or out.is_contiguous(memory_format=torch.channels_last)):
+        out = torch.empty_like(x) if out is None else out           # preserve_format: channels_last like x
+        return xa, out, out.permute(0, 2, 3, 1)
+    if aliased:
+        xa = x.contiguous()
+    out = torch.empty_like(xa) if out is None else out
+    return xa, out, out
+
+
 def _lib():
     return _ffi.load()
 
@@ -51,7 +80,7 @@ def absmax_rows(x, rows, out=None):
 
 def minmax(x, out=None):
     """{min, max} of x.  nn/quantized_conv.py:68-69; distribution_calibrate.py:34-35."""
-    x = _f32(x)
+    x = _act(x)
     out = torch.empty(2, dtype=torch.float32, device=x.device) if out is None else out
     a, o = dl(x), dl(out)
     check_call(_lib().fq_minmax(a.ptr, o.ptr, workspace(x.device), current_stream()))
@@ -70,7 +99,7 @@ def mean_kahan(v, out=None):
 
 def input_range(x, n_samples=None, cur_max=None, per_sample=None):
     """current_input_max = mean_n max_chw |x| in one launch.  convert_conv2d.py:56."""
-    x = _f32(x)
+    x = _act(x)
     n_samples = x.shape[0] if n_samples is None else n_samples
     cur_max = torch.empty(1, dtype=torch.float32, device=x.device) if cur_max is None else cur_max
     a, c, p = dl(x), dl(cur_max), dl(per_sample)
@@ -121,20 +150,18 @@ def _codes_like(x, codes_dtype):
 
 def forward_scalar(x, qparams, out=None, codes_dtype=None):
     """y = roundf(clip(x, lo, hi) / d) * s with device-resident {d, s, lo, hi}.  ste_func.py:41."""
-    x = _f32(x)
-    out = torch.empty_like(x) if out is None else out
+    x, out, ov = _ew(x, out, codes_dtype)
     codes = _codes_like(x, codes_dtype)
-    a, q, o, c = dl(x), dl(qparams), dl(out), dl(codes)
+    a, q, o, c = dl(x), dl(qparams), dl(ov), dl(codes)
     check_call(_lib().fq_forward_scalar(a.ptr, q.ptr, o.ptr, ptr(c), current_stream()))
     return (out, codes) if codes_dtype is not None else out
 
 
 def forward_scalar_host(x, d, s, lo=0.0, hi=0.0, clip=True, out=None, codes_dtype=None):
     """Same with host scalars; clip=False is ste_func.py:39."""
-    x = _f32(x)
-    out = torch.empty_like(x) if out is None else out
+    x, out, ov = _ew(x, out, codes_dtype)
     codes = _codes_like(x, codes_dtype)
-    a, o, c = dl(x), dl(out), dl(codes)
+    a, o, c = dl(x), dl(ov), dl(codes)
     check_call(_lib().fq_forward_scalar_host(a.ptr, d, s, lo, hi, int(bool(clip)), o.ptr, ptr(c), current_stream()))
     return (out, codes) if codes_dtype is not None else out
 
@@ -157,15 +184,16 @@ def forward_online(x, bits=8, signed=False, lo_mode=LO_ZERO, input_max=None, qua
 
     Returns (y, cur_max, qparams[, codes]); y is None when ``quantize`` is False (range tracking only).
     """
-    x = _f32(x)
+    y = yv = None
+    if quantize:
+        x, y, yv = _ew(x, out, codes_dtype)
+    else:
+        x = _act(x)
     n_samples = x.shape[0] if n_samples is None else n_samples
     cur_max = torch.empty(1, dtype=torch.float32, device=x.device) if cur_max is None else cur_max
     qparams = torch.empty(4, dtype=torch.float32, device=x.device) if qparams is None else qparams
-    y = None
-    if quantize:
-        y = torch.empty_like(x) if out is None else out
     codes = _codes_like(x, codes_dtype) if quantize else None
-    a, im, yo, c, cm, q, ps = dl(x), dl(input_max), dl(y), dl(codes), dl(cur_max), dl(qparams), dl(per_sample)
+    a, im, yo, c, cm, q, ps = dl(x), dl(input_max), dl(yv), dl(codes), dl(cur_max), dl(qparams), dl(per_sample)
     check_call(_lib().fq_forward_online(a.ptr, n_samples, bits, int(bool(signed)), lo_mode, _promo(promotion),
                                         ptr(im), ptr(yo), ptr(c), cm.ptr, q.ptr, ptr(ps), workspace(x.device),
                                         current_stream()))
@@ -215,11 +243,17 @@ class InputPlan:
     def run(self, x, out=None):
         """x: float32 CUDA tensor of the plan's shape (checked by the caller through ``shape``).  Returns y (None
         for a range-only plan)."""
+        # elementwise with whole samples as rows: any dense layout that keeps the samples outermost is read and
+        # written as it lies (a channels_last activation gives a channels_last result); anything else is copied
         if not x.is_contiguous():
-            x = x.contiguous()
+            if not (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)) or (
+                    out is not None and out.stride() != x.stride()):
+                x = x.contiguous()
         y = None
         if self.quantize:
             y = torch.empty_like(x) if out is None else out
+            if y.stride() != x.stride():
+                raise _ffi.FQError("InputPlan.run: out must have the memory layout of x")
         dev = self.dev_index
         raw = _ffi._raw_stream(dev)
         if self._run(self.handle, x.data_ptr(), 0 if y is None else y.data_ptr(), _ffi.workspace_for(dev, raw), raw):
@@ -524,7 +558,7 @@ def ema_update(state, cur, momentum=0.9, scalar_cur=True, promotion=None):
 def hist_nonzero(x, max_, bins, counts, promotion=None, bad_flag=None):
     """counts[bin] += 1 over the clipped non-zero elements.  distribution_calibrate.py:39-45.
     ``bad_flag`` (int32 [1]) is raised when the reference's asserts (:35-36) would fail on this tensor."""
-    a, m, c, f = dl(_f32(x)), dl(max_), dl(counts), dl(bad_flag)
+    a, m, c, f = dl(_act(x)), dl(max_), dl(counts), dl(bad_flag)
     check_call(_lib().fq_hist_nonzero(a.ptr, m.ptr, bins, _promo(promotion), c.ptr, ptr(f), current_stream()))
     return counts
 
@@ -532,7 +566,7 @@ def hist_nonzero(x, max_, bins, counts, promotion=None, bad_flag=None):
 def hist_nonzero_multi(xs, maxes, max_stride, max_offset, bins, counts, promotion=None, bad_flags=None):
     """Histograms of several layer inputs in one launch; ``counts`` is int64 [len(xs), bins + 1] and the
     frozen max of ``xs[i]`` is ``maxes.view(-1)[i * max_stride + max_offset]``; ``bad_flags``: int32 [len(xs)]."""
-    args = [dl(_f32(x)) for x in xs]
+    args = [dl(_act(x)) for x in xs]
     arr = (_ffi.P * len(args))(*[_ffi._c.pointer(a.t) for a in args])
     m, c, f = dl(maxes), dl(counts), dl(bad_flags)
     check_call(_lib().fq_hist_nonzero_multi(arr, len(args), m.ptr, max_stride, max_offset, bins, _promo(promotion),

@@ -229,8 +229,9 @@ def _prefetch(loader, ctx):
         fetched += 1
         if consumed[slot] is not None:
             consumed[slot].synchronize()        # the step that read this buffer two batches ago has finished
-        if bufs[slot] is None or bufs[slot].shape != X.shape or bufs[slot].dtype != X.dtype:
-            bufs[slot] = torch.empty(X.shape, dtype=X.dtype, device=dev)
+        if bufs[slot] is None or bufs[slot].shape != X.shape or bufs[slot].dtype != X.dtype or \
+                bufs[slot].stride() != X.stride():
+            bufs[slot] = torch.empty_like(X, device=dev)       # keeps the batch's memory format (channels_last)
             copy_stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(copy_stream):
             bufs[slot].copy_(X, non_blocking=True)

@@ -692,3 +692,57 @@ def test_eager_host_caches_follow_weight_updates_flag_switches_and_moves(Q):
     with torch.enable_grad():                               # autograd forwards allocate fresh outputs in between
         net(x).sum().backward()
     check("after an autograd step")
+
+
+def test_channels_last_activations_are_read_as_they_lie(Q):
+    """A channels_last activation is dense memory in N, H, W, C order.  Elementwise quantisers, per-sample / global
+    ranges and histograms do not depend on the order inside a sample, so they take that memory as it is (no NCHW
+    copy) and an elementwise result comes back channels_last: same values as for the contiguous tensor."""
+    ops = Q.ops
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(6, 24, 9, 7, generator=g) * 2).cuda()
+    xc = x.contiguous(memory_format=torch.channels_last)
+    assert not xc.is_contiguous() and torch.equal(x, xc)
+    assert torch.equal(ops.minmax(x), ops.minmax(xc))
+    cur_a, cur_b = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    ps_a, ps_b = torch.zeros(6, device="cuda"), torch.zeros(6, device="cuda")
+    ops.input_range(x, cur_max=cur_a, per_sample=ps_a)
+    ops.input_range(xc, cur_max=cur_b, per_sample=ps_b)
+    assert torch.equal(cur_a, cur_b) and torch.equal(ps_a, ps_b)
+    pos, posc = x.abs(), xc.abs()
+    mx = ops.minmax(pos)[1:2].clone()
+    ca = torch.zeros(2049, dtype=torch.int64, device="cuda")
+    cb = torch.zeros(2049, dtype=torch.int64, device="cuda")
+    ops.hist_nonzero(pos, mx, 2048, ca)
+    ops.hist_nonzero(posc, mx, 2048, cb)
+    assert torch.equal(ca, cb) and int(ca.sum()) > 0
+    for mode_kw in (dict(), dict(input_max=torch.tensor([1.3], device="cuda"))):
+        ya, _, qa = ops.forward_online(x, 8, True, ops.LO_NEG_MAX, **mode_kw)
+        yb, _, qb = ops.forward_online(xc, 8, True, ops.LO_NEG_MAX, **mode_kw)
+        assert yb.is_contiguous(memory_format=torch.channels_last) and not yb.is_contiguous()
+        assert torch.equal(ya, yb) and torch.equal(qa, qb)
+        assert torch.equal(ops.forward_scalar(xc, qa), ops.forward_scalar(x, qa))
+    # with a codes output the layouts of y and codes must agree: the input is copied to NCHW as before
+    yc, codes = ops.forward_scalar(xc, qa, codes_dtype=torch.int8)
+    yd, codes_d = ops.forward_scalar(x, qa, codes_dtype=torch.int8)
+    assert torch.equal(yc, yd) and torch.equal(codes, codes_d)
+    # the block-level call plan
+    cm, qp = torch.zeros(1, device="cuda"), torch.zeros(4, device="cuda")
+    plan = ops.InputPlan(x, 8, True, ops.LO_NEG_MAX, cur_max=cm, qparams=qp)
+    yp = plan.run(xc)
+    assert yp.is_contiguous(memory_format=torch.channels_last) and torch.equal(yp, ops.forward_online(x, 8, True, ops.LO_NEG_MAX)[0])
+    # a converted network in channels_last: calibration histograms equal those of the NCHW network's activations
+    net = _two_conv_net(Q)
+    batches = [torch.rand(4, 3, 16, 16, generator=g) for _ in range(2)]
+    h_a, m_a = Q.dc.collect_feature_maps(net, 2048, [(b, None) for b in batches], torch.device("cuda"))
+    blocks = net.collect_quantized_blocks()
+    first = {}
+    def remember(mod, xin, y):              # (a hook that returns something would replace the block's output)
+        first.setdefault("x", xin[0])
+    hook = blocks[0].register_forward_hook(remember)
+    net_cl = net.to(memory_format=torch.channels_last)
+    h_b, m_b = Q.dc.collect_feature_maps(net_cl, 2048, [(b.contiguous(memory_format=torch.channels_last), None) for b in batches],
+                                         torch.device("cuda"))
+    hook.remove()
+    assert not first["x"].is_contiguous()                    # the hooked input really was channels_last
+    assert np.array_equal(h_a[blocks[0]], h_b[blocks[0]]) and m_a[blocks[0]] == m_b[blocks[0]]   # the network input itself
