@@ -8,11 +8,13 @@ namespace fq {
 
 // ---- code (rounded quotient) sinks -----------------------------------------------------------
 struct NoCode {
+  static constexpr int kBytes = 0;
   __device__ __forceinline__ void put4(int64_t, float4) const {}
   __device__ __forceinline__ void put1(int64_t, float) const {}
 };
 template <class T>
 struct IntCode {
+  static constexpr int kBytes = (int)sizeof(T);
   T* p;
   __device__ __forceinline__ void put1(int64_t i, float c) const { p[i] = (T)(int)c; }
   __device__ __forceinline__ void put4(int64_t i, float4 c) const {
@@ -31,6 +33,7 @@ struct IntCode {
   }
 };
 struct FloatCode {
+  static constexpr int kBytes = 4;
   float* p;
   __device__ __forceinline__ void put1(int64_t i, float c) const { p[i] = c; }
   __device__ __forceinline__ void put4(int64_t i, float4 c) const { st_stream(reinterpret_cast<float4*>(p + i), c); }
@@ -55,6 +58,14 @@ struct ScalarQuant {
     st_stream(reinterpret_cast<float4*>(y + i),
               make_float4(__fmul_rn(c.x, s), __fmul_rn(c.y, s), __fmul_rn(c.z, s), __fmul_rn(c.w, s)));
     code.put4(i, c);
+  }
+  // y only; the codes are returned (8-bit codes leave through a shared-memory stage, see the kernel)
+  __device__ __forceinline__ float4 vec_y(int64_t i, float4 v) const {
+    if (CLIP) v = make_float4(clipf(v.x, lo, hi), clipf(v.y, lo, hi), clipf(v.z, lo, hi), clipf(v.w, lo, hi));
+    const float4 c = q.code4(v);
+    st_stream(reinterpret_cast<float4*>(y + i),
+              make_float4(__fmul_rn(c.x, s), __fmul_rn(c.y, s), __fmul_rn(c.z, s), __fmul_rn(c.w, s)));
+    return c;
   }
   __device__ __forceinline__ void sca(int64_t i, float v) const {
     float c;
@@ -118,8 +129,24 @@ __global__ void __launch_bounds__(kThreads, PDL ? 4 : 6) forward_scalar_kernel(c
         if constexpr (PDL) {
           if (t == blockIdx.x) wait_for_qparams();       // first tile: its loads are already in flight
         }
+        if constexpr (Code::kBytes == 1) {
+          // 8-bit codes: four 4-byte stores per thread would be the slowest stream of the kernel; the tile's 4096
+          // codes are staged in shared memory and leave as one 16-byte streaming store per thread
+          __shared__ __align__(16) uchar4 stage[kThreads * kUnroll];
+          if (t != (int64_t)blockIdx.x) __syncthreads();               // the previous tile's stage has been read
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) op.vec(4 * (v0 + u * kThreads), v[u]);
+          for (int u = 0; u < kUnroll; ++u) {
+            const float4 c = op.vec_y(4 * (v0 + u * kThreads), v[u]);
+            stage[threadIdx.x + u * kThreads] = make_uchar4((unsigned char)(int)c.x, (unsigned char)(int)c.y,
+                                                            (unsigned char)(int)c.z, (unsigned char)(int)c.w);
+          }
+          __syncthreads();
+          const uint4 packed = reinterpret_cast<const uint4*>(stage)[threadIdx.x];
+          __stcs(reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(op.code.p) + tile * kTileElems) + threadIdx.x, packed);
+        } else {
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) op.vec(4 * (v0 + u * kThreads), v[u]);
+        }
       } else {
         if constexpr (PDL) {
           if (t == blockIdx.x) wait_for_qparams();
