@@ -993,8 +993,8 @@ int fq_qconv_igemm(const DLTensor* xq_, const DLTensor* wq_, const DLTensor* bia
                              estride, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FQ_REQUIRE(er == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed with %d", who, (int)er);
-  // A = the padded NHWC codes [N, Hp, Wp, C] read through an im2col tensor map when a k-block is 128 channels of one
-  // filter tap (Cg % 128 == 0).  The padding is materialised, so the bounding box of the window origins starts at 0 and
+  // A = the padded NHWC codes [N, Hp, Wp, C] read through an im2col tensor map when a k-block is 128 (or 64) channels
+  // of one filter tap.  The padding is materialised, so the bounding box of the window origins starts at 0 and
   // ends KW-1 / KH-1 short of the far edges; the convolution stride is the traversal stride.
   CUtensorMap tmap_a = tmap_b;
   a.tma_a = 0;
