@@ -494,6 +494,64 @@ def sweep_block(dev, peak):
             "stat": "median", "rows": rows}
 
 
+def qconv_block(dev):
+    """nn.Conv2D(quantized=True) on the int8 tensor cores (tcgen05, csrc/fq_qconv_mma.cu), two ResNet-like 3x3 layers
+    at batch 32: GPU time of the implicit-GEMM kernel and of the whole layer (range + pack + GEMM), CUDA events around
+    a graph replay of 20 calls, beside a plain cuDNN fp32 convolution of the same shape.  The roofline of the GEMM
+    kernel is the tensor pipe: nominal dense int8 is 4.5 POP/s; MEASURED_PEAKS' cuBLAS bf16 figure x 2 is what a
+    library GEMM reaches on this part."""
+    import torch
+    from quantization.mxnet_b200 import ops
+    from quantization.mxnet_b200.nn import Conv2D
+
+    def gpu_ms(fn, reps=20):
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):      # other threads (NCCL watchdog) may call CUDA
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) / reps
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    bf16 = float(json.load(open(peaks_path)).get("bf16_tflops", 0.0)) if os.path.exists(peaks_path) else 0.0
+    rows = []
+    saved_benchmark = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True             # the cuDNN comparison gets its autotuned algorithm
+    for n, c, hw, co in ((32, 256, 56, 256), (32, 128, 28, 128)):
+        conv = Conv2D(co, 3, 1, 1, in_channels=c, quantized=True, input_dtype="int8", weight_dtype="int8").to(dev)
+        x = torch.randn(n, c, hw, hw, device=dev)
+        with torch.no_grad():
+            in_rng, unsigned, w_rng = conv._tensor_core_ranges(x)
+            xq, s_in = ops.qconv_pack_input(x, in_rng, 1, 1)
+            wq, s_w = conv._weight_codes(w_rng)
+            t_mm = gpu_ms(lambda: ops.qconv_igemm(xq, wq, None, s_in, s_w, (1, 1), 1))
+            t_layer = gpu_ms(lambda: conv(x))
+            t_cudnn = gpu_ms(lambda: torch.nn.functional.conv2d(x, conv.weight, None, 1, 1))
+        tops = 2.0 * n * hw * hw * co * c * 9 / (t_mm * 1e-3) / 1e12
+        rows.append({"layer": "N%d %dx%dx%d -> %d, 3x3" % (n, c, hw, hw, co), "igemm_us": round(t_mm * 1e3, 1),
+                     "igemm_tops_int8": round(tops, 1), "layer_us": round(t_layer * 1e3, 1),
+                     "cudnn_fp32_conv_us": round(t_cudnn * 1e3, 1),
+                     "roofline": {"bound": "tensor", "achieved": round(tops, 1), "peak": 4500.0, "unit": "TOP/s",
+                                  "frac": round(tops / 4500.0, 3), "peak_kind": "nominal dense int8",
+                                  "frac_of_2x_measured_bf16": round(tops / (2 * bf16), 3) if bf16 else None}})
+        del conv, x, xq, wq
+    torch.backends.cudnn.benchmark = saved_benchmark
+    return {"rows": rows, "timing": "CUDA events around a CUDA-graph replay of 20 calls"}
+
+
 def _fwd_codes(ops, x, qp, y, codes):
     from quantization.mxnet_b200._ffi import check_call, current_stream, dl
     a, q, o, c = dl(x), dl(qp), dl(y), dl(codes)
@@ -756,6 +814,16 @@ def run_b200(args):
         torch.cuda.empty_cache()
         barrier()
 
+    # ---- QConv2D on the tensor cores (rank 0, a few hundred ms) ---------------------
+    if not args.no_qconv:
+        if rank == 0:
+            try:
+                line["qconv"] = qconv_block(dev)
+            except Exception as e:
+                line["qconv"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        torch.cuda.empty_cache()
+        barrier()
+
     # ---- configs 1 / 3 / 4 at this N --------------------------------------------------------------
     graphs_live = False
     if not args.no_configs:
@@ -803,6 +871,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-qconv", action="store_true")
     ap.add_argument("--check-inputs", type=int, default=1,
                     help="1: the histogram kernel also evaluates the reference's per-batch asserts (>= 0, no NaN)")
     ap.add_argument("--deadline", type=int, default=420, help="seconds after which the line is printed as is")
