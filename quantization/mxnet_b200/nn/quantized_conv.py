@@ -54,6 +54,21 @@ def dequantize(x, scale):
     return ops.qconv_dequantize(x, scale, one)
 
 
+_OVERLAP_MIN_ELEMS = 1 << 23        # below this the layer is bound by host time and a second stream only adds to it
+_side_streams = {}
+
+
+def _side_stream(device):
+    """One private side stream per device.  Every use starts with ``side.wait_stream(current)`` and ends with
+    ``current.wait_stream(side)``, so memory the caching allocator hands out on it is never reused while the main
+    stream still reads an earlier tensor from it."""
+    key = torch.device(device).index or 0
+    s = _side_streams.get(key)
+    if s is None:
+        s = _side_streams[key] = torch.cuda.Stream(device=device)
+    return s
+
+
 class Conv2D(nn.Module):
     def __init__(self, channels, kernel_size, strides, padding, in_channels, groups=1,
                  activation=None, use_bias=True, quantized=False,
@@ -75,6 +90,7 @@ class Conv2D(nn.Module):
         self._weight_range = None
         self.use_tensor_cores = True       # set to False to force the framework convolution on float codes
         self.cache_weight_codes = False    # True: keep the int8 weight codes while the weight is unchanged
+        self.overlap_weight_prep = True    # large inputs: weight codes are prepared on a side stream meanwhile
 
         self.weight = nn.Parameter(torch.empty(channels, in_channels // groups, *self._kernel_size))
         nn.init.uniform_(self.weight, -0.07, 0.07)          # mxnet's default Uniform(0.07)
@@ -132,11 +148,26 @@ class Conv2D(nn.Module):
         weight, bias = self.weight, self.bias
         ph, pw = self._padding
         if self._quantized:
+            # The weight side (max |w|, int8 K-major codes) does not depend on the activation: for layers whose input
+            # side is long enough to hide it, it runs on a side stream beside the input's range and packing passes
+            # (fork / join through events, so a CUDA-graph capture records two parallel branches).
+            side = None
+            if (self.overlap_weight_prep and inputs.is_cuda and inputs.numel() >= _OVERLAP_MIN_ELEMS
+                    and self._weight_dtype == 'int8' and self._weight_range is None and not self.cache_weight_codes
+                    and self.use_tensor_cores and (self._in_channels // self._groups) % 16 == 0
+                    and (self._input_range is not None or self._input_dtype == 'int8')):
+                cur = torch.cuda.current_stream(inputs.device)
+                side = _side_stream(inputs.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    early = self._weight_codes(None)
             tc = self._tensor_core_ranges(inputs)
+            if side is not None:
+                cur.wait_stream(side)          # join before anything on this stream touches (or outlives) the codes
             if tc is not None:
                 in_rng, unsigned, w_rng = tc
                 xq, in_scale = ops.qconv_pack_input(inputs, in_rng, ph, pw, unsigned=unsigned)
-                wq, w_scale = self._weight_codes(w_rng)
+                wq, w_scale = early if side is not None else self._weight_codes(w_rng)
                 # the float bias goes in as it is: the kernel's epilogue quantises it with b_scale = s_in * s_w,
                 # clipped to +- b_scale * 2^31 (:122-127) -- in_scale only exists on the device
                 return ops.qconv_igemm(xq, wq, None if bias is None else bias.detach(), in_scale, w_scale, self._strides,

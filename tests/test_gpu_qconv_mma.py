@@ -181,3 +181,46 @@ def test_tensor_core_integer_conv_random_shapes(mode, monkeypatch):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (mode, idx, case, float(np.abs(got - want).max()))
         ran += 1
     assert ran >= 10
+
+
+def test_weight_preparation_on_a_side_stream_gives_the_same_layer():
+    """Large inputs: the weight side (max |w|, int8 codes) runs on a side stream beside the input's range and packing
+    passes.  Same bits as the single-stream order, eagerly and when the fork / join is captured in a CUDA graph."""
+    from quantization.mxnet_b200.nn import Conv2D
+    from quantization.mxnet_b200.nn import quantized_conv as QC
+    torch.manual_seed(5)
+    conv = Conv2D(64, 3, 1, 1, in_channels=128, activation="relu", use_bias=True, quantized=True, input_dtype="int8",
+                  weight_dtype="int8").cuda()
+    conv.bias.data.uniform_(-0.2, 0.2)
+    x = torch.randn(8, 128, 96, 96, device="cuda")
+    assert x.numel() >= QC._OVERLAP_MIN_ELEMS
+    with torch.no_grad():
+        conv.overlap_weight_prep = False
+        want = conv(x)
+        conv.overlap_weight_prep = True
+        for _ in range(3):                                   # repeated: the side stream's allocations are recycled
+            got = conv(x)
+            assert torch.equal(got.view(torch.int32), want.view(torch.int32))
+        conv.weight.data.mul_(0.5)                           # new weights are picked up (nothing is cached)
+        conv.overlap_weight_prep = False
+        want2 = conv(x)
+        conv.overlap_weight_prep = True
+        assert torch.equal(conv(x).view(torch.int32), want2.view(torch.int32))
+        assert not torch.equal(want2, want)
+        # captured: two parallel branches in the graph
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                conv(x)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            out = conv(x)
+        x.mul_(1.5)
+        ref = None
+        g.replay()
+        torch.cuda.synchronize()
+        conv.overlap_weight_prep = False
+        ref = conv(x)
+        assert torch.equal(out.view(torch.int32), ref.view(torch.int32))
