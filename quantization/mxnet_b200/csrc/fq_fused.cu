@@ -153,8 +153,10 @@ __global__ void __launch_bounds__(kThreads, 6) input_path_kernel(InputArgs a) {
 // History (2^30 elements; profiles/README.md): one tile per block with a block-wide reduce (two __syncthreads) and an
 // atomicMax per tile 5.9 TB/s; up to 8 consecutive tiles per block with the running row maximum in registers and one
 // block reduce per row change 6.4 (prefetching the next tile: the same); one RED.MAX per WARP straight to the row
-// slot 2.1 -- two million same-address global atomics serialise at ~170 ns each; this version 6.76 (6.57 at 2^28).
-__global__ void __launch_bounds__(kThreads, 5) offline_track_tiles_kernel(InputArgs a) {
+// slot 2.1 -- two million same-address global atomics serialise at ~170 ns each; this version at 5 blocks/SM (48
+// registers) 6.76 (6.57 at 2^28); with the one-row tile path separated and 6 blocks/SM (40 registers, 8 bytes of
+// spill) 6.93 (6.79 at 2^28) -- the plain quantiser's speed.
+__global__ void __launch_bounds__(kThreads, 6) offline_track_tiles_kernel(InputArgs a) {
   __shared__ float qp[4];
   __shared__ int64_t row_s;
   __shared__ unsigned int blk_max[2], ticket;
@@ -180,14 +182,23 @@ __global__ void __launch_bounds__(kThreads, 5) offline_track_tiles_kernel(InputA
   const int64_t row = row_s;
   const int64_t rel64 = (row + 1) * a.L - tile * kTileElems;         // row boundary relative to the tile start
   const int rel = rel64 > (int64_t)kTileElems ? (int)kTileElems + 8 : (int)rel64;
+  const bool two = rel < (int)kTileElems;            // block-uniform: this tile holds the start of the next row
   float m_cur = 0.f, m_nxt = 0.f;
+  if (!two) {                                        // the common case: the whole tile lies in one row
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) m_cur = absmax4(m_cur, v[u]);
+  } else {
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int ir = 4 * ((int)threadIdx.x + u * kThreads);
+      const float m = absmax4(0.f, v[u]);
+      if (ir < rel) m_cur = fmaxf(m_cur, m);           // selects, not branches
+      else m_nxt = fmaxf(m_nxt, m);
+    }
+  }
 #pragma unroll
   for (int u = 0; u < kUnroll; ++u) {
     const int64_t j = v0 + u * kThreads;
-    const int ir = 4 * ((int)threadIdx.x + u * kThreads);
-    const float m = absmax4(0.f, v[u]);
-    if (ir < rel) m_cur = fmaxf(m_cur, m);
-    else m_nxt = fmaxf(m_nxt, m);
     if (j < nvec) {
       const float4 c = qd.code4(make_float4(clipf(v[u].x, lo, hi), clipf(v[u].y, lo, hi), clipf(v[u].z, lo, hi),
                                             clipf(v[u].w, lo, hi)));
@@ -196,7 +207,6 @@ __global__ void __launch_bounds__(kThreads, 5) offline_track_tiles_kernel(InputA
       if (a.code_kind) put_code4(a.codes, a.code_kind, 4 * j, c);
     }
   }
-  const bool two = rel < (int)kTileElems;            // block-uniform: this tile holds the start of the next row
   m_cur = warp_max(m_cur);
   if (two) m_nxt = warp_max(m_nxt);
   if ((threadIdx.x & 31) == 0) {
