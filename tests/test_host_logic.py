@@ -173,3 +173,27 @@ def test_weight_job_cache_signature_follows_every_switch_and_every_job_tensor():
     # the job list itself: CPU weights cannot be batched (no CPU path) -> nothing to launch, per-block path decides
     jobs, owners = C._collect_weight_jobs(blocks)
     assert jobs == [] and owners == []
+
+
+def test_activation_layout_helpers_alias_channels_last_memory_instead_of_copying():
+    """ops._act / ops._ew decide how an activation reaches the kernels (pure host logic, no launch): contiguous tensors
+    as they are, channels_last tensors as the contiguous NHWC view of the SAME memory (elementwise results then are
+    channels_last as well), anything else -- or an elementwise call with a codes output -- through an NCHW copy."""
+    from quantization.mxnet_b200 import ops
+    x = torch.randn(2, 8, 5, 3)
+    assert ops._act(x) is x
+    xc = x.contiguous(memory_format=torch.channels_last)
+    v = ops._act(xc)
+    assert v.is_contiguous() and tuple(v.shape) == (2, 5, 3, 8) and v.data_ptr() == xc.data_ptr()
+    xin, out, ov = ops._ew(xc, None)
+    assert xin.data_ptr() == xc.data_ptr() and out.is_contiguous(memory_format=torch.channels_last)
+    assert tuple(out.shape) == (2, 8, 5, 3) and ov.is_contiguous() and ov.data_ptr() == out.data_ptr()
+    xin, out, ov = ops._ew(xc, None, codes_dtype=torch.int8)            # codes are NCHW: so must x and y be
+    assert xin.is_contiguous() and tuple(xin.shape) == (2, 8, 5, 3) and xin.data_ptr() != xc.data_ptr() and ov is out
+    given = torch.empty(2, 8, 5, 3)                                       # a caller-provided NCHW output forces NCHW
+    xin, out, ov = ops._ew(xc, given)
+    assert out is given and ov is given and xin.is_contiguous() and xin.data_ptr() != xc.data_ptr()
+    sliced = x[:, ::2]                                                    # neither layout: copied, as before
+    assert ops._act(sliced).is_contiguous() and ops._act(sliced).data_ptr() != sliced.data_ptr()
+    with pytest.raises(Exception, match="float32"):
+        ops._act(x.double())
